@@ -1,0 +1,306 @@
+"""Local executor: runs tasks in-process on CPU tensors or on one B200.
+
+Each task's output is partitioned in memory into a :class:`TaskBuffer`;
+consumers read partitions directly (the "shuffle" is a pointer hand-off).
+``parallelism`` bounds concurrently running tasks (procs), honouring
+``Procs(n)`` and ``Exclusive`` pragmas.  With ``device='cuda'`` frames live in
+HBM and partitioning, combining, sorting and compaction use the sm_100a
+kernels; this is the single-GPU execution path.  The multi-GPU SPMD executor
+(:mod:`.spmd`) reuses this class for per-rank task execution.
+
+Failure model matches the reference: a fatal error (user panic, application
+error) puts the task in ``ERR``; anything else — including a missing or
+discarded dependency — marks it ``LOST`` so the evaluator recomputes it.
+
+Capability parity: reference ``exec/local.go:24-265`` (localExecutor.Run/
+Reader/Discard, depReaders, bufferOutput) and ``exec/buffer.go:19-95``
+(taskBuffer).
+"""
+from __future__ import annotations
+
+import threading
+import time
+import traceback
+from typing import Callable, Dict, List, Optional, Sequence
+
+import torch
+
+from .. import context as _context
+from .. import errors, metrics, slicefunc
+from ..frame import Frame, concat
+from ..sliceio import EmptyReader, FrameReader, MultiReader, Reader
+from .combiner import Combiner
+from .eval import Executor
+from .task import Task, TaskState
+
+
+class TaskBuffer:
+    """In-memory output of one task: frames per partition (``taskBuffer``)."""
+
+    def __init__(self, npartition: int):
+        self.parts: List[List[Frame]] = [[] for _ in range(npartition)]
+        self.combined_unique = False
+        self.nbytes = 0
+        self.nrows = 0
+
+    def append(self, partition: int, f: Frame) -> None:
+        if len(f):
+            self.parts[partition].append(f)
+            self.nrows += len(f)
+
+    def reader(self, partition: int) -> Reader:
+        frames = self.parts[partition]
+        if not frames:
+            return EmptyReader()
+        return _BufferReader(frames)
+
+    def rows(self, partition: int) -> int:
+        return sum(len(f) for f in self.parts[partition])
+
+
+class _BufferReader(Reader):
+    """Streams buffered frames; reading after close is a bug (buffer.go:54)."""
+
+    def __init__(self, frames: List[Frame]):
+        self.frames: Optional[List[Frame]] = list(frames)
+        self.i = 0
+        self.cur: Optional[Reader] = None
+
+    def read(self, n=None):
+        if self.frames is None:
+            raise RuntimeError("TaskBuffer reader: read after close")
+        while True:
+            if self.cur is None:
+                if self.i >= len(self.frames):
+                    return None
+                self.cur = FrameReader(self.frames[self.i])
+                self.i += 1
+            f = self.cur.read(n)
+            if f is not None:
+                return f
+            self.cur = None
+
+    def close(self):
+        self.frames = None
+
+
+class _Limiter:
+    """Counting semaphore with multi-unit acquire (procs)."""
+
+    def __init__(self, n: int):
+        self.n = n
+        self.avail = n
+        self.cond = threading.Condition()
+
+    def acquire(self, k: int) -> None:
+        k = min(k, self.n)
+        with self.cond:
+            self.cond.wait_for(lambda: self.avail >= k)
+            self.avail -= k
+
+    def release(self, k: int) -> None:
+        k = min(k, self.n)
+        with self.cond:
+            self.avail += k
+            self.cond.notify_all()
+
+
+def split_by_partition(f: Frame, ids: torch.Tensor, npart: int) -> List[Frame]:
+    """Split rows of ``f`` into ``npart`` frames by destination id, keeping
+    the relative row order inside each partition (stable)."""
+    if f.device.type == "cuda":
+        from ..ops import gpu
+        if gpu.available():
+            return gpu.partition_frame(f, ids, npart)
+    ids = ids.to(torch.int64).cpu() if ids.device.type != "cpu" else ids.to(torch.int64)
+    order = torch.sort(ids, stable=True)[1]
+    counts = torch.bincount(ids, minlength=npart).tolist()
+    g = f.take(order)
+    out, off = [], 0
+    for c in counts:
+        out.append(g.slice(off, off + c))
+        off += c
+    return out
+
+
+class LocalExecutor(Executor):
+    def __init__(self, parallelism: int = 1, device=None):
+        self.parallelism = max(1, int(parallelism))
+        self.device = torch.device(device) if device is not None else None
+        self.limiter = _Limiter(self.parallelism)
+        self.lock = threading.Lock()
+        self.buffers: Dict[int, TaskBuffer] = {}
+        self.session = None
+        self.tracer = None
+
+    def name(self) -> str:
+        return "local"
+
+    def start(self, session):
+        self.session = session
+        self.tracer = getattr(session, "tracer", None)
+        return None
+
+    def max_workers(self) -> int:
+        return max(8, self.parallelism * 4)
+
+    # -- running -------------------------------------------------------------
+    def run(self, task: Task) -> None:
+        procs = task.pragma.procs()
+        if task.pragma.exclusive():
+            procs = self.parallelism
+        self.limiter.acquire(procs)
+        t0 = time.time()
+        if self.tracer is not None:
+            self.tracer.event(self._pid(), task, "B")
+        try:
+            self._run(task)
+        finally:
+            self.limiter.release(procs)
+            if self.tracer is not None:
+                st = task.state()
+                args = {}
+                if st == TaskState.ERR:
+                    args = {"error": str(task.err()), "error_type": "fatal"}
+                elif st == TaskState.LOST:
+                    args = {"error_type": "lost"}
+                args.update({k: v for k, v in task.stats.items()})
+                self.tracer.event(self._pid(), task, "E", **args)
+
+    def _pid(self):
+        return "local"
+
+    def _run(self, task: Task) -> None:
+        try:
+            ins = self.dep_readers(task)
+        except errors.TaskLostError:
+            task.set(TaskState.LOST)
+            return
+        except BaseException as e:
+            if errors.is_fatal(e):
+                task.error(e)
+            else:
+                task.set(TaskState.LOST)
+            return
+        task.set(TaskState.RUNNING)
+        task.scope.reset()
+        ctx = slicefunc.Context(task.scope, task.name.shard, self.device)
+        try:
+            with _context.use(ctx):
+                out = task.do(ins)
+                buf = self.buffer_output(task, out, ctx)
+        except errors.TaskLostError:
+            task.set(TaskState.LOST)
+            return
+        except errors.Error as e:
+            if errors.is_fatal(e):
+                task.error(e)
+            else:
+                task.set(TaskState.LOST)
+            return
+        except BaseException as e:
+            # A panic in user code is an application error: fatal.
+            tb = traceback.format_exc()
+            task.error(errors.fatal("panic while evaluating slice: %s\n%s" % (e, tb), e))
+            return
+        finally:
+            for r in ins:
+                try:
+                    r.close()
+                except Exception:
+                    pass
+        with self.lock:
+            self.buffers[id(task)] = buf
+        task.set(TaskState.OK)
+
+    def dep_readers(self, task: Task) -> List[Reader]:
+        """Readers for every dependency (expanded deps contribute one reader
+        per producer task), failing with TaskLost if any output is gone."""
+        ins: List[Reader] = []
+        for dep in task.deps:
+            readers = []
+            for dt in dep.tasks():
+                if dt.state() != TaskState.OK:
+                    raise errors.TaskLostError("dependency %s is not available" % dt.name)
+                readers.append(self.reader(dt, dep.partition))
+            if dep.expand:
+                ins.extend(readers)
+            else:
+                ins.append(MultiReader(readers))
+        return ins
+
+    def buffer_output(self, task: Task, out: Reader, ctx) -> TaskBuffer:
+        """Drain the task's pipeline, partitioning (and map-side combining)
+        its output (``bufferOutput`` + inline combine)."""
+        npart = task.num_partition
+        buf = TaskBuffer(npart)
+        combiners: Optional[List[Combiner]] = None
+        if task.combiner is not None:
+            combiners = [Combiner(task.type.typ if hasattr(task.type, "typ") else task.type,
+                                  task.combiner, "%s-p%d" % (task.name.op, p), ctx=ctx)
+                         for p in range(npart)]
+        t_read = t_write = 0.0
+        nrec = 0
+        try:
+            while True:
+                t0 = time.perf_counter()
+                f = out.read(None)
+                t1 = time.perf_counter()
+                t_read += t1 - t0
+                if f is None:
+                    break
+                if len(f) == 0:
+                    continue
+                nrec += len(f)
+                if npart > 1:
+                    ids = task.partitioner(f, npart)
+                    parts = split_by_partition(f, ids, npart)
+                else:
+                    parts = [f]
+                for p, g in enumerate(parts):
+                    if len(g) == 0:
+                        continue
+                    if combiners is not None:
+                        combiners[p].combine(g)
+                    else:
+                        buf.append(p, g)
+                t_write += time.perf_counter() - t1
+            if combiners is not None:
+                t1 = time.perf_counter()
+                for p, c in enumerate(combiners):
+                    r = c.reader(self.device)
+                    for g in r:
+                        buf.append(p, g)
+                    r.close()
+                t_write += time.perf_counter() - t1
+        finally:
+            out.close()
+            if combiners is not None:
+                for c in combiners:
+                    c.discard()
+        task.stats = {"inrecords": nrec, "readDuration": int(t_read * 1e6),
+                      "writeDuration": int(t_write * 1e6), "write": buf.nrows}
+        return buf
+
+    # -- output access ---------------------------------------------------------
+    def reader(self, task: Task, partition: int) -> Reader:
+        with self.lock:
+            buf = self.buffers.get(id(task))
+        if buf is None:
+            raise errors.TaskLostError("output of %s is not available" % task.name)
+        return buf.reader(partition)
+
+    def discard(self, task: Task) -> None:
+        if task.combine_key:
+            return  # shared-combiner tasks are not individually discardable
+        with self.lock:
+            self.buffers.pop(id(task), None)
+        if task.state() == TaskState.OK:
+            task.set(TaskState.LOST)
+
+    def stored_bytes(self) -> int:
+        with self.lock:
+            bufs = list(self.buffers.values())
+        return sum(f.nbytes() for b in bufs for part in b.parts for f in part)
+
+    Run, Reader, Discard = run, reader, discard

@@ -1,0 +1,30 @@
+"""Top-n selection helper.
+
+``top_n(values, n)`` returns the indices of the ``n`` largest values (ties
+broken towards lower index), descending.  On device tensors it uses the
+radix-select kernel path via ``torch.topk``; parity with the reference heap
+helper ``exec/topn.go:39-57``.
+"""
+from __future__ import annotations
+
+import heapq
+from typing import List, Sequence
+
+import torch
+
+
+def top_n(values, n: int) -> List[int]:
+    """Indices of the ``n`` largest elements of ``values``."""
+    if n <= 0:
+        return []
+    if isinstance(values, torch.Tensor):
+        k = min(n, values.numel())
+        if k == 0:
+            return []
+        return torch.topk(values, k, sorted=True).indices.tolist()
+    idx = heapq.nlargest(min(n, len(values)), range(len(values)),
+                         key=lambda i: (values[i], -i))
+    return list(idx)
+
+
+topN = top_n

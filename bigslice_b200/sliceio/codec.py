@@ -1,0 +1,329 @@
+"""The frame wire/disk format: checksummed little-endian column blocks.
+
+A stream is a sequence of batches::
+
+    u32 magic 'BSF1' | u64 body_len | body | u32 crc32(magic..body)
+
+    body := u64 nrows | u32 ncols | column*
+    column := u8 tag | u8 dtype | u32 width | u64 payload_len | payload
+      tag 0 tensor  : raw little-endian elements (2-D vec: row-major)
+      tag 1 strings : (nrows+1) int64 offsets | utf-8 bytes
+      tag 2 bytes   : (nrows+1) int64 offsets | bytes
+      tag 3 objects : pickle of a python list
+      tag 4 list    : (nrows+1) int64 offsets | nested column (child values)
+      tag 5 custom  : u16 len | qualified class name | Ops.encode() bytes
+
+Every batch is protected by CRC32 (IEEE); a mismatch surfaces as
+:class:`~bigslice_b200.errors.IntegrityError`.  Tensor payloads are written
+straight from (pinned) host memory, so device frames round-trip with one D2H /
+H2D copy per column and no per-row work.
+
+Capability parity: reference ``sliceio/codec.go:68-235`` (NewEncodingWriter /
+NewDecodingReader, per-batch CRC, custom per-column codecs with session
+state, integrity errors).  The gob wire format itself is intentionally not
+reproduced.
+"""
+from __future__ import annotations
+
+import io
+import pickle
+import struct
+import zlib
+from typing import BinaryIO, List, Optional
+
+import numpy as np
+import torch
+
+from .. import _native, errors, slicetype
+from ..frame import Frame, ListColumn
+from ..frame import columns as C
+from ..frame.codec import Session
+from ..frame.ops import ops_for, ops_for_value
+from ..slicetype import DType, Type
+from .reader import Reader
+
+MAGIC = 0x31465342  # 'BSF1' little endian
+
+_DT_CODES = ["int8", "int16", "int32", "int64", "uint8", "uint16", "uint32",
+             "uint64", "float16", "bfloat16", "float32", "float64", "bool",
+             "string", "bytes", "object"]
+_DT_INDEX = {n: i for i, n in enumerate(_DT_CODES)}
+_NP = {"int8": np.int8, "int16": np.int16, "int32": np.int32, "int64": np.int64,
+       "uint8": np.uint8, "uint16": np.uint16, "uint32": np.uint32,
+       "uint64": np.uint64, "float16": np.float16, "float32": np.float32,
+       "float64": np.float64, "bool": np.bool_}
+
+
+def crc32(data, value: int = 0) -> int:
+    """CRC32-IEEE; native slice-by-8 when built, zlib otherwise."""
+    nat = _native.lib()
+    if nat is not None:
+        return nat.crc32(data, value)
+    return zlib.crc32(data, value) & 0xFFFFFFFF
+
+
+def _tensor_bytes(t: torch.Tensor) -> bytes:
+    t = t.detach()
+    if t.is_cuda:
+        t = t.cpu()
+    t = t.contiguous()
+    if t.dtype == torch.bfloat16:
+        return t.view(torch.int16).numpy().tobytes()
+    return t.numpy().tobytes()
+
+
+def _base(dt: DType) -> DType:
+    return dt.child if dt.kind in ("vec", "list") else dt
+
+
+def _encode_varlen(vals, is_str: bool) -> bytes:
+    enc = []
+    for v in vals:
+        if v is None:
+            enc.append(b"")
+        elif is_str:
+            enc.append(v.encode("utf-8"))
+        else:
+            enc.append(bytes(v))
+    offs = np.zeros(len(enc) + 1, dtype="<i8")
+    if enc:
+        np.cumsum([len(e) for e in enc], out=offs[1:])
+    return offs.tobytes() + b"".join(enc)
+
+
+def _encode_column(col, dt: DType, session: Session) -> bytes:
+    hdr = struct.Struct("<BBIQ")
+    if dt.kind == "list":
+        offs = col.offsets.detach().cpu().to(torch.int64).numpy().astype("<i8").tobytes()
+        child = _encode_column(col.values, dt.child, session)
+        payload = offs + child
+        return hdr.pack(4, _DT_INDEX[_base(dt.child).name] if _base(dt.child).name in _DT_INDEX else 15,
+                        0, len(payload)) + payload
+    if dt.is_tensor:
+        payload = _tensor_bytes(col)
+        return hdr.pack(0, _DT_INDEX[_base(dt).name], dt.width, len(payload)) + payload
+    if dt.kind == "str":
+        payload = _encode_varlen(col, True)
+        return hdr.pack(1, _DT_INDEX["string"], 0, len(payload)) + payload
+    if dt.kind == "bytes":
+        payload = _encode_varlen(col, False)
+        return hdr.pack(2, _DT_INDEX["bytes"], 0, len(payload)) + payload
+    # object column: custom codec if the element class registered one
+    vals = list(col)
+    o = ops_for_value(vals[0]) if vals else None
+    if o is not None and o.encode is not None:
+        cls = type(vals[0])
+        name = ("%s:%s" % (cls.__module__, cls.__qualname__)).encode()
+        try:
+            body = o.encode(session, vals)
+        except Exception as e:
+            raise errors.fatal("sliceio: custom encode failed for %s" % cls.__name__, e)
+        payload = struct.pack("<H", len(name)) + name + body
+        return hdr.pack(5, _DT_INDEX["object"], 0, len(payload)) + payload
+    try:
+        payload = pickle.dumps(vals, protocol=pickle.HIGHEST_PROTOCOL)
+    except Exception as e:  # unencodable values are application errors
+        raise errors.fatal("sliceio: cannot encode object column", e)
+    return hdr.pack(3, _DT_INDEX["object"], 0, len(payload)) + payload
+
+
+def encode_frame(f: Frame, session: Optional[Session] = None) -> bytes:
+    """Encode one frame as one checksummed batch."""
+    session = session or Session()
+    body = [struct.pack("<QI", len(f), f.num_out())]
+    for col, dt in zip(f.cols(), f.typ.cols):
+        body.append(_encode_column(col, dt, session))
+    b = b"".join(body)
+    head = struct.pack("<IQ", MAGIC, len(b))
+    crc = crc32(b, crc32(head))
+    return head + b + struct.pack("<I", crc)
+
+
+class Encoder:
+    """Writes frames to a binary stream (``sliceio.NewEncodingWriter``)."""
+
+    def __init__(self, w: BinaryIO):
+        self.w = w
+        self.session = Session()
+        self.bytes_written = 0
+
+    def write(self, f: Frame) -> int:
+        b = encode_frame(f, self.session)
+        self.w.write(b)
+        self.bytes_written += len(b)
+        return len(b)
+
+    encode = write
+
+
+def _read_exact(r: BinaryIO, n: int) -> bytes:
+    chunks, got = [], 0
+    while got < n:
+        b = r.read(n - got)
+        if not b:
+            break
+        chunks.append(b)
+        got += len(b)
+    return b"".join(chunks)
+
+
+def _decode_varlen(payload: memoryview, n: int, is_str: bool) -> np.ndarray:
+    ob = (n + 1) * 8
+    if len(payload) < ob:
+        raise errors.IntegrityError("sliceio: short string column")
+    offs = np.frombuffer(payload[:ob], dtype="<i8")
+    data = bytes(payload[ob:])
+    out = np.empty(n, dtype=object)
+    if n and (offs[0] != 0 or offs[-1] != len(data) or np.any(np.diff(offs) < 0)):
+        raise errors.IntegrityError("sliceio: corrupt string offsets")
+    for i in range(n):
+        b = data[offs[i]:offs[i + 1]]
+        out[i] = b.decode("utf-8") if is_str else b
+    return out
+
+
+def _decode_column(buf: memoryview, pos: int, n: int, dt: DType, session: Session,
+                   device):
+    hdr = struct.Struct("<BBIQ")
+    if pos + hdr.size > len(buf):
+        raise errors.IntegrityError("sliceio: truncated column header")
+    tag, code, width, plen = hdr.unpack_from(buf, pos)
+    pos += hdr.size
+    if pos + plen > len(buf):
+        raise errors.IntegrityError("sliceio: truncated column payload")
+    payload = buf[pos:pos + plen]
+    pos += plen
+    if tag == 0:
+        name = _DT_CODES[code]
+        rows = n
+        if name == "bfloat16":
+            a = np.frombuffer(payload, dtype="<i2").copy()
+            t = torch.from_numpy(a).view(torch.bfloat16)
+        else:
+            a = np.frombuffer(payload, dtype=np.dtype(_NP[name]).newbyteorder("<")).copy()
+            t = torch.from_numpy(a)
+        if width:
+            t = t.reshape(rows, width)
+        if t.shape[0] != rows:
+            raise errors.IntegrityError("sliceio: column length mismatch")
+        return (t.to(device) if device is not None else t), pos
+    if tag in (1, 2):
+        return _decode_varlen(payload, n, tag == 1), pos
+    if tag == 3:
+        vals = pickle.loads(bytes(payload))
+        a = np.empty(len(vals), dtype=object)
+        for i, v in enumerate(vals):
+            a[i] = v
+        return a, pos
+    if tag == 4:
+        ob = (n + 1) * 8
+        offs = torch.from_numpy(np.frombuffer(payload[:ob], dtype="<i8").copy())
+        total = int(offs[-1]) if n >= 0 and offs.numel() else 0
+        child, _ = _decode_column(payload, ob, total, dt.child, session, device)
+        if device is not None:
+            offs = offs.to(device)
+        return ListColumn(offs, child, dt.child), pos
+    if tag == 5:
+        (ln,) = struct.unpack_from("<H", payload, 0)
+        name = bytes(payload[2:2 + ln]).decode()
+        mod, _, qual = name.partition(":")
+        import importlib
+        obj = importlib.import_module(mod)
+        for part in qual.split("."):
+            obj = getattr(obj, part)
+        o = ops_for(obj)
+        if o is None or o.decode is None:
+            raise errors.fatal("sliceio: no decoder registered for %s" % name)
+        vals = o.decode(session, bytes(payload[2 + ln:]), n)
+        a = np.empty(len(vals), dtype=object)
+        for i, v in enumerate(vals):
+            a[i] = v
+        return a, pos
+    raise errors.IntegrityError("sliceio: unknown column tag %d" % tag)
+
+
+def decode_batch(buf: bytes, typ: Type, session: Optional[Session] = None,
+                 device=None) -> Frame:
+    """Decode the body of one batch (CRC already verified)."""
+    session = session or Session()
+    mv = memoryview(buf)
+    if len(mv) < 12:
+        raise errors.IntegrityError("sliceio: truncated batch")
+    n, ncols = struct.unpack_from("<QI", mv, 0)
+    if ncols != typ.num_out():
+        raise errors.IntegrityError("sliceio: batch has %d columns, want %d" % (ncols, typ.num_out()))
+    pos = 12
+    cols = []
+    for dt in typ.cols:
+        c, pos = _decode_column(mv, pos, n, dt, session, device)
+        if C.col_len(c) != n:
+            raise errors.IntegrityError("sliceio: column length mismatch")
+        cols.append(c)
+    return Frame(cols, typ)
+
+
+class Decoder(Reader):
+    """Reads frames back from a binary stream (``sliceio.NewDecodingReader``).
+
+    Verifies each batch's CRC before decoding; oversize batches relative to the
+    requested ``n`` are buffered and handed out in pieces.
+    """
+
+    def __init__(self, r: BinaryIO, typ, device=None, closer=None):
+        self.r = r
+        self.typ = slicetype.as_type(typ)
+        self.session = Session()
+        self.device = device
+        self._pending: Optional[Frame] = None
+        self._closer = closer
+        self.bytes_read = 0
+
+    def _next(self) -> Optional[Frame]:
+        head = _read_exact(self.r, 12)
+        if not head:
+            return None
+        if len(head) < 12:
+            raise errors.IntegrityError("sliceio: unexpected EOF in batch header")
+        magic, blen = struct.unpack("<IQ", head)
+        if magic != MAGIC:
+            raise errors.IntegrityError("sliceio: bad batch magic %#x" % magic)
+        body = _read_exact(self.r, blen + 4)
+        if len(body) < blen + 4:
+            raise errors.IntegrityError("sliceio: unexpected EOF in batch body")
+        (want,) = struct.unpack_from("<I", body, blen)
+        got = crc32(memoryview(body)[:blen], crc32(head))
+        if got != want:
+            raise errors.IntegrityError(
+                "sliceio: computed checksum %x but expected checksum %x" % (got, want))
+        self.bytes_read += 16 + blen
+        try:
+            return decode_batch(memoryview(body)[:blen], self.typ, self.session, self.device)
+        except errors.Error:
+            raise
+        except Exception as e:
+            raise errors.IntegrityError("sliceio: corrupt batch", e)
+
+    def read(self, n=None):
+        f = self._pending
+        self._pending = None
+        if f is None:
+            f = self._next()
+            if f is None:
+                return None
+        if n is not None and len(f) > n:
+            self._pending = f.slice(n, len(f))
+            f = f.slice(0, n)
+        return f
+
+    def close(self):
+        c, self._closer = self._closer, None
+        if c is not None:
+            c()
+
+
+def NewEncodingWriter(w: BinaryIO) -> Encoder:
+    return Encoder(w)
+
+
+def NewDecodingReader(r: BinaryIO, typ, device=None) -> Decoder:
+    return Decoder(r, typ, device)
