@@ -33,9 +33,10 @@ from .cogroup import Cogroup
 from .reshuffle import Repartition, Reshard, Reshuffle
 from .scan import ScanReader
 from .cache import Cache, CachePartial, ReadCache
-from .func import Func, FuncValue, Invocation, func
+from .func import Func, FuncValue, Invocation
 from .ops import functors as ops
 from . import exec  # noqa: A004 - mirrors the reference package name
+from . import slicetest, sliceio, sortio, frame  # noqa: F401,E402
 from .exec import (Local, LocalDevice, MachineCombiners, MaxLoad, Parallelism, Result,
                    Session, Spmd, TracePath, start, Start)
 

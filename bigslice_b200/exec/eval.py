@@ -186,7 +186,9 @@ class _State:
             # Re-traverse dependencies: lost producers are recomputed too.
             self.enqueue(task)
         else:
-            raise AssertionError("task %s returned in state %s" % (task.name, st))
+            # Restarted by a concurrent evaluation of the same graph since the
+            # waiter fired: wait for (or resubmit) it again.
+            self.enqueue(task)
 
     def idle(self) -> bool:
         return not self.pending

@@ -144,6 +144,9 @@ class LocalExecutor(Executor):
     def max_workers(self) -> int:
         return max(8, self.parallelism * 4)
 
+    def eventer(self):
+        return getattr(self.session, "eventer_", None)
+
     # -- running -------------------------------------------------------------
     def run(self, task: Task) -> None:
         procs = task.pragma.procs()

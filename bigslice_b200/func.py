@@ -186,7 +186,7 @@ def Func(fn: Callable) -> FuncValue:
     return v
 
 
-func = Func
+
 
 
 def func_by_index(i: int) -> FuncValue:

@@ -373,10 +373,24 @@ def ReaderFunc(nshard: int, read: Callable, *pragmas, out=None, state=None,
     if nshard < 1:
         typecheck.panic("readerfunc: shard must be >= 1")
     if out is None:
-        f = slicefunc.Func(read)
-        if f.In is not None and f.In.num_out() > 2:
-            out = list(f.In.cols[2:])
-        else:
+        import inspect
+        import typing
+        try:
+            params = list(inspect.signature(read).parameters.values())
+            hints = typing.get_type_hints(read)
+        except (TypeError, ValueError, NameError):
+            params, hints = [], {}
+        if params and (params[0].name == "ctx" or params[0].annotation is slicefunc.Context):
+            params = params[1:]
+        out = []
+        for p in params[2:]:
+            ann = hints.get(p.name, p.annotation)
+            try:
+                out.append(slicetype.dtype_of(ann))
+            except TypeError:
+                out = []
+                break
+        if not out:
             typecheck.panicf("readerfunc: function %s is not vectorized", _fn_name(read))
     typ = Type([slicetype.dtype_of(t) for t in out])
     if typ.num_out() == 0:
