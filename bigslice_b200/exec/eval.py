@@ -253,13 +253,9 @@ def evaluate(executor: Executor, roots: Sequence[Task], group=None,
                         raise errors.Error("evaluation canceled", errors.Kind.Canceled)
             while True:
                 st = task.state()
-                if st == TaskState.LOST:
-                    task.consecutive_lost += 1
-                    if task.consecutive_lost >= MAX_CONSECUTIVE_LOST:
-                        task.error(errors.TooManyTriesError(
-                            "task %s lost on %d consecutive attempts" % (task.name, task.consecutive_lost)))
-                elif st == TaskState.OK:
-                    task.consecutive_lost = 0
+                if st == TaskState.LOST and task.consecutive_lost >= MAX_CONSECUTIVE_LOST:
+                    task.error(errors.TooManyTriesError(
+                        "task %s lost on %d consecutive attempts" % (task.name, task.consecutive_lost)))
                 if eventer is not None:
                     eventer.event("bigslice:taskComplete", "name", str(task.name),
                                   "state", str(task.state()))

@@ -148,6 +148,10 @@ class Task:
     def set(self, state: TaskState, err: Optional[BaseException] = None) -> None:
         """Set the state (and error for ERR) and notify waiters/subscribers."""
         with self._cond:
+            if state == TaskState.LOST and self._state != TaskState.LOST:
+                self.consecutive_lost += 1  # counted once per loss, not per observer
+            elif state == TaskState.OK:
+                self.consecutive_lost = 0
             self._state = state
             self._err = err if state == TaskState.ERR else None
             subs = list(self._subs)
