@@ -1,5 +1,319 @@
-"""placeholder until the ctypes bindings are written"""
-HASHABLE = ()
-SEGREDUCE_DTYPES = ()
-def available():
-    return False
+"""ctypes bindings for the sm_100a kernels in ``bigslice_b200/_bscuda.so``.
+
+Every wrapper launches on the current torch CUDA stream and takes/returns
+torch tensors; nothing here falls back to PyTorch silently — on a machine with
+a GPU the library must load (``require()`` raises otherwise), so a passing GPU
+test always exercised the hand-written kernels.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import threading
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+
+from ..frame import Frame
+from ..frame import columns as C
+
+_lib = None
+_lock = threading.Lock()
+_load_error: Optional[str] = None
+
+c_void_p, c_int, c_ll, c_ull = ctypes.c_void_p, ctypes.c_int, ctypes.c_longlong, ctypes.c_ulonglong
+
+VTYPE = {torch.int32: 0, torch.int64: 1, torch.float32: 2, torch.float64: 3}
+OPS = {"add": 0, "min": 1, "max": 2}
+HASHABLE = (torch.int8, torch.int16, torch.int32, torch.int64, torch.uint8, torch.float32,
+            torch.float64, torch.uint16, torch.uint32, torch.uint64)
+SEGREDUCE_DTYPES = tuple(VTYPE)
+
+
+def lib_path() -> str:
+    return os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "_bscuda.so")
+
+
+def _load():
+    global _lib, _load_error
+    with _lock:
+        if _lib is not None or _load_error is not None:
+            return _lib
+        path = lib_path()
+        if not os.path.exists(path):
+            _load_error = "%s not built (run python -m bigslice_b200.build)" % path
+            return None
+        try:
+            lib = ctypes.CDLL(path)
+        except OSError as e:
+            _load_error = str(e)
+            return None
+        lib.bs_launches.restype = c_ll
+        lib.bs_sort_scratch_bytes.restype = c_ll
+        lib.bs_compact_scratch_bytes.restype = c_ll
+        lib.bs_crc32_nblocks.restype = c_ll
+        _lib = lib
+        return _lib
+
+
+def available() -> bool:
+    """True when CUDA is usable and the kernel library is loaded."""
+    if not torch.cuda.is_available():
+        return False
+    if _load() is None:
+        raise RuntimeError("bigslice_b200: CUDA device present but kernels missing: %s" % _load_error)
+    return True
+
+
+def require():
+    if not available():
+        raise RuntimeError("bigslice_b200.ops.gpu: no CUDA device / kernel library")
+    return _lib
+
+
+def launches() -> int:
+    """Number of kernels this library has launched in this process."""
+    lib = _load()
+    return int(lib.bs_launches()) if lib is not None else 0
+
+
+def _stream() -> c_void_p:
+    return c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t: Optional[torch.Tensor]) -> c_void_p:
+    return c_void_p(0 if t is None else t.data_ptr())
+
+
+def _chk(rc: int, what: str):
+    if rc != 0:
+        raise RuntimeError("bigslice_b200 kernel %s failed: cuda error %d" % (what, rc))
+
+
+# ---------------------------------------------------------------- hashing
+
+def hash_column(col: torch.Tensor, seed: int = 0, out: Optional[torch.Tensor] = None,
+                xor_into: bool = False) -> torch.Tensor:
+    """murmur3 of every element (int64 tensor of uint32 values)."""
+    lib = require()
+    col = col.contiguous()
+    n = col.numel()
+    if out is None:
+        out = torch.empty(n, dtype=torch.int64, device=col.device)
+    es = col.element_size()
+    signed = col.dtype in (torch.int8, torch.int16)
+    _chk(lib.bs_hash_column(_ptr(col), c_int(es), c_int(1 if signed else 0), c_ll(n),
+                            ctypes.c_uint(seed & 0xFFFFFFFF), _ptr(out),
+                            c_int(1 if xor_into else 0), _stream()), "hash_column")
+    return out
+
+
+# ---------------------------------------------------------------- partition
+
+def partition_perm(ids: Optional[torch.Tensor], keys: Optional[torch.Tensor], n: int,
+                   npart: int) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Permutation grouping rows by destination, and per-destination counts.
+
+    Either explicit ``ids`` (int64) or int64 ``keys`` hashed with the default
+    partitioner inside the kernel.  Row order inside a partition is unspecified
+    (as across any shuffle)."""
+    lib = require()
+    dev = (ids if ids is not None else keys).device
+    counts = torch.zeros(npart, dtype=torch.int64, device=dev)
+    cursors = torch.empty(npart, dtype=torch.int64, device=dev)
+    perm = torch.empty(n, dtype=torch.int64, device=dev)
+    _chk(lib.bs_partition_perm(_ptr(ids), _ptr(keys), c_ll(n), c_int(npart), _ptr(counts),
+                               _ptr(cursors), _ptr(perm), _stream()), "partition_perm")
+    return perm, counts
+
+
+def gather_rows(col: torch.Tensor, idx: torch.Tensor) -> torch.Tensor:
+    """out[i] = col[idx[i]] with the hand-written gather kernel."""
+    lib = require()
+    col = col.contiguous()
+    n = idx.numel()
+    out = torch.empty((n,) + tuple(col.shape[1:]), dtype=col.dtype, device=col.device)
+    row_bytes = col.element_size() * (col.numel() // col.shape[0] if col.shape[0] else 1)
+    _chk(lib.bs_gather_rows(_ptr(col), c_int(row_bytes), _ptr(idx), c_ll(n), _ptr(out), _stream()),
+         "gather_rows")
+    return out
+
+
+def take_frame(f: Frame, idx: torch.Tensor) -> Frame:
+    cols = []
+    for c in f.cols():
+        if isinstance(c, torch.Tensor) and c.is_cuda and c.dtype != torch.bool:
+            cols.append(gather_rows(c, idx))
+        else:
+            cols.append(C.col_take(c, idx))
+    return Frame(cols, f.typ)
+
+
+def partition_frame(f: Frame, ids: torch.Tensor, npart: int) -> List[Frame]:
+    """Split a device frame into ``npart`` frames by destination id."""
+    n = len(f)
+    ids = ids.to(device=f.device, dtype=torch.int64).contiguous()
+    perm, counts = partition_perm(ids, None, n, npart)
+    g = take_frame(f, perm)
+    out, off = [], 0
+    for c in counts.tolist():
+        out.append(g.slice(off, off + c))
+        off += c
+    return out
+
+
+# ---------------------------------------------------------------- hash combine
+
+class HashTable:
+    """HBM open-addressing table used by the combine kernels."""
+
+    def __init__(self, capacity: int, vdtype: torch.dtype, op: str, device):
+        lib = require()
+        cap = 1
+        while cap < max(capacity, 1024):
+            cap <<= 1
+        self.cap, self.vdtype, self.op, self.device = cap, vdtype, op, device
+        self.keys = torch.empty(cap, dtype=torch.int64, device=device)
+        self.vals = torch.empty(cap, dtype=vdtype, device=device)
+        self.status = torch.zeros(4, dtype=torch.int64, device=device)
+        self.reset()
+
+    def reset(self):
+        _chk(_lib.bs_table_init(_ptr(self.keys), _ptr(self.vals), c_ll(self.cap),
+                                c_int(VTYPE[self.vdtype]), c_int(OPS[self.op]), _ptr(self.status),
+                                _stream()), "table_init")
+
+    def combine(self, keys: torch.Tensor, vals: torch.Tensor, force_simple: bool = False):
+        keys, vals = keys.contiguous(), vals.contiguous()
+        _chk(_lib.bs_hash_combine(_ptr(keys), _ptr(vals), c_ll(keys.numel()),
+                                  c_int(VTYPE[self.vdtype]), c_int(OPS[self.op]), _ptr(self.keys),
+                                  _ptr(self.vals), c_ll(self.cap), _ptr(self.status),
+                                  c_int(1 if force_simple else 0), _stream()), "hash_combine")
+
+    def compact(self, max_rows: Optional[int] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+        """Dense (keys, vals) of the occupied slots; syncs once for the count."""
+        cap_out = self.cap + 1 if max_rows is None else max_rows
+        ok = torch.empty(cap_out, dtype=torch.int64, device=self.device)
+        ov = torch.empty(cap_out, dtype=self.vdtype, device=self.device)
+        _chk(_lib.bs_table_compact(_ptr(self.keys), _ptr(self.vals), c_ll(self.cap),
+                                   c_int(VTYPE[self.vdtype]), _ptr(ok), _ptr(ov), _ptr(self.status),
+                                   _stream()), "table_compact")
+        st = self.status.tolist()
+        if st[0]:
+            raise TableFull(st[0])
+        n = st[3]
+        return ok[:n], ov[:n]
+
+    def failed(self) -> int:
+        return int(self.status[0])
+
+
+class TableFull(RuntimeError):
+    def __init__(self, n):
+        super().__init__("hash table full: %d rows found no slot" % n)
+        self.rows = n
+
+
+def can_hash_combine(f: Frame, op: str) -> bool:
+    if op not in OPS or f.num_out() != 2 or f.prefix() != 1:
+        return False
+    k, v = f.col(0), f.col(1)
+    return (isinstance(k, torch.Tensor) and k.dtype == torch.int64 and k.dim() == 1
+            and isinstance(v, torch.Tensor) and v.dtype in VTYPE and v.dim() == 1)
+
+
+def hash_combine(keys: torch.Tensor, vals: torch.Tensor, op: str,
+                 distinct_hint: Optional[int] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Reduce ``vals`` by ``keys`` with the hash-aggregation kernels."""
+    n = keys.numel()
+    cap = 2 * (distinct_hint if distinct_hint is not None else min(n, 1 << 22))
+    while True:
+        t = HashTable(max(cap, 2048), vals.dtype, op, keys.device)
+        t.combine(keys, vals)
+        try:
+            return t.compact()
+        except TableFull:
+            cap = t.cap * 4  # rare: grow and redo
+
+
+def hash_combine_frame(f: Frame, op: str) -> Frame:
+    k, v = hash_combine(f.col(0), f.col(1), op)
+    return Frame([k, v], f.typ)
+
+
+# ---------------------------------------------------------------- sort
+
+def sort_pairs_i64(keys: torch.Tensor, vals: Optional[torch.Tensor]) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Stable radix sort of int64 keys with a 64-bit payload (default: row
+    index, i.e. the sorting permutation)."""
+    lib = require()
+    n = keys.numel()
+    dev = keys.device
+    ka = keys.contiguous().clone()
+    va = torch.arange(n, dtype=torch.int64, device=dev) if vals is None else vals.contiguous().clone()
+    if n <= 1:
+        return ka, va
+    kb, vb = torch.empty_like(ka), torch.empty_like(va)
+    scratch = torch.empty(int(lib.bs_sort_scratch_bytes(c_ll(n))) // 8 + 8, dtype=torch.int64, device=dev)
+    rc = lib.bs_radix_sort_pairs(_ptr(ka), _ptr(va), _ptr(kb), _ptr(vb), c_ll(n), _ptr(scratch), _stream())
+    if rc < 0:
+        raise RuntimeError("radix sort failed: cuda error %d" % -rc)
+    return (kb, vb) if rc == 1 else (ka, va)
+
+
+# ---------------------------------------------------------------- compaction / segments
+
+def compact_indices(mask: torch.Tensor) -> torch.Tensor:
+    """Indices of the true elements of a bool mask, in order."""
+    lib = require()
+    mask = mask.contiguous()
+    n = mask.numel()
+    out = torch.empty(n, dtype=torch.int64, device=mask.device)
+    scratch = torch.empty(int(lib.bs_compact_scratch_bytes(c_ll(n))) // 8 + 2, dtype=torch.int64,
+                          device=mask.device)
+    count = torch.zeros(1, dtype=torch.int64, device=mask.device)
+    _chk(lib.bs_compact_indices(_ptr(mask), c_ll(n), _ptr(out), _ptr(scratch), _ptr(count), _stream()),
+         "compact_indices")
+    return out[:int(count)]
+
+
+def segmented_reduce(vals: torch.Tensor, starts: torch.Tensor, nseg: int, op: str) -> torch.Tensor:
+    lib = require()
+    vals = vals.contiguous()
+    seg = (torch.cumsum(starts.to(torch.int64), 0) - 1).contiguous()
+    out = torch.empty(nseg, dtype=vals.dtype, device=vals.device)
+    _chk(lib.bs_segreduce(_ptr(vals), _ptr(seg), c_ll(vals.numel()), _ptr(out), c_ll(nseg),
+                          c_int(VTYPE[vals.dtype]), c_int(OPS[op]), _stream()), "segreduce")
+    return out
+
+
+def expand_indices(offsets: torch.Tensor) -> torch.Tensor:
+    """src row for every output slot given exclusive offsets (n+1)."""
+    lib = require()
+    offsets = offsets.contiguous()
+    n = offsets.numel() - 1
+    total = int(offsets[-1])
+    src = torch.empty(total, dtype=torch.int64, device=offsets.device)
+    _chk(lib.bs_expand_indices(_ptr(offsets), c_ll(n), c_ll(total), _ptr(src), _stream()),
+         "expand_indices")
+    return src
+
+
+def crc32(t: torch.Tensor) -> int:
+    """CRC32-IEEE of a device tensor's bytes (device per-block CRCs + host
+    GF(2) combine)."""
+    lib = require()
+    from .. import _native
+    t = t.contiguous()
+    nbytes = t.numel() * t.element_size()
+    if nbytes == 0:
+        return 0
+    nb = int(lib.bs_crc32_nblocks(c_ll(nbytes)))
+    out = torch.empty(nb, dtype=torch.int32, device=t.device)
+    _chk(lib.bs_crc32_blocks(_ptr(t), c_ll(nbytes), _ptr(out), _stream()), "crc32")
+    crcs = out.cpu().numpy().view("uint32")
+    nat = _native.lib()
+    block = int(lib.bs_crc32_block_bytes())
+    if nat is not None:
+        return int(nat.crc32_combine_blocks(crcs, nbytes, block))
+    raise RuntimeError("crc32 combine needs the native module")

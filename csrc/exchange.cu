@@ -1,0 +1,445 @@
+// K2: fused hash -> partition -> all-to-all over NVLink peer memory.
+//
+// Every rank maps every peer's control block and receive arena (CUDA IPC).  A
+// shuffle is four launches on each rank's stream and **no NCCL call**:
+//
+//   xchg_count   per-destination-shard row counts of the local rows
+//                (murmur3 of the key prefix, or caller-provided ids; optional
+//                "skip EMPTY" predicate so a hash table can be shuffled in
+//                place — fused compaction).
+//   xchg_plan    one CTA: stores this rank's counts row (+ its arena base) into
+//                every peer's control block with P2P stores, releases a flag at
+//                system scope, acquire-spins for all peers' flags, then turns
+//                the W x P count matrix into exact, densely packed destination
+//                addresses for every (dest shard, column).  This is the
+//                all-gather of counts done with peer stores + flags.
+//   xchg_scatter per 2048-row tile: rank rows by destination in shared memory,
+//                reserve a slot range per destination with one local atomic,
+//                stage each column in destination order in shared memory and
+//                write it out with coalesced stores that land directly in the
+//                destination GPU's HBM (NVLink).  The last CTA releases the
+//                "data complete" flag on every peer.
+//   xchg_wait    acquire-spins until every peer's data flag reached the epoch.
+//
+// Spins are bounded (timeout -> abort flag) so a dead peer cannot hang the GPU.
+// Replaces the reference's pull-based file+RPC shuffle (exec/bigmachine.go:
+// 857-1005) and the in-memory row copies of exec/local.go:217-230.
+#include "common.cuh"
+#include <string.h>
+
+#define XC_MAXW 16    // ranks
+#define XC_MAXP 256   // destination shards
+#define XC_MAXC 8     // columns per row
+#define XC_MAXK 4     // key columns hashed
+#define XC_TILE 2048
+#define XC_THREADS 512
+#define XC_TIMEOUT_NS 30000000000ULL
+
+// Symmetric control block, one per rank, mapped by every peer.
+struct XcCtrl {
+  unsigned long long count_flag[XC_MAXW];   // epoch of the last counts row from rank s
+  unsigned long long data_flag[XC_MAXW];    // epoch of the last completed scatter from rank s
+  unsigned long long arena_base[2][XC_MAXW];
+  long long cnt[2][XC_MAXW][XC_MAXP];
+  unsigned long long abort_flag;
+  unsigned long long barrier_flag[XC_MAXW];
+};
+
+struct XcPeers {
+  int world, rank;
+  XcCtrl* ctrl[XC_MAXW];            // peer-mapped control blocks
+  unsigned char* arena[XC_MAXW];    // peer-mapped receive arenas
+  unsigned long long arena_bytes;
+};
+
+struct XcSpec {
+  long long n;                       // local rows (or table slots)
+  int nparts;                        // destination shards; shard d lives on rank d % world
+  int ncols;
+  int nkeys;                         // key columns (first nkeys columns of cols) when ids == null
+  int skip_empty;                    // skip rows whose first column equals BS_EMPTY_KEY
+  const long long* ids;              // optional explicit destination per row
+  const unsigned char* cols[XC_MAXC];
+  int es[XC_MAXC];                   // bytes per row of each column
+};
+
+// Per-exchange plan, written by xchg_plan, read by xchg_scatter and the host.
+struct XcPlan {
+  unsigned char* dst[XC_MAXP][XC_MAXC];          // where this rank's rows of shard d, col c go
+  long long recv_total[XC_MAXP];                 // total rows of shard d (all sources)
+  unsigned long long recv_off[XC_MAXP][XC_MAXC]; // byte offset of (d, c) region in the owner's arena
+  unsigned long long arena_end[XC_MAXW];         // bytes used in each rank's arena
+  long long send_count[XC_MAXP];                 // this rank's rows per shard
+  unsigned long long cursor[XC_MAXP];            // running slot reservation (scatter)
+  unsigned int done_ctas;
+  int error;                                     // 1 overflow, 2 timeout/abort
+};
+
+__device__ __forceinline__ int xc_dest(const XcSpec& sp, long long i) {
+  if (sp.ids) return (int)sp.ids[i];
+  uint32_t h = 0;
+#pragma unroll
+  for (int k = 0; k < XC_MAXK; ++k) {
+    if (k < sp.nkeys) {
+      if (sp.es[k] == 8) h ^= bs_murmur3_u64(((const uint64_t*)sp.cols[k])[i], 0u);
+      else h ^= bs_murmur3_u32(((const uint32_t*)sp.cols[k])[i], 0u);
+    }
+  }
+  return (int)(h % (uint32_t)sp.nparts);
+}
+__device__ __forceinline__ bool xc_valid(const XcSpec& sp, long long i) {
+  return !sp.skip_empty || ((const long long*)sp.cols[0])[i] != BS_EMPTY_KEY;
+}
+
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(XC_THREADS) xchg_count_kernel(XcSpec sp, XcPlan* plan) {
+  __shared__ int hist[XC_MAXP];
+  for (int d = threadIdx.x; d < sp.nparts; d += blockDim.x) hist[d] = 0;
+  __syncthreads();
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long stride = (long long)gridDim.x * blockDim.x;
+  for (; i < sp.n; i += stride)
+    if (xc_valid(sp, i)) atomicAdd(&hist[xc_dest(sp, i)], 1);
+  __syncthreads();
+  for (int d = threadIdx.x; d < sp.nparts; d += blockDim.x)
+    if (hist[d]) atomicAdd((unsigned long long*)&plan->send_count[d], (unsigned long long)hist[d]);
+}
+
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) xchg_plan_kernel(XcPeers pe, XcSpec sp, XcPlan* plan,
+                                                        unsigned long long epoch,
+                                                        unsigned long long my_arena_base) {
+  const int W = pe.world, me = pe.rank, P = sp.nparts;
+  const int par = (int)(epoch & 1);
+  const int tid = threadIdx.x;
+  __shared__ int bad;
+  if (tid == 0) bad = 0;
+  // 1. publish my counts row and arena base to every peer (P2P stores)
+  for (int x = tid; x < W * P; x += blockDim.x) {
+    int p = x / P, d = x - p * P;
+    pe.ctrl[p]->cnt[par][me][d] = plan->send_count[d];
+  }
+  if (tid < W) pe.ctrl[tid]->arena_base[par][me] = my_arena_base;
+  __threadfence_system();
+  __syncthreads();
+  // 2. release flag on every peer, then 3. acquire all peers' flags
+  if (tid < W) bs_st_release_sys(&pe.ctrl[tid]->count_flag[me], epoch);
+  if (tid < W) {
+    const unsigned long long* f = &pe.ctrl[me]->count_flag[tid];
+    unsigned long long t0 = bs_globaltimer_ns();
+    while (bs_ld_acquire_sys(f) < epoch) {
+      if (bs_ld_relaxed_sys(&pe.ctrl[me]->abort_flag) != 0 ||
+          bs_globaltimer_ns() - t0 > XC_TIMEOUT_NS) {
+        atomicExch(&bad, 2);
+        break;
+      }
+      __nanosleep(200);
+    }
+  }
+  __syncthreads();
+  if (bad) {
+    if (tid == 0) {
+      plan->error = 2;
+      for (int p = 0; p < W; ++p) bs_st_release_sys(&pe.ctrl[p]->abort_flag, 1ULL);
+    }
+    return;
+  }
+  // 4. layout: shards of rank p are packed in increasing d, each (d, c) region
+  //    256-byte aligned.  Every rank computes the same layout from the matrix.
+  XcCtrl* mine = pe.ctrl[me];
+  if (tid < P) {
+    long long total = 0, before = 0;
+    for (int s = 0; s < W; ++s) {
+      long long c = mine->cnt[par][s][tid];
+      if (s < me) before += c;
+      total += c;
+    }
+    plan->recv_total[tid] = total;
+    plan->cursor[tid] = (unsigned long long)before;  // my first slot inside shard tid
+  }
+  __syncthreads();
+  if (tid < W) {
+    const int p = tid;
+    unsigned long long off = mine->arena_base[par][p];
+    for (int d = p; d < P; d += W) {
+      for (int c = 0; c < sp.ncols; ++c) {
+        plan->recv_off[d][c] = off;
+        plan->dst[d][c] = pe.arena[p] + off;
+        off += (((unsigned long long)plan->recv_total[d] * (unsigned long long)sp.es[c]) + 255ULL) & ~255ULL;
+      }
+    }
+    plan->arena_end[p] = off;
+    if (off > pe.arena_bytes) atomicExch(&plan->error, 1);
+  }
+  if (tid == 0) plan->done_ctas = 0;
+}
+
+// ---------------------------------------------------------------------------
+template <int VW>
+__device__ __forceinline__ void xc_copy_chunk(unsigned char* dst, const unsigned char* src) {
+  if (VW == 16) *(int4*)dst = *(const int4*)src;
+  else if (VW == 8) *(long long*)dst = *(const long long*)src;
+  else if (VW == 4) *(int*)dst = *(const int*)src;
+  else if (VW == 2) *(short*)dst = *(const short*)src;
+  else *dst = *src;
+}
+
+template <int VW>
+__device__ __forceinline__ void xc_move_column(const XcSpec& sp, const XcPlan* plan, int c,
+                                               long long row0, int rows, const int* sortpos,
+                                               const unsigned short* pos_dest, const int* segstart,
+                                               const unsigned long long* base,
+                                               unsigned char* stage) {
+  constexpr int PER = XC_TILE / XC_THREADS;
+  const int es = sp.es[c];
+  const int nchunk = es / VW;
+  for (int q = 0; q < nchunk; ++q) {
+    // stage this chunk of the column in destination-sorted order
+#pragma unroll
+    for (int j = 0; j < PER; ++j) {
+      int r = threadIdx.x + j * XC_THREADS;
+      if (r < rows && sortpos[j] >= 0)
+        xc_copy_chunk<VW>(stage + (size_t)sortpos[j] * VW,
+                          sp.cols[c] + (size_t)(row0 + r) * es + (size_t)q * VW);
+    }
+    __syncthreads();
+    const int nsorted = segstart[sp.nparts];
+    for (int pos = threadIdx.x; pos < nsorted; pos += XC_THREADS) {
+      int d = pos_dest[pos];
+      unsigned long long slot = base[d] + (unsigned long long)(pos - segstart[d]);
+      xc_copy_chunk<VW>(plan->dst[d][c] + slot * (unsigned long long)es + (size_t)q * VW,
+                        stage + (size_t)pos * VW);
+    }
+    __syncthreads();
+  }
+}
+
+__global__ void __launch_bounds__(XC_THREADS) xchg_scatter_kernel(XcPeers pe, XcSpec sp, XcPlan* plan,
+                                                                 unsigned long long epoch) {
+  __shared__ int hist[XC_MAXP];
+  __shared__ int segstart[XC_MAXP + 1];
+  __shared__ unsigned long long base[XC_MAXP];
+  __shared__ unsigned short pos_dest[XC_TILE];
+  __shared__ __align__(16) unsigned char stage[XC_TILE * 16];
+  constexpr int PER = XC_TILE / XC_THREADS;
+  const int P = sp.nparts;
+  if (plan->error == 0) {
+    const long long ntiles = (sp.n + XC_TILE - 1) / XC_TILE;
+    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      for (int d = threadIdx.x; d < P; d += blockDim.x) hist[d] = 0;
+      __syncthreads();
+      const long long row0 = tile * XC_TILE;
+      const int rows = (int)(sp.n - row0 < XC_TILE ? sp.n - row0 : XC_TILE);
+      int dest[PER], rank[PER], sortpos[PER];
+#pragma unroll
+      for (int j = 0; j < PER; ++j) {
+        int r = threadIdx.x + j * XC_THREADS;
+        dest[j] = -1;
+        if (r < rows && xc_valid(sp, row0 + r)) {
+          dest[j] = xc_dest(sp, row0 + r);
+          rank[j] = atomicAdd(&hist[dest[j]], 1);
+        }
+      }
+      __syncthreads();
+      // exclusive scan of hist (P <= 256: one warp, 8 entries per lane)
+      if (threadIdx.x < 32) {
+        const int lane = threadIdx.x;
+        const int per = (P + 31) / 32;
+        int local = 0;
+        for (int k = 0; k < per; ++k) {
+          int d = lane * per + k;
+          if (d < P) local += hist[d];
+        }
+        int incl = local;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          int t = __shfl_up_sync(0xffffffffu, incl, o);
+          if (lane >= o) incl += t;
+        }
+        int run = incl - local;
+        for (int k = 0; k < per; ++k) {
+          int d = lane * per + k;
+          if (d < P) {
+            segstart[d] = run;
+            run += hist[d];
+          }
+        }
+        if (lane == 31) segstart[P] = incl;
+      }
+      __syncthreads();
+      // one local atomic per destination reserves this tile's slot range
+      for (int d = threadIdx.x; d < P; d += blockDim.x)
+        if (hist[d]) base[d] = atomicAdd(&plan->cursor[d], (unsigned long long)hist[d]);
+#pragma unroll
+      for (int j = 0; j < PER; ++j) {
+        sortpos[j] = -1;
+        if (dest[j] >= 0) {
+          sortpos[j] = segstart[dest[j]] + rank[j];
+          pos_dest[sortpos[j]] = (unsigned short)dest[j];
+        }
+      }
+      __syncthreads();
+      for (int c = 0; c < sp.ncols; ++c) {
+        const int es = sp.es[c];
+        const bool a16 = ((uintptr_t)sp.cols[c] & 15) == 0;
+        if (es % 16 == 0 && a16) xc_move_column<16>(sp, plan, c, row0, rows, sortpos, pos_dest, segstart, base, stage);
+        else if (es % 8 == 0) xc_move_column<8>(sp, plan, c, row0, rows, sortpos, pos_dest, segstart, base, stage);
+        else if (es % 4 == 0) xc_move_column<4>(sp, plan, c, row0, rows, sortpos, pos_dest, segstart, base, stage);
+        else if (es % 2 == 0) xc_move_column<2>(sp, plan, c, row0, rows, sortpos, pos_dest, segstart, base, stage);
+        else xc_move_column<1>(sp, plan, c, row0, rows, sortpos, pos_dest, segstart, base, stage);
+      }
+    }
+  }
+  // completion: every CTA fences its peer stores; the last one signals peers.
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence_system();
+    unsigned int prev = atomicAdd(&plan->done_ctas, 1u);
+    if (prev == gridDim.x - 1) {
+      __threadfence_system();
+      for (int p = 0; p < pe.world; ++p) bs_st_release_sys(&pe.ctrl[p]->data_flag[pe.rank], epoch);
+    }
+  }
+}
+
+__global__ void xchg_wait_kernel(XcPeers pe, XcPlan* plan, unsigned long long epoch) {
+  const int tid = threadIdx.x;
+  if (tid < pe.world) {
+    const unsigned long long* f = &pe.ctrl[pe.rank]->data_flag[tid];
+    unsigned long long t0 = bs_globaltimer_ns();
+    while (bs_ld_acquire_sys(f) < epoch) {
+      if (bs_ld_relaxed_sys(&pe.ctrl[pe.rank]->abort_flag) != 0 ||
+          bs_globaltimer_ns() - t0 > XC_TIMEOUT_NS) {
+        plan->error = 2;
+        break;
+      }
+      __nanosleep(200);
+    }
+  }
+  __threadfence_system();
+}
+
+// In-kernel barrier across ranks (flag all-to-all), used to fence arena reuse
+// and for device-side timing alignment.  No NCCL.
+__global__ void xchg_barrier_kernel(XcPeers pe, unsigned long long epoch, int* err) {
+  const int tid = threadIdx.x;
+  __threadfence_system();
+  if (tid < pe.world) bs_st_release_sys(&pe.ctrl[tid]->barrier_flag[pe.rank], epoch);
+  if (tid < pe.world) {
+    const unsigned long long* f = &pe.ctrl[pe.rank]->barrier_flag[tid];
+    unsigned long long t0 = bs_globaltimer_ns();
+    while (bs_ld_acquire_sys(f) < epoch) {
+      if (bs_globaltimer_ns() - t0 > XC_TIMEOUT_NS) {
+        if (err) *err = 2;
+        break;
+      }
+      __nanosleep(200);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// host API
+BS_EXPORT int bs_xc_sizes(int* ctrl_bytes, int* plan_bytes, int* peers_bytes, int* spec_bytes) {
+  *ctrl_bytes = (int)sizeof(XcCtrl);
+  *plan_bytes = (int)sizeof(XcPlan);
+  *peers_bytes = (int)sizeof(XcPeers);
+  *spec_bytes = (int)sizeof(XcSpec);
+  return 0;
+}
+BS_EXPORT int bs_xc_limits(int* maxw, int* maxp, int* maxc, int* maxk) {
+  *maxw = XC_MAXW; *maxp = XC_MAXP; *maxc = XC_MAXC; *maxk = XC_MAXK;
+  return 0;
+}
+
+// Offsets inside XcPlan for the host to read results without a header.
+BS_EXPORT int bs_xc_plan_offsets(long long* recv_total, long long* recv_off, long long* arena_end,
+                                 long long* send_count, long long* error) {
+  XcPlan* p = nullptr;
+  *recv_total = (long long)(uintptr_t)&p->recv_total[0];
+  *recv_off = (long long)(uintptr_t)&p->recv_off[0][0];
+  *arena_end = (long long)(uintptr_t)&p->arena_end[0];
+  *send_count = (long long)(uintptr_t)&p->send_count[0];
+  *error = (long long)(uintptr_t)&p->error;
+  return 0;
+}
+
+BS_EXPORT int bs_ipc_alloc(long long bytes, void** ptr, unsigned char* handle64) {
+  cudaError_t e = cudaMalloc(ptr, (size_t)bytes);
+  if (e != cudaSuccess) return (int)e;
+  e = cudaMemset(*ptr, 0, (size_t)bytes);
+  if (e != cudaSuccess) return (int)e;
+  cudaIpcMemHandle_t h;
+  e = cudaIpcGetMemHandle(&h, *ptr);
+  if (e != cudaSuccess) return (int)e;
+  memcpy(handle64, &h, sizeof(h));
+  return 0;
+}
+BS_EXPORT int bs_ipc_open(const unsigned char* handle64, void** ptr) {
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle64, sizeof(h));
+  return (int)cudaIpcOpenMemHandle(ptr, h, cudaIpcMemLazyEnablePeerAccess);
+}
+BS_EXPORT int bs_ipc_close(void* ptr) { return (int)cudaIpcCloseMemHandle(ptr); }
+BS_EXPORT int bs_dev_free(void* ptr) { return (int)cudaFree(ptr); }
+BS_EXPORT int bs_dev_alloc(long long bytes, void** ptr) {
+  cudaError_t e = cudaMalloc(ptr, (size_t)bytes);
+  if (e != cudaSuccess) return (int)e;
+  return (int)cudaMemset(*ptr, 0, (size_t)bytes);
+}
+BS_EXPORT int bs_enable_peer(int peer_device) {
+  cudaError_t e = cudaDeviceEnablePeerAccess(peer_device, 0);
+  if (e == cudaErrorPeerAccessAlreadyEnabled) {
+    cudaGetLastError();
+    return 0;
+  }
+  return (int)e;
+}
+BS_EXPORT int bs_memcpy_d2d(void* dst, const void* src, long long bytes, cudaStream_t stream) {
+  return (int)cudaMemcpyAsync(dst, src, (size_t)bytes, cudaMemcpyDeviceToDevice, stream);
+}
+BS_EXPORT int bs_memcpy_d2h(void* dst, const void* src, long long bytes, cudaStream_t stream) {
+  return (int)cudaMemcpyAsync(dst, src, (size_t)bytes, cudaMemcpyDeviceToHost, stream);
+}
+BS_EXPORT int bs_memset(void* dst, int v, long long bytes, cudaStream_t stream) {
+  return (int)cudaMemsetAsync(dst, v, (size_t)bytes, stream);
+}
+BS_EXPORT int bs_stream_sync(cudaStream_t stream) { return (int)cudaStreamSynchronize(stream); }
+
+// One full exchange enqueued on `stream`.  peers/spec are host structs laid out
+// exactly as XcPeers/XcSpec (built by the python side with ctypes).
+BS_EXPORT int bs_xc_exchange(const void* peers_h, const void* spec_h, void* plan_d,
+                             unsigned long long epoch, unsigned long long arena_base,
+                             cudaStream_t stream) {
+  XcPeers pe = *(const XcPeers*)peers_h;
+  XcSpec sp = *(const XcSpec*)spec_h;
+  if (pe.world > XC_MAXW || sp.nparts > XC_MAXP || sp.ncols > XC_MAXC || sp.nkeys > XC_MAXK) return -1;
+  XcPlan* plan = (XcPlan*)plan_d;
+  cudaError_t e = cudaMemsetAsync(plan, 0, sizeof(XcPlan), stream);
+  if (e != cudaSuccess) return (int)e;
+  int sms = bs_num_sms();
+  if (sp.n > 0) {
+    long long want = (sp.n + XC_THREADS - 1) / XC_THREADS;
+    int blocks = (int)(want < (long long)sms * 4 ? want : (long long)sms * 4);
+    xchg_count_kernel<<<blocks, XC_THREADS, 0, stream>>>(sp, plan);
+    BS_LAUNCH_CHECK();
+  }
+  xchg_plan_kernel<<<1, 256, 0, stream>>>(pe, sp, plan, epoch, arena_base);
+  BS_LAUNCH_CHECK();
+  long long ntiles = (sp.n + XC_TILE - 1) / XC_TILE;
+  int blocks = (int)(ntiles < (long long)sms * 2 ? ntiles : (long long)sms * 2);
+  if (blocks < 1) blocks = 1;
+  xchg_scatter_kernel<<<blocks, XC_THREADS, 0, stream>>>(pe, sp, plan, epoch);
+  BS_LAUNCH_CHECK();
+  xchg_wait_kernel<<<1, 32, 0, stream>>>(pe, plan, epoch);
+  BS_LAUNCH_CHECK();
+  return 0;
+}
+
+BS_EXPORT int bs_xc_barrier(const void* peers_h, unsigned long long epoch, int* err_d,
+                            cudaStream_t stream) {
+  XcPeers pe = *(const XcPeers*)peers_h;
+  xchg_barrier_kernel<<<1, 32, 0, stream>>>(pe, epoch, err_d);
+  BS_LAUNCH_CHECK();
+  return 0;
+}

@@ -1,0 +1,184 @@
+"""Numerics tests of the sm_100a kernels against plain PyTorch references.
+All marked gpu: they run on the B200 box (pytest -m gpu)."""
+import random
+
+import numpy as np
+import pytest
+import torch
+
+import bigslice_b200 as bs
+from bigslice_b200.frame import Frame, hashing
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def gpu():
+    from bigslice_b200.ops import gpu as g
+    assert g.available()
+    return g
+
+
+def dev(t):
+    return t.cuda()
+
+
+@pytest.mark.parametrize("dtype", [torch.int64, torch.int32, torch.int16, torch.int8, torch.uint8,
+                                   torch.float32, torch.float64])
+def test_hash_column_matches_reference(gpu, dtype):
+    g = torch.Generator().manual_seed(1)
+    if dtype.is_floating_point:
+        x = torch.randn(100003, generator=g).to(dtype)
+    else:
+        info = torch.iinfo(dtype)
+        x = torch.randint(max(info.min, -2**62), min(info.max, 2**62), (100003,), generator=g).to(dtype)
+    for seed in (0, 0x9acb0442):
+        want = hashing.hash_tensor(x, seed)
+        got = gpu.hash_column(dev(x), seed).cpu()
+        assert torch.equal(got, want)
+    a = gpu.hash_column(dev(x), 0)
+    b = gpu.hash_column(dev(x), 5, out=a.clone(), xor_into=True).cpu()
+    assert torch.equal(b, hashing.hash_tensor(x, 0) ^ hashing.hash_tensor(x, 5))
+
+
+def test_golden_placement_on_device(gpu):
+    f = Frame.of(torch.arange(7).cuda())
+    assert (f.hash() % 4).tolist() == [0, 0, 0, 3, 2, 3, 1]
+
+
+@pytest.mark.parametrize("npart", [1, 2, 7, 16, 300])
+def test_partition_perm_and_frame(gpu, npart):
+    n = 200001
+    g = torch.Generator().manual_seed(2)
+    keys = torch.randint(0, 1 << 40, (n,), generator=g)
+    vals = torch.arange(n, dtype=torch.float32)
+    ids = hashing.hash64(keys, 0) % npart
+    perm, counts = gpu.partition_perm(None, dev(keys), n, npart)
+    assert torch.equal(counts.cpu(), torch.bincount(ids, minlength=npart))
+    assert torch.equal(torch.sort(perm.cpu())[0], torch.arange(n))
+    off = 0
+    for d, c in enumerate(counts.tolist()):
+        assert bool((ids[perm[off:off + c].cpu()] == d).all())
+        off += c
+    parts = gpu.partition_frame(Frame.of(dev(keys), dev(vals)), dev(ids), npart)
+    assert sum(len(p) for p in parts) == n
+    for d, p in enumerate(parts):
+        k = p.col(0).cpu()
+        assert bool((hashing.hash64(k, 0) % npart == d).all())
+        assert torch.equal(keys[p.col(1).cpu().long()], k)
+
+
+def zipf_keys(n, vocab, seed):
+    rng = np.random.default_rng(seed)
+    w = 1.0 / np.arange(1, vocab + 1)
+    cdf = np.cumsum(w) / w.sum()
+    r = np.searchsorted(cdf, rng.random(n))
+    return torch.from_numpy((r.astype(np.int64) * 0x9E3779B97F4A7C15) & 0x7FFFFFFFFFFFFFFF)
+
+
+@pytest.mark.parametrize("vdtype", [torch.int64, torch.int32, torch.float32, torch.float64])
+@pytest.mark.parametrize("op", ["add", "min", "max"])
+def test_hash_combine_matches_torch(gpu, vdtype, op):
+    n = 300007
+    keys = zipf_keys(n, 5000, 3)
+    g = torch.Generator().manual_seed(4)
+    vals = torch.randint(-50, 50, (n,), generator=g).to(vdtype)
+    uk, inv = torch.unique(keys, return_inverse=True)
+    if op == "add":
+        want = torch.zeros(len(uk), dtype=torch.float64).index_add_(0, inv, vals.double())
+    else:
+        want = torch.empty(len(uk), dtype=torch.float64).scatter_reduce_(
+            0, inv, vals.double(), "amin" if op == "min" else "amax", include_self=False)
+    for simple in (False, True):
+        t = gpu.HashTable(4 * len(uk), vdtype, op, "cuda")
+        t.combine(dev(keys), dev(vals), force_simple=simple)
+        k, v = t.compact()
+        order = torch.sort(k.cpu())[1]
+        assert torch.equal(k.cpu()[order], uk)
+        assert torch.allclose(v.cpu()[order].double(), want, rtol=1e-5, atol=1e-3)
+
+
+def test_hash_combine_special_key_unaligned_and_growth(gpu):
+    EMPTY = -(1 << 63)
+    keys = torch.tensor([EMPTY, 5, EMPTY, 7, 5] * 5000)
+    vals = torch.ones(len(keys), dtype=torch.int64)
+    k, v = gpu.hash_combine(dev(keys)[1:], dev(vals)[1:], "add")  # 8-byte aligned only
+    got = dict(zip(k.tolist(), v.tolist()))
+    assert got == {EMPTY: 9999, 5: 10000, 7: 5000}
+    many = torch.arange(50000)
+    k, v = gpu.hash_combine(dev(many), dev(torch.ones_like(many)), "add", distinct_hint=100)
+    assert len(k) == 50000 and int(v.sum()) == 50000  # table grew after TableFull
+
+
+@pytest.mark.parametrize("n", [0, 1, 5, 4096, 100003, 1 << 20])
+def test_radix_sort_stable(gpu, n):
+    g = torch.Generator().manual_seed(n)
+    keys = torch.randint(-(1 << 62), 1 << 62, (n,), generator=g)
+    if n > 10:
+        keys[: n // 2] = keys[: n // 2] % 100 - 50  # duplicates + negatives
+    sk, perm = gpu.sort_pairs_i64(dev(keys), None)
+    wk, wperm = torch.sort(keys, stable=True)
+    assert torch.equal(sk.cpu(), wk) and torch.equal(perm.cpu(), wperm)
+    f = Frame.of(dev(keys), dev(torch.arange(n)))
+    assert f.sorted().col(1).cpu().tolist() == wperm.tolist()
+
+
+def test_compact_segreduce_expand_crc(gpu):
+    g = torch.Generator().manual_seed(9)
+    m = torch.rand(100001, generator=g) < 0.3
+    assert torch.equal(gpu.compact_indices(dev(m)).cpu(), torch.nonzero(m).flatten())
+    assert gpu.compact_indices(dev(torch.zeros(10, dtype=torch.bool))).numel() == 0
+    keys = torch.sort(torch.randint(0, 2000, (50000,), generator=g))[0]
+    starts = torch.ones(50000, dtype=torch.bool)
+    starts[1:] = keys[1:] != keys[:-1]
+    nseg = int(starts.sum())
+    seg = torch.cumsum(starts.long(), 0) - 1
+    for dt in (torch.int64, torch.float32, torch.float64, torch.int32):
+        vals = torch.randint(-9, 9, (50000,), generator=g).to(dt)
+        for op, red in (("add", "sum"), ("min", "amin"), ("max", "amax")):
+            want = torch.zeros(nseg, dtype=dt).scatter_reduce_(0, seg, vals, red, include_self=False)
+            got = gpu.segmented_reduce(dev(vals), dev(starts), nseg, op).cpu()
+            assert torch.allclose(got.double(), want.double())
+    counts = torch.randint(0, 5, (1000,), generator=g)
+    offs = torch.zeros(1001, dtype=torch.int64)
+    offs[1:] = torch.cumsum(counts, 0)
+    assert torch.equal(gpu.expand_indices(dev(offs)).cpu(),
+                       torch.repeat_interleave(torch.arange(1000), counts))
+    import zlib
+    data = torch.randint(0, 256, (100001,), generator=g, dtype=torch.uint8)
+    assert gpu.crc32(dev(data)) == zlib.crc32(data.numpy().tobytes()) & 0xFFFFFFFF
+
+
+def test_local_device_session_end_to_end(gpu):
+    """All combinators on the single-GPU executor give the CPU answers."""
+    n = 50000
+    g = torch.Generator().manual_seed(5)
+    keys = torch.randint(0, 500, (n,), generator=g)
+    vals = torch.ones(n, dtype=torch.int64)
+
+    @bs.Func
+    def pipeline(nshard: int):
+        s = bs.Const(nshard, keys, vals)
+        s = bs.Filter(s, lambda k, v: k % 2 == 0)
+        s = bs.Map(s, lambda k, v: (k // 2, v * 3))
+        return bs.Reduce(s, bs.ops.add)
+
+    want = {}
+    for k in keys.tolist():
+        if k % 2 == 0:
+            want[k // 2] = want.get(k // 2, 0) + 3
+    before = gpu.launches()
+    with bs.start(bs.LocalDevice("cuda"), bs.Parallelism(2)) as sess:
+        res = sess.run(pipeline, 4)
+        assert all(f.device.type == "cuda" for f in res.frames())
+        assert dict(res.rows()) == want
+    assert gpu.launches() > before
+    with bs.start(bs.LocalDevice("cuda")) as sess:
+        a = bs.Const(3, torch.tensor([1, 2, 1, 3]), torch.tensor([10., 20., 30., 40.]))
+        b = bs.Const(2, torch.tensor([2, 4]), torch.tensor([5, 6]))
+        res = bs.slicetest.run(bs.Cogroup(a, b), session=sess)
+        assert bs.slicetest.sorted_rows(res) == [(1, (10.0, 30.0), ()), (2, (20.0,), (5,)),
+                                                 (3, (40.0,), ()), (4, (), (6,))]
+        f = bs.Fold(bs.Const(2, torch.tensor([1, 2, 1]), torch.tensor([1., 2., 3.])),
+                    lambda acc, v: acc + v)
+        assert sorted(bs.slicetest.run(f, session=sess).rows()) == [(1, 4.0), (2, 2.0)]
