@@ -208,11 +208,12 @@ class Session:
             with self._status_lock:
                 inv = funcv.invocation(location, *args)
             einv = ExecInvocation(inv)
-            prepare = getattr(self.executor, "prepare_invocation", None)
-            if prepare is not None:
-                einv = prepare(einv)
-            slice_ = einv.invoke()
-            tasks = compile_slice(einv, slice_, self.machine_combiners)
+
+            def do_compile(ei):
+                sl = ei.invoke()
+                return sl, compile_slice(ei, sl, self.machine_combiners)
+            hook = getattr(self.executor, "compile_invocation", None)
+            slice_, tasks = hook(einv, do_compile) if hook is not None else do_compile(einv)
         einv.env.freeze()
         group = None
         status_tasks = []
@@ -227,6 +228,9 @@ class Session:
             for t in tasks:
                 self.roots[id(t)] = t
         t0 = time.time()
+        begin = getattr(self.executor, "begin_invocation", None)
+        if begin is not None:
+            begin(tasks)
         try:
             evaluate(self.executor, tasks, group)
         finally:

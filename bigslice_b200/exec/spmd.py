@@ -1,0 +1,423 @@
+"""SPMD executor: one process (rank) per GPU, shuffles over NVLink.
+
+Every rank runs the same driver program, registers the same Funcs and compiles
+the identical task graph (the compile environment is broadcast from rank 0, the
+Func registries are compared at start).  Shard ``s`` is owned by rank
+``s % world``; a rank executes only its own tasks.  A shuffle dependency is
+served by one *group exchange* per producer group:
+
+* **fused** (CUDA, default): the ``csrc/exchange.cu`` kernels hash, partition
+  and store rows directly into the destination GPU's receive arena through
+  NVLink peer mappings — no NCCL on the data path.  With a builtin combiner the
+  producer side first hash-aggregates locally (``csrc/hash_combine.cu``) and
+  the destination combines what it receives.
+* **nccl** — local partition + ``all_to_all_single``: the measured baseline.
+* **object** — codec-encoded frames over the control-plane (gloo) group: any
+  column type (strings, lists, python objects) and the CPU test path.
+
+Exchanges are collective, so they are issued by a single per-invocation thread
+in a canonical order (producer groups sorted by graph depth, then name), which
+is identical on all ranks; tasks themselves still run under the normal
+evaluator with ``parallelism`` local procs.
+
+This executor takes the place of the reference's cluster executor
+(``exec/bigmachine.go``, ``exec/slicemachine.go``): the "machines" are the GPUs
+of one NVSwitch box.  Like the reference's machine-combiner mode it does not
+recover lost tasks: a failure on any rank aborts the invocation everywhere.
+"""
+from __future__ import annotations
+
+import os
+import pickle
+import threading
+import time
+from typing import Any, Dict, List, Optional, Sequence, Tuple
+
+import torch
+import torch.distributed as dist
+
+from .. import context as _context
+from .. import errors, func as _func, slicefunc
+from ..frame import Frame, concat
+from ..frame import columns as C
+from ..sliceio import EmptyReader, FrameReader, MultiReader, Reader, decode_batch, encode_frame
+from ..slices import default_partitioner
+from .combiner import combine_frame
+from .local import LocalExecutor, TaskBuffer, split_by_partition
+from .task import Task, TaskState, iter_tasks
+
+
+class _TaggedReader(FrameReader):
+    combined_unique = False
+
+
+def init_process_group(device: Optional[str] = None) -> None:
+    """Initialise torch.distributed from the torchrun environment if needed."""
+    if dist.is_initialized():
+        return
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    os.environ.setdefault("MASTER_PORT", "29511")
+    os.environ.setdefault("RANK", "0")
+    os.environ.setdefault("WORLD_SIZE", "1")
+    use_cuda = (device or "").startswith("cuda") or (device is None and torch.cuda.is_available())
+    if use_cuda:
+        local = int(os.environ.get("LOCAL_RANK", os.environ.get("RANK", "0")))
+        torch.cuda.set_device(local % max(torch.cuda.device_count(), 1))
+        dist.init_process_group("nccl", device_id=torch.device("cuda", torch.cuda.current_device()))
+    else:
+        dist.init_process_group("gloo")
+
+
+class SpmdExecutor(LocalExecutor):
+    def __init__(self, parallelism: int = 1, device: Optional[str] = "auto",
+                 shuffle: str = "auto", arena_bytes: int = 1 << 30, zero_copy: bool = False):
+        if device == "auto":
+            device = "cuda" if torch.cuda.is_available() else None
+        if device == "cuda":
+            init_process_group("cuda")
+            device = "cuda:%d" % torch.cuda.current_device()
+        super().__init__(parallelism, device)
+        self.shuffle = shuffle
+        self.arena_bytes = arena_bytes
+        self.zero_copy = zero_copy
+        self.rank = 0
+        self.world = 1
+        self.ctrl_group = None
+        self.peers = None
+        self.exchanged: Dict[Tuple[int, int], List[Frame]] = {}
+        self.group_done: Dict[int, threading.Event] = {}
+        self.group_err: Dict[int, BaseException] = {}
+        self._glock = threading.Lock()
+        self.exchange_log: List[dict] = []
+
+    def name(self) -> str:
+        return "spmd"
+
+    def _pid(self):
+        return "rank%d" % self.rank
+
+    # -- lifecycle -----------------------------------------------------------
+    def start(self, session):
+        super().start(session)
+        init_process_group(str(self.device) if self.device is not None else "cpu")
+        self.rank, self.world = dist.get_rank(), dist.get_world_size()
+        if dist.get_backend() != "gloo":
+            self.ctrl_group = dist.new_group(backend="gloo")
+        else:
+            self.ctrl_group = dist.group.WORLD
+        # Func registries must match on every rank (slicemachine.go:689-702).
+        locs = _func.func_locations()
+        all_locs: List = [None] * self.world
+        dist.all_gather_object(all_locs, locs, group=self.ctrl_group)
+        for r, other in enumerate(all_locs):
+            if other != all_locs[0]:
+                diff = _func.func_locations_diff(all_locs[0], other)
+                raise errors.fatal("bigslice.Func registry differs between rank 0 and rank %d:\n%s"
+                                   % (r, "\n".join(d for d in diff if d)))
+        if self.shuffle == "auto":
+            self.shuffle = "fused" if (self.device is not None and self.device.type == "cuda") else "object"
+        if self.shuffle == "fused":
+            from ..parallel.peer import PeerGroup
+            self.peers = PeerGroup(self.ctrl_group, self.arena_bytes, self.device)
+
+        def shutdown():
+            if self.peers is not None:
+                self.peers.close()
+        return shutdown
+
+    def owner(self, shard: int) -> int:
+        return shard % self.world
+
+    def owns(self, task: Task) -> bool:
+        return self.owner(task.name.shard) == self.rank
+
+    # -- compile consistency ---------------------------------------------------
+    def compile_invocation(self, einv, do_compile):
+        """Rank 0 compiles with a writable environment and broadcasts it; the
+        other ranks compile against the frozen copy (CompileEnv semantics)."""
+        if self.world == 1:
+            return do_compile(einv)
+        if self.rank == 0:
+            out = do_compile(einv)
+            box = [pickle.dumps(einv.env)]
+            dist.broadcast_object_list(box, src=0, group=self.ctrl_group)
+            return out
+        box = [None]
+        dist.broadcast_object_list(box, src=0, group=self.ctrl_group)
+        einv.env = pickle.loads(box[0])
+        return do_compile(einv)
+
+    def begin_invocation(self, roots: Sequence[Task]) -> None:
+        """Start the collective thread that performs this invocation's group
+        exchanges in canonical order."""
+        groups: Dict[int, List[Task]] = {}
+        depth: Dict[int, int] = {}
+
+        def task_depth(t: Task, memo: Dict[int, int]) -> int:
+            if id(t) in memo:
+                return memo[id(t)]
+            d = 0
+            for dep in t.deps:
+                for dt in dep.tasks():
+                    dd = task_depth(dt, memo)
+                    if dt.group is not None:
+                        dd += 1
+                    d = max(d, dd)
+            memo[id(t)] = d
+            return d
+        memo: Dict[int, int] = {}
+        seen: List[Task] = []
+        iter_tasks(roots, seen.append)
+        for t in seen:
+            if t.group is not None:
+                gid = id(t.group[0])
+                if gid not in groups:
+                    groups[gid] = t.group
+                    depth[gid] = max(task_depth(x, memo) for x in t.group)
+        todo = []
+        with self._glock:
+            for gid, g in groups.items():
+                if gid not in self.group_done:
+                    self.group_done[gid] = threading.Event()
+                    todo.append((depth[gid], str(g[0].name), gid, g))
+        todo.sort(key=lambda x: (x[0], x[1]))
+        if not todo:
+            return
+        th = threading.Thread(target=self._collective_loop, args=(todo,), daemon=True,
+                              name="bigslice-spmd-collective")
+        th.start()
+
+    # -- the collective thread ---------------------------------------------------
+    def _collective_loop(self, todo) -> None:
+        if self.device is not None and self.device.type == "cuda":
+            torch.cuda.set_device(self.device)
+        failed: Optional[BaseException] = None
+        for _, _, gid, group in todo:
+            ev = self.group_done[gid]
+            if failed is None:
+                try:
+                    self._exchange_group(gid, group)
+                except BaseException as e:  # noqa: BLE001
+                    failed = e
+            if failed is not None:
+                self.group_err[gid] = failed
+            ev.set()
+
+    def _local_status(self, group: List[Task]) -> int:
+        """Wait for this rank's producers; 0 ok, 1 failed."""
+        for t in group:
+            if not self.owns(t):
+                continue
+            st = t.wait_state(TaskState.OK)
+            if st != TaskState.OK:
+                return 1
+        return 0
+
+    def _exchange_group(self, gid: int, group: List[Task]) -> None:
+        bad = self._local_status(group)
+        if self.world > 1:
+            flag = torch.tensor([bad], dtype=torch.int32)
+            dist.all_reduce(flag, op=dist.ReduceOp.MAX, group=self.ctrl_group)
+            bad = int(flag[0])
+        if bad:
+            raise errors.fatal("spmd: a producer of %s failed on some rank" % group[0].name)
+        head = group[0]
+        nparts = head.num_partition
+        typ = head.type.typ
+        frames: List[Frame] = []
+        for t in group:
+            if self.owns(t):
+                with self.lock:
+                    buf = self.buffers.pop(id(t), None)
+                if buf is not None:
+                    frames.extend(buf.parts[0])
+        f = concat(frames, typ, self.device) if frames else Frame.empty(typ, self.device)
+        ctx = slicefunc.Context(None, 0, self.device)
+        t0 = time.perf_counter()
+        with _context.use(ctx):
+            if head.combiner is not None and len(f):
+                f = combine_frame(f, head.combiner, ctx)
+            mode, parts = self._shuffle(f, head, nparts)
+            if head.combiner is not None:
+                parts = {p: [combine_frame(concat(fr, typ, self.device), head.combiner, ctx)]
+                         if fr else [] for p, fr in parts.items()}
+        with self._glock:
+            for p in range(self.rank, nparts, self.world):
+                self.exchanged[(gid, p)] = [x for x in parts.get(p, []) if len(x)]
+        self.exchange_log.append({"group": str(head.name), "mode": mode, "rows_in": len(f),
+                                  "seconds": time.perf_counter() - t0})
+
+    def _fused_ok(self, f: Frame, head: Task, nparts: int) -> bool:
+        from ..parallel import peer
+        if self.peers is None or nparts > peer.MAXP or f.num_out() > peer.MAXC or f.num_out() == 0:
+            return False
+        for c in f.cols():
+            if not (isinstance(c, torch.Tensor) and c.is_cuda and c.dtype != torch.bool):
+                return False
+        if head.partitioner is default_partitioner:
+            if f.prefix() > peer.MAXK:
+                return False
+            for k in range(f.prefix()):
+                c = f.col(k)
+                if c.dim() != 1 or c.element_size() not in (4, 8):
+                    return False
+        return True
+
+    def _shuffle(self, f: Frame, head: Task, nparts: int):
+        """Returns (mode, {local shard: [frames]})."""
+        typ = f.typ
+        if self.world == 1 and self.peers is None:
+            ids = head.partitioner(f, nparts) if len(f) else torch.zeros(0, dtype=torch.int64)
+            parts = split_by_partition(f, ids, nparts) if len(f) else [f] * nparts
+            return "local", {p: [parts[p]] for p in range(nparts)}
+        if self.shuffle == "fused" and self._fused_ok(f, head, nparts):
+            ids = None
+            if head.partitioner is not default_partitioner:
+                ids = head.partitioner(f, nparts).to(self.device)
+            got = self.peers.exchange(f.cols(), nparts, nkeys=f.prefix(), ids=ids,
+                                      zero_copy=self.zero_copy)
+            return "fused", {p: [Frame(cols, typ)] for p, cols in got.items()}
+        ids = head.partitioner(f, nparts) if len(f) else torch.zeros(0, dtype=torch.int64)
+        tensor_only = all(isinstance(c, torch.Tensor) for c in f.cols()) and f.num_out() > 0
+        if self.shuffle in ("nccl", "fused") and tensor_only and f.device.type == "cuda" \
+                and nparts <= self.world * 64:
+            return "nccl", self._shuffle_collective(f, ids, nparts)
+        return "object", self._shuffle_objects(f, ids, nparts)
+
+    def _shuffle_collective(self, f: Frame, ids: torch.Tensor, nparts: int):
+        """Baseline: library all-to-all of each column (plus the shard id)."""
+        from ..parallel.peer import collective_exchange_tensors
+        ids = ids.to(f.device)
+        cols = f.cols() + [ids]
+        got = collective_exchange_tensors(cols, ids % self.world, None)
+        rid = got[-1]
+        g = Frame(got[:-1], f.typ)
+        out = {}
+        for p in range(self.rank, nparts, self.world):
+            out[p] = [g.mask(rid == p)]
+        return out
+
+    def _shuffle_objects(self, f: Frame, ids: torch.Tensor, nparts: int):
+        """Any column type: codec-encoded per-shard frames over the control
+        plane (all_gather_object)."""
+        parts = split_by_partition(f, ids, nparts) if len(f) else []
+        mine = {}
+        for p, g in enumerate(parts):
+            if len(g) and self.owner(p) != self.rank:
+                mine[p] = encode_frame(g.to("cpu") if g.device.type != "cpu" else g)
+        allsends: List = [None] * self.world
+        if self.world > 1:
+            dist.all_gather_object(allsends, mine, group=self.ctrl_group)
+        out: Dict[int, List[Frame]] = {}
+        for p in range(self.rank, nparts, self.world):
+            frs = []
+            if parts and len(parts[p]):
+                frs.append(parts[p])
+            for r, sends in enumerate(allsends):
+                if r == self.rank or not sends or p not in sends:
+                    continue
+                b = sends[p]
+                frs.append(_decode_one(b, f.typ, self.device))
+            out[p] = frs
+        return out
+
+    # -- task execution ---------------------------------------------------------
+    def run(self, task: Task) -> None:
+        if not self.owns(task):
+            task.set(TaskState.RUNNING)
+            task.set(TaskState.OK)  # executed by its owner rank
+            return
+        super().run(task)
+        if task.state() == TaskState.LOST:
+            # no lineage recovery across ranks: surface as a fatal error
+            task.error(errors.fatal("spmd: task %s lost (no recovery in SPMD mode)" % task.name))
+
+    def dep_readers(self, task: Task) -> List[Reader]:
+        ins: List[Reader] = []
+        for dep in task.deps:
+            if dep.head.group is None:
+                dt = dep.head
+                if dt.state() != TaskState.OK:
+                    raise errors.TaskLostError("dependency %s is not available" % dt.name)
+                ins.append(self.reader(dt, dep.partition))
+                continue
+            gid = id(dep.head.group[0])
+            ev = self.group_done.get(gid)
+            if ev is None:
+                raise errors.fatal("spmd: no exchange scheduled for %s" % dep.head.name)
+            ev.wait()
+            if gid in self.group_err:
+                raise errors.fatal("spmd: exchange for %s failed" % dep.head.name, self.group_err[gid])
+            with self._glock:
+                frames = self.exchanged.get((gid, dep.partition), [])
+            typ = dep.head.type.typ
+            r: Reader
+            if frames:
+                r = _TaggedReader(concat(frames, typ, self.device))
+            else:
+                r = EmptyReader()
+            if dep.head.combiner is not None:
+                r.combined_unique = True
+            ins.append(r)
+        return ins
+
+    def buffer_output(self, task: Task, out: Reader, ctx) -> TaskBuffer:
+        if task.group is None:
+            return super().buffer_output(task, out, ctx)
+        # Shuffle producer: keep whole tiles; the group exchange partitions (and
+        # combines) them in one fused pass.
+        buf = TaskBuffer(1)
+        nrec = 0
+        try:
+            while True:
+                f = out.read(None)
+                if f is None:
+                    break
+                nrec += len(f)
+                buf.append(0, f)
+        finally:
+            out.close()
+        task.stats = {"inrecords": nrec, "write": nrec}
+        return buf
+
+    def reader(self, task: Task, partition: int) -> Reader:
+        if not self.owns(task):
+            return EmptyReader()
+        return super().reader(task, partition)
+
+    def discard(self, task: Task) -> None:
+        with self.lock:
+            self.buffers.pop(id(task), None)
+
+    # -- results -------------------------------------------------------------------
+    def result_reader(self, result) -> Reader:
+        """Rows of the shards this rank owns, in shard order (SPMD view)."""
+        return MultiReader([self.reader(t, 0) for t in result.tasks if self.owns(t)])
+
+    def gather(self, result) -> List[tuple]:
+        """All rows of ``result`` on every rank, in shard order."""
+        local = {}
+        for t in result.tasks:
+            if self.owns(t):
+                rows = []
+                for f in self.reader(t, 0):
+                    rows.extend(f.to("cpu").rows())
+                local[t.name.shard] = rows
+        everyone: List = [None] * self.world
+        if self.world > 1:
+            dist.all_gather_object(everyone, local, group=self.ctrl_group)
+        else:
+            everyone = [local]
+        merged = {}
+        for d in everyone:
+            merged.update(d)
+        out: List[tuple] = []
+        for s in sorted(merged):
+            out.extend(merged[s])
+        return out
+
+
+def _decode_one(b: bytes, typ, device) -> Frame:
+    import io
+    from ..sliceio import Decoder, read_all
+    return read_all(Decoder(io.BytesIO(b), typ, device), typ, device)

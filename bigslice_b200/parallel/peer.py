@@ -1,0 +1,228 @@
+"""NVLink peer memory and the fused exchange (host side).
+
+A :class:`PeerGroup` gives every rank (one process per GPU) direct pointers to
+every peer's *control block* (flags + count matrix) and *receive arena*:
+memory is ``cudaMalloc``'d by ``_bscuda.so``, exported with CUDA IPC handles
+that are all-gathered once over the bootstrap process group, and opened with
+``cudaIpcOpenMemHandle`` (peer access enabled lazily).  After that a shuffle is
+:meth:`PeerGroup.exchange`: the four kernels of ``csrc/exchange.cu`` on the
+current stream — no NCCL, no host round trips except one small D2H read of the
+plan to learn the received row counts.
+
+NCCL (or gloo on CPU) all-to-all of the same data is available as
+:func:`collective_exchange` — the measured baseline, and the path for columns
+the kernel does not handle (strings, lists, objects).
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from ..ops import gpu
+
+c_void_p, c_int, c_ll, c_ull = ctypes.c_void_p, ctypes.c_int, ctypes.c_longlong, ctypes.c_ulonglong
+
+MAXW, MAXP, MAXC, MAXK = 16, 256, 8, 4
+
+
+class XcPeers(ctypes.Structure):
+    _fields_ = [("world", c_int), ("rank", c_int), ("ctrl", c_void_p * MAXW),
+                ("arena", c_void_p * MAXW), ("arena_bytes", c_ull)]
+
+
+class XcSpec(ctypes.Structure):
+    _fields_ = [("n", c_ll), ("nparts", c_int), ("ncols", c_int), ("nkeys", c_int),
+                ("skip_empty", c_int), ("ids", c_void_p), ("cols", c_void_p * MAXC),
+                ("es", c_int * MAXC)]
+
+
+class _DevMem:
+    """Exposes raw device memory to torch through __cuda_array_interface__."""
+
+    def __init__(self, ptr: int, nbytes: int, owner=None):
+        self.owner = owner
+        self.__cuda_array_interface__ = {
+            "shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 3,
+            "strides": None}
+
+
+def device_view(ptr: int, nbytes: int, device, owner=None) -> torch.Tensor:
+    """uint8 tensor aliasing ``nbytes`` of device memory at ``ptr`` (zero copy)."""
+    if nbytes == 0:
+        return torch.empty(0, dtype=torch.uint8, device=device)
+    return torch.as_tensor(_DevMem(ptr, nbytes, owner), device=device)
+
+
+class ExchangeError(RuntimeError):
+    pass
+
+
+class PeerGroup:
+    """Symmetric NVLink-mapped buffers shared by the ranks of one box."""
+
+    def __init__(self, group=None, arena_bytes: int = 1 << 30, device=None):
+        lib = gpu.require()
+        self.lib = lib
+        self.group = group
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        if self.world > MAXW:
+            raise ExchangeError("fused exchange supports at most %d ranks" % MAXW)
+        self.device = torch.device(device if device is not None else
+                                   "cuda:%d" % torch.cuda.current_device())
+        sizes = [c_int() for _ in range(4)]
+        lib.bs_xc_sizes(*[ctypes.byref(s) for s in sizes])
+        self.ctrl_bytes, self.plan_bytes, peers_b, spec_b = [s.value for s in sizes]
+        if peers_b != ctypes.sizeof(XcPeers) or spec_b != ctypes.sizeof(XcSpec):
+            raise ExchangeError("ctypes/CUDA struct layout mismatch (%d/%d, %d/%d)" % (
+                peers_b, ctypes.sizeof(XcPeers), spec_b, ctypes.sizeof(XcSpec)))
+        offs = [c_ll() for _ in range(5)]
+        lib.bs_xc_plan_offsets(*[ctypes.byref(o) for o in offs])
+        (self.off_recv_total, self.off_recv_off, self.off_arena_end, self.off_send_count,
+         self.off_error) = [o.value for o in offs]
+        self.arena_bytes = int(arena_bytes)
+        # local allocations + IPC handles
+        self._ctrl = c_void_p()
+        self._arena = c_void_p()
+        h_ctrl = (ctypes.c_ubyte * 64)()
+        h_arena = (ctypes.c_ubyte * 64)()
+        self._chk(lib.bs_ipc_alloc(c_ll(self.ctrl_bytes), ctypes.byref(self._ctrl), h_ctrl), "ipc_alloc ctrl")
+        self._chk(lib.bs_ipc_alloc(c_ll(self.arena_bytes), ctypes.byref(self._arena), h_arena), "ipc_alloc arena")
+        mine = (bytes(h_ctrl), bytes(h_arena), torch.cuda.current_device(), os.getpid())
+        everyone: List = [None] * self.world
+        dist.all_gather_object(everyone, mine, group=group)
+        self.peers = XcPeers()
+        self.peers.world, self.peers.rank = self.world, self.rank
+        self.peers.arena_bytes = self.arena_bytes
+        self._opened: List[int] = []
+        for r, (hc, ha, devidx, pid) in enumerate(everyone):
+            if r == self.rank:
+                self.peers.ctrl[r], self.peers.arena[r] = self._ctrl.value, self._arena.value
+                continue
+            if devidx != torch.cuda.current_device():
+                lib.bs_enable_peer(c_int(devidx))  # best effort; IPC open enables lazily too
+            pc, pa = c_void_p(), c_void_p()
+            self._chk(lib.bs_ipc_open((ctypes.c_ubyte * 64).from_buffer_copy(hc), ctypes.byref(pc)),
+                      "ipc_open ctrl of rank %d" % r)
+            self._chk(lib.bs_ipc_open((ctypes.c_ubyte * 64).from_buffer_copy(ha), ctypes.byref(pa)),
+                      "ipc_open arena of rank %d" % r)
+            self.peers.ctrl[r], self.peers.arena[r] = pc.value, pa.value
+            self._opened += [pc.value, pa.value]
+        self.epoch = 0
+        self.barrier_epoch = 0
+        self.plan = torch.zeros(self.plan_bytes, dtype=torch.uint8, device=self.device)
+        self.err = torch.zeros(2, dtype=torch.int32, device=self.device)
+        self.arena_view = device_view(self._arena.value, self.arena_bytes, self.device, self)
+        self.stats = {"exchanges": 0, "bytes_sent": 0, "rows_sent": 0}
+        dist.barrier(group=group)
+
+    @staticmethod
+    def _chk(rc: int, what: str):
+        if rc != 0:
+            raise ExchangeError("%s failed: cuda error %d" % (what, rc))
+
+    def barrier(self) -> None:
+        """Device-side barrier across ranks (flag all-to-all kernel)."""
+        self.barrier_epoch += 1
+        self._chk(self.lib.bs_xc_barrier(ctypes.byref(self.peers), c_ull(self.barrier_epoch),
+                                         c_void_p(self.err.data_ptr()), gpu._stream()), "barrier")
+
+    # ------------------------------------------------------------------
+    def exchange(self, cols: Sequence[torch.Tensor], nparts: int, nkeys: int = 1,
+                 ids: Optional[torch.Tensor] = None, skip_empty: bool = False,
+                 zero_copy: bool = False) -> Dict[int, List[torch.Tensor]]:
+        """Shuffle rows (given as equal-length column tensors) to the owners of
+        ``nparts`` destination shards (shard d lives on rank d % world).
+
+        Returns ``{local shard: [column tensors]}`` holding every row of that
+        shard from all ranks.  Collective: every rank must call it in the same
+        order."""
+        if nparts > MAXP or len(cols) > MAXC or nkeys > MAXK:
+            raise ExchangeError("exchange shape outside fused-kernel limits")
+        cols = [c.contiguous() for c in cols]
+        n = int(cols[0].shape[0]) if cols else 0
+        spec = XcSpec()
+        spec.n, spec.nparts, spec.ncols, spec.nkeys = n, nparts, len(cols), nkeys
+        spec.skip_empty = 1 if skip_empty else 0
+        if ids is not None:
+            ids = ids.to(torch.int64).contiguous()
+            spec.ids = ids.data_ptr()
+        row_bytes = []
+        for i, c in enumerate(cols):
+            spec.cols[i] = c.data_ptr()
+            rb = c.element_size() * (c.numel() // c.shape[0] if c.shape[0] else
+                                     int(np.prod(c.shape[1:])) if c.dim() > 1 else 1)
+            spec.es[i] = rb
+            row_bytes.append(rb)
+        if ids is None:
+            for k in range(nkeys):
+                if spec.es[k] not in (4, 8):
+                    raise ExchangeError("fused exchange hashes 4- or 8-byte key columns only")
+        self.epoch += 1
+        self._chk(self.lib.bs_xc_exchange(ctypes.byref(self.peers), ctypes.byref(spec),
+                                          c_void_p(self.plan.data_ptr()), c_ull(self.epoch),
+                                          c_ull(0), gpu._stream()), "exchange")
+        plan = self.plan.cpu().numpy()  # one small D2H; syncs the stream
+        err = int(plan[self.off_error:self.off_error + 4].view(np.int32)[0])
+        if err == 1:
+            raise ExchangeError("receive arena overflow (%d bytes): raise arena_bytes" % self.arena_bytes)
+        if err:
+            raise ExchangeError("peer exchange aborted (timeout or peer failure)")
+        recv_total = plan[self.off_recv_total:self.off_recv_total + 8 * MAXP].view(np.int64)
+        recv_off = plan[self.off_recv_off:self.off_recv_off + 8 * MAXP * MAXC].view(np.uint64).reshape(MAXP, MAXC)
+        send = plan[self.off_send_count:self.off_send_count + 8 * MAXP].view(np.int64)
+        self.stats["exchanges"] += 1
+        self.stats["rows_sent"] += int(send[:nparts].sum())
+        self.stats["bytes_sent"] += int(send[:nparts].sum()) * sum(row_bytes)
+        out: Dict[int, List[torch.Tensor]] = {}
+        for d in range(self.rank, nparts, self.world):
+            rows = int(recv_total[d])
+            got = []
+            for i, c in enumerate(cols):
+                nb = rows * row_bytes[i]
+                view = self.arena_view[int(recv_off[d, i]):int(recv_off[d, i]) + nb]
+                t = view.view(c.dtype).reshape((rows,) + tuple(c.shape[1:]))
+                got.append(t if zero_copy else t.clone())
+            out[d] = got
+        if not zero_copy:
+            # the arena may be overwritten by the next exchange only after every
+            # rank has copied its rows out: the next count exchange orders that.
+            pass
+        return out
+
+    def close(self) -> None:
+        for p in self._opened:
+            self.lib.bs_ipc_close(c_void_p(p))
+        self._opened = []
+
+
+# ----------------------------------------------------------------------------
+# Baseline / fallback: partition locally, then a library all-to-all.
+
+def collective_exchange_tensors(cols: Sequence[torch.Tensor], dest_rank: torch.Tensor,
+                                group=None) -> List[torch.Tensor]:
+    """All-to-all of rows by destination *rank* using torch.distributed
+    (NCCL on GPU, gloo on CPU).  Returns the received columns."""
+    world = dist.get_world_size(group)
+    dest_rank = dest_rank.to(torch.int64)
+    order = torch.sort(dest_rank, stable=True)[1]
+    counts = torch.bincount(dest_rank, minlength=world)
+    send_counts = counts.cpu()
+    recv_counts = torch.empty_like(send_counts)
+    sc = send_counts.to(dest_rank.device) if dest_rank.is_cuda else send_counts
+    rc = torch.empty_like(sc)
+    dist.all_to_all_single(rc, sc, group=group)
+    recv_counts = rc.cpu()
+    out = []
+    in_splits, out_splits = send_counts.tolist(), recv_counts.tolist()
+    for c in cols:
+        s = c.index_select(0, order.to(c.device)).contiguous()
+        r = torch.empty((int(recv_counts.sum()),) + tuple(c.shape[1:]), dtype=c.dtype, device=c.device)
+        dist.all_to_all_single(r, s, out_splits, in_splits, group=group)
+        out.append(r)
+    return out
