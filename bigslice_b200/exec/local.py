@@ -153,7 +153,8 @@ class LocalExecutor(Executor):
         if task.pragma.exclusive():
             procs = self.parallelism
         self.limiter.acquire(procs)
-        t0 = time.time()
+        if self.device is not None and self.device.type == "cuda":
+            torch.cuda.set_device(self.device)  # CUDA's current device is per thread
         if self.tracer is not None:
             self.tracer.event(self._pid(), task, "B")
         try:

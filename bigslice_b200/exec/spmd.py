@@ -89,6 +89,8 @@ class SpmdExecutor(LocalExecutor):
         self.group_err: Dict[int, BaseException] = {}
         self._glock = threading.Lock()
         self.exchange_log: List[dict] = []
+        self.group_tables: Dict[int, Any] = {}       # gid -> streaming HashTable
+        self.card_hints: Dict[str, int] = {}         # slice name -> distinct keys seen
 
     def name(self) -> str:
         return "spmd"
@@ -224,6 +226,10 @@ class SpmdExecutor(LocalExecutor):
         head = group[0]
         nparts = head.num_partition
         typ = head.type.typ
+        with self._glock:
+            table = self.group_tables.pop(gid, None)
+        if table is not None:
+            return self._exchange_table(gid, head, table, nparts)
         frames: List[Frame] = []
         for t in group:
             if self.owns(t):
@@ -246,6 +252,97 @@ class SpmdExecutor(LocalExecutor):
                 self.exchanged[(gid, p)] = [x for x in parts.get(p, []) if len(x)]
         self.exchange_log.append({"group": str(head.name), "mode": mode, "rows_in": len(f),
                                   "seconds": time.perf_counter() - t0})
+
+    # -- fast Reduce path: streaming hash-aggregation, table shuffled in place --
+    def _table_path_ok(self, task: Task) -> bool:
+        if self.device is None or self.device.type != "cuda" or task.combiner is None:
+            return False
+        if task.partitioner is not default_partitioner:
+            return False
+        if self.world > 1 and self.peers is None:
+            return False
+        from ..ops import gpu
+        typ = task.type.typ
+        if task.combiner.builtin not in gpu.OPS or typ.num_out() != 2 or typ.prefix() != 1:
+            return False
+        return (typ.out(0).torch_dtype == torch.int64 and typ.out(0).kind == "int"
+                and typ.out(1).torch_dtype in gpu.VTYPE and typ.out(1).kind != "vec"
+                and task.num_partition <= 256)
+
+    def _hint_key(self, task: Task) -> str:
+        return "%s/%s" % (task.type.name(), task.combiner.builtin)
+
+    def _group_table(self, task: Task, rows_hint: int):
+        """The (per rank, per producer group) HBM table all local producer
+        tasks aggregate into; sized from the cardinality seen last time."""
+        from ..ops import gpu
+        gid = id(task.group[0])
+        with self._glock:
+            t = self.group_tables.get(gid)
+            if t is None:
+                hint = self.card_hints.get(self._hint_key(task))
+                cap = 2 * hint + 1024 if hint is not None else 2 * max(rows_hint, 1 << 16)
+                t = gpu.HashTable(cap, task.type.typ.out(1).torch_dtype, task.combiner.builtin,
+                                  self.device)
+                self.group_tables[gid] = t
+            return t
+
+    def _exchange_table(self, gid: int, head: Task, table, nparts: int) -> None:
+        from ..ops import gpu
+        typ = head.type.typ
+        t0 = time.perf_counter()
+        out: Dict[int, List[Frame]] = {}
+        if self.world == 1 and nparts == 1:
+            k, v = table.compact()  # the local table is already the answer
+            out[0] = [Frame([k, v], typ)]
+            sent = len(k)
+            mode = "table-local"
+        else:
+            got = self.peers.exchange([table.keys, table.vals], nparts, nkeys=1, skip_empty=True,
+                                      zero_copy=True)
+            st = table.status.tolist()
+            if st[0]:
+                raise errors.fatal("spmd: combine table overflow (%d rows); cardinality hint too low" % st[0])
+            sent = 0
+            for p, (rk, rv) in got.items():
+                sent += rk.numel()
+                if rk.numel() == 0:
+                    out[p] = []
+                    continue
+                # rows from different ranks may share keys: combine on arrival
+                fk, fv = gpu.hash_combine(rk, rv, head.combiner.builtin, distinct_hint=rk.numel())
+                out[p] = [Frame([fk, fv], typ)]
+            if st[1]:  # the reserved EMPTY key was present: route it on the host (rare)
+                self._route_special(head, st[2], nparts, out, typ)
+            mode = "fused-table"
+        self.card_hints[self._hint_key(head)] = max(int(sent * 1.25), 1 << 12) if self.world == 1 \
+            else max(int(self.peers.last_sent * 1.25), 1 << 12)
+        with self._glock:
+            for p in range(self.rank, nparts, self.world):
+                self.exchanged[(gid, p)] = [x for x in out.get(p, []) if len(x)]
+        self.exchange_log.append({"group": str(head.name), "mode": mode,
+                                  "seconds": time.perf_counter() - t0})
+
+    def _route_special(self, head: Task, bits: int, nparts: int, out, typ) -> None:
+        """A row with the reserved sentinel key: all ranks contribute their
+        partial over the control plane and its owner adds the row."""
+        import struct
+        from ..frame import hashing
+        key = -(1 << 63)
+        vt = typ.out(1).torch_dtype
+        raw = struct.pack("<q", bits if bits < (1 << 63) else bits - (1 << 64))
+        val = torch.frombuffer(bytearray(raw), dtype=vt)[0].item()
+        vals = [None] * self.world
+        dist.all_gather_object(vals, val, group=self.ctrl_group)
+        d = int(hashing.hash64(torch.tensor([key]), 0)[0]) % nparts
+        if self.owner(d) != self.rank:
+            return
+        op = head.combiner.builtin
+        tot = vals[0]
+        for x in vals[1:]:
+            tot = tot + x if op == "add" else (min(tot, x) if op == "min" else max(tot, x))
+        out.setdefault(d, []).append(Frame([torch.tensor([key], device=self.device),
+                                            torch.tensor([tot], dtype=vt, device=self.device)], typ))
 
     def _fused_ok(self, f: Frame, head: Task, nparts: int) -> bool:
         from ..parallel import peer
@@ -368,13 +465,25 @@ class SpmdExecutor(LocalExecutor):
         # combines) them in one fused pass.
         buf = TaskBuffer(1)
         nrec = 0
+        table = None
+        fast = self._table_path_ok(task)
         try:
             while True:
                 f = out.read(None)
                 if f is None:
                     break
                 nrec += len(f)
-                buf.append(0, f)
+                if fast and len(f):
+                    if table is None:
+                        hint_rows = 0
+                        src = task.slices[-1] if task.slices else None
+                        rh = getattr(src, "rows_hint", None)
+                        if rh is not None:
+                            hint_rows = int(rh(task.name.shard))
+                        table = self._group_table(task, max(hint_rows, len(f)))
+                    table.combine(f.col(0), f.col(1))  # async: overlaps the next read
+                else:
+                    buf.append(0, f)
         finally:
             out.close()
         task.stats = {"inrecords": nrec, "write": nrec}
@@ -388,6 +497,13 @@ class SpmdExecutor(LocalExecutor):
     def discard(self, task: Task) -> None:
         with self.lock:
             self.buffers.pop(id(task), None)
+        if task.group is not None and task is task.group[0]:
+            gid = id(task)
+            with self._glock:
+                for k in [k for k in self.exchanged if k[0] == gid]:
+                    del self.exchanged[k]
+                self.group_done.pop(gid, None)
+                self.group_err.pop(gid, None)
 
     # -- results -------------------------------------------------------------------
     def result_reader(self, result) -> Reader:

@@ -114,6 +114,7 @@ class PeerGroup:
             self.peers.ctrl[r], self.peers.arena[r] = pc.value, pa.value
             self._opened += [pc.value, pa.value]
         self.epoch = 0
+        self.last_sent = 0
         self.barrier_epoch = 0
         self.plan = torch.zeros(self.plan_bytes, dtype=torch.uint8, device=self.device)
         self.err = torch.zeros(2, dtype=torch.int32, device=self.device)
@@ -176,6 +177,7 @@ class PeerGroup:
         recv_total = plan[self.off_recv_total:self.off_recv_total + 8 * MAXP].view(np.int64)
         recv_off = plan[self.off_recv_off:self.off_recv_off + 8 * MAXP * MAXC].view(np.uint64).reshape(MAXP, MAXC)
         send = plan[self.off_send_count:self.off_send_count + 8 * MAXP].view(np.int64)
+        self.last_sent = int(send[:nparts].sum())
         self.stats["exchanges"] += 1
         self.stats["rows_sent"] += int(send[:nparts].sum())
         self.stats["bytes_sent"] += int(send[:nparts].sum()) * sum(row_bytes)
