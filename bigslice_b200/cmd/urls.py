@@ -1,0 +1,119 @@
+"""urls: count URL domains and report the most frequent ones.
+
+    python -m bigslice_b200.cmd.urls [session flags] [--input FILE ...] [--synthetic N] [--top K]
+
+The reference demo reads GDELT CSVs from S3, extracts the domain of every URL
+and counts domains with Reduce (``cmd/urls/urls.go:37-126``).  There is no
+network here, so inputs are local files (one URL per line / any column
+containing a URL) or a synthetic generator with Zipf-distributed domains.
+
+Pipeline: ``ScanReader/ReaderFunc -> Flatmap(extract domain) -> Map(domain ->
+(hash id, 1)) -> Reduce(add) -> per-shard top-K``.  Domains are dictionary-
+encoded to int64 ids (murmur3 of the domain; the id->domain table is a host
+side-output), so on the GPU executors the count runs on the fused int64
+hash-aggregation path.
+"""
+from __future__ import annotations
+
+import argparse
+import sys
+import threading
+from typing import Dict
+from urllib.parse import urlparse
+
+import numpy as np
+import torch
+
+import bigslice_b200 as bs
+from bigslice_b200 import sliceconfig
+from bigslice_b200.frame import hashing
+
+_domains: Dict[int, str] = {}
+_domains_lock = threading.Lock()
+
+
+def domain_of(url: str) -> str:
+    if "://" not in url:
+        url = "http://" + url
+    try:
+        return urlparse(url).netloc.lower()
+    except ValueError:
+        return ""
+
+
+def synthetic_urls(n: int, ndomain: int, seed: int) -> np.ndarray:
+    rng = np.random.default_rng(seed)
+    w = 1.0 / np.arange(1, ndomain + 1)
+    cdf = np.cumsum(w) / w.sum()
+    r = np.searchsorted(cdf, rng.random(n))
+    out = np.empty(n, dtype=object)
+    out[:] = ["https://site%d.example.com/page/%d" % (d, i) for i, d in enumerate(r.tolist())]
+    return out
+
+
+@bs.Func
+def count_domains(nshard: int, files: list, synthetic: int, ndomain: int, top: int):
+    if files:
+        def opener():
+            import io
+            return io.StringIO("".join(open(f).read() for f in files))
+        lines = bs.ScanReader(nshard, opener)
+    else:
+        def gen(shard):
+            per = synthetic // nshard
+            yield (synthetic_urls(per, ndomain, shard),)
+        lines = bs.ReaderGen(nshard, gen, [bs.string])
+
+    @bs.rowwise
+    def extract(line):
+        out = []
+        for tok in line.replace(",", " ").replace("\t", " ").split():
+            if "." in tok and ("/" in tok or tok.startswith("http")):
+                d = domain_of(tok)
+                if d:
+                    out.append(d)
+        return (out,)
+    domains = bs.Flatmap(lines, extract, out=[bs.string])
+
+    def encode(d):
+        ids = hashing.hash_objects(d, 0) | (hashing.hash_objects(d, 1) << 32)
+        with _domains_lock:
+            for i, s in zip(ids.tolist(), d.tolist()):
+                _domains.setdefault(i, s)
+        from bigslice_b200 import context as _ctx
+        dev = _ctx.current_device()
+        ids = ids.to(dev) if dev is not None else ids
+        return ids, torch.ones_like(ids)
+    pairs = bs.Map(domains, encode, out=[bs.int64, bs.int64])
+    counts = bs.Reduce(pairs, bs.ops.add)
+
+    def topk(k, v):
+        kk = min(top, v.numel())
+        idx = torch.topk(v, kk).indices
+        return k[idx], v[idx]
+    return bs.Flatmap(counts, topk, out=[bs.int64, bs.int64])
+
+
+def main(argv=None) -> int:
+    sess, rest = sliceconfig.parse(argv)
+    ap = argparse.ArgumentParser(prog="urls")
+    ap.add_argument("--input", action="append", default=[])
+    ap.add_argument("--synthetic", type=int, default=100000)
+    ap.add_argument("--ndomain", type=int, default=5000)
+    ap.add_argument("--nshard", type=int, default=8)
+    ap.add_argument("--top", type=int, default=10)
+    a = ap.parse_args(rest)
+    try:
+        res = sess.run(count_domains, a.nshard, a.input, a.synthetic, a.ndomain, a.top)
+        g = getattr(sess.executor, "gather", None)
+        rows = g(res) if g is not None else res.rows()
+    finally:
+        sess.shutdown()
+    rows.sort(key=lambda r: -r[1])
+    for k, v in rows[:a.top]:
+        print("%s\t%d" % (_domains.get(k, "<%d>" % k), v))
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -224,6 +224,14 @@ class Session:
             for t in sorted(seen, key=lambda t: str(t.name)):
                 t.status = group.start(str(t.name))
                 status_tasks.append(t.status)
+        maint = stop_log = slice_group = None
+        if self.status_ is not None:
+            from .slicestatus import SliceGroupMaintainer, log_invocation
+            slice_group = self.status_.groupf("run %s [%d] slices", location, inv.index)
+            maint = SliceGroupMaintainer(slice_group, tasks)
+            stop_log = threading.Event()
+            threading.Thread(target=log_invocation, daemon=True,
+                             args=(inv.index, location, maint, stop_log)).start()
         with self._lock:
             for t in tasks:
                 self.roots[id(t)] = t
@@ -239,6 +247,10 @@ class Session:
                 for st in status_tasks:
                     st.done()
                 group.done()
+            if maint is not None:
+                stop_log.set()
+                maint.close()
+                slice_group.done()
         res = Result(slice_, self, inv.index, tasks)
         with self._lock:
             self._results.append(res)

@@ -116,6 +116,7 @@ class SpmdExecutor(LocalExecutor):
                 diff = _func.func_locations_diff(all_locs[0], other)
                 raise errors.fatal("bigslice.Func registry differs between rank 0 and rank %d:\n%s"
                                    % (r, "\n".join(d for d in diff if d)))
+        self.registry_size = len(locs)
         if self.shuffle == "auto":
             self.shuffle = "fused" if (self.device is not None and self.device.type == "cuda") else "object"
         if self.shuffle == "fused":
@@ -127,6 +128,13 @@ class SpmdExecutor(LocalExecutor):
                 self.peers.close()
         return shutdown
 
+    def check_registry(self) -> None:
+        """Fail if Funcs were registered after the session started."""
+        n = len(_func.func_locations())
+        if n != self.registry_size:
+            raise errors.fatal("bigslice.Func registry changed after session start (%d -> %d)"
+                               % (self.registry_size, n))
+
     def owner(self, shard: int) -> int:
         return shard % self.world
 
@@ -137,6 +145,9 @@ class SpmdExecutor(LocalExecutor):
     def compile_invocation(self, einv, do_compile):
         """Rank 0 compiles with a writable environment and broadcasts it; the
         other ranks compile against the frozen copy (CompileEnv semantics)."""
+        if einv.inv.func >= self.registry_size:
+            raise errors.fatal("bigslice.Func #%d was registered after the session started; "
+                               "ranks cannot agree on it" % einv.inv.func)
         if self.world == 1:
             return do_compile(einv)
         if self.rank == 0:

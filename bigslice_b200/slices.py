@@ -384,6 +384,8 @@ def ReaderFunc(nshard: int, read: Callable, *pragmas, out=None, state=None,
             params = params[1:]
         out = []
         for p in params[2:]:
+            if p.default is not p.empty or p.kind not in (p.POSITIONAL_ONLY, p.POSITIONAL_OR_KEYWORD):
+                continue  # bound extras (closures via defaults) are not columns
             ann = hints.get(p.name, p.annotation)
             try:
                 out.append(slicetype.dtype_of(ann))
