@@ -251,6 +251,7 @@ class SpmdExecutor(LocalExecutor):
         f = concat(frames, typ, self.device) if frames else Frame.empty(typ, self.device)
         ctx = slicefunc.Context(None, 0, self.device)
         t0 = time.perf_counter()
+        ev0 = self._cuda_event()
         with _context.use(ctx):
             if head.combiner is not None and len(f):
                 f = combine_frame(f, head.combiner, ctx)
@@ -261,8 +262,7 @@ class SpmdExecutor(LocalExecutor):
         with self._glock:
             for p in range(self.rank, nparts, self.world):
                 self.exchanged[(gid, p)] = [x for x in parts.get(p, []) if len(x)]
-        self.exchange_log.append({"group": str(head.name), "mode": mode, "rows_in": len(f),
-                                  "seconds": time.perf_counter() - t0})
+        self._log_exchange(head, mode, t0, ev0, rows_in=len(f))
 
     # -- fast Reduce path: streaming hash-aggregation, table shuffled in place --
     def _table_path_ok(self, task: Task) -> bool:
@@ -302,6 +302,7 @@ class SpmdExecutor(LocalExecutor):
         from ..ops import gpu
         typ = head.type.typ
         t0 = time.perf_counter()
+        ev0 = self._cuda_event()
         out: Dict[int, List[Frame]] = {}
         if self.world == 1 and nparts == 1:
             k, v = table.compact()  # the local table is already the answer
@@ -331,8 +332,7 @@ class SpmdExecutor(LocalExecutor):
         with self._glock:
             for p in range(self.rank, nparts, self.world):
                 self.exchanged[(gid, p)] = [x for x in out.get(p, []) if len(x)]
-        self.exchange_log.append({"group": str(head.name), "mode": mode,
-                                  "seconds": time.perf_counter() - t0})
+        self._log_exchange(head, mode, t0, ev0)
 
     def _route_special(self, head: Task, bits: int, nparts: int, out, typ) -> None:
         """A row with the reserved sentinel key: all ranks contribute their
@@ -354,6 +354,30 @@ class SpmdExecutor(LocalExecutor):
             tot = tot + x if op == "add" else (min(tot, x) if op == "min" else max(tot, x))
         out.setdefault(d, []).append(Frame([torch.tensor([key], device=self.device),
                                             torch.tensor([tot], dtype=vt, device=self.device)], typ))
+
+    def _cuda_event(self):
+        if self.device is not None and self.device.type == "cuda":
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record()
+            return ev
+        return None
+
+    def _log_exchange(self, head: Task, mode: str, t0: float, ev0, **kw) -> None:
+        """Record the exchange in the log and, device-timed with CUDA events,
+        in the session trace (pid = rank, category "exchange")."""
+        rec = {"group": str(head.name), "mode": mode, "seconds": time.perf_counter() - t0}
+        rec.update(kw)
+        if ev0 is not None:
+            ev1 = torch.cuda.Event(enable_timing=True)
+            ev1.record()
+            ev1.synchronize()
+            rec["device_ms"] = ev0.elapsed_time(ev1)
+        self.exchange_log.append(rec)
+        if self.tracer is not None:
+            now = self.tracer._now_us()
+            dur = int(rec.get("device_ms", rec["seconds"] * 1e3) * 1e3)
+            self.tracer.complete(self._pid(), "exchange:%s[%s]" % (head.name, mode), now - dur, dur,
+                                 cat="exchange", rows_in=kw.get("rows_in", 0))
 
     def _fused_ok(self, f: Frame, head: Task, nparts: int) -> bool:
         from ..parallel import peer
