@@ -123,8 +123,36 @@ def split_by_partition(f: Frame, ids: torch.Tensor, npart: int) -> List[Frame]:
     return out
 
 
+class _StoredBuffer:
+    """Task output parked in a Store (files) instead of memory."""
+
+    def __init__(self, store, task: Task, buf: TaskBuffer, device):
+        self.store, self.name, self.typ, self.device = store, task.name, task.type.typ, device
+        self.npart = len(buf.parts)
+        self.nrows = buf.nrows
+        for p, frames in enumerate(buf.parts):
+            w = store.create(task.name, p)
+            try:
+                for f in frames:
+                    w.write(f.to("cpu") if f.device.type != "cpu" else f)
+                w.commit()
+            except BaseException:
+                w.discard()
+                raise
+        self.parts = [[] for _ in range(self.npart)]  # nothing resident
+
+    def reader(self, partition: int) -> Reader:
+        from ..sliceio import RetryReader
+        return RetryReader(lambda off: self.store.open(self.name, partition, self.typ, off, self.device))
+
+    def discard(self):
+        for p in range(self.npart):
+            self.store.discard(self.name, p)
+
+
 class LocalExecutor(Executor):
-    def __init__(self, parallelism: int = 1, device=None):
+    def __init__(self, parallelism: int = 1, device=None, store=None):
+        self.store = store
         self.parallelism = max(1, int(parallelism))
         self.device = torch.device(device) if device is not None else None
         self.limiter = _Limiter(self.parallelism)
@@ -213,6 +241,12 @@ class LocalExecutor(Executor):
                     r.close()
                 except Exception:
                     pass
+        if self.store is not None and task.num_out() > 0:
+            try:
+                buf = _StoredBuffer(self.store, task, buf, self.device)
+            except BaseException as e:  # storage trouble is not an application error
+                task.set(TaskState.LOST)
+                return
         with self.lock:
             self.buffers[id(task)] = buf
         task.set(TaskState.OK)
@@ -298,7 +332,9 @@ class LocalExecutor(Executor):
         if task.combine_key:
             return  # shared-combiner tasks are not individually discardable
         with self.lock:
-            self.buffers.pop(id(task), None)
+            buf = self.buffers.pop(id(task), None)
+        if isinstance(buf, _StoredBuffer):
+            buf.discard()
         if task.state() == TaskState.OK:
             task.set(TaskState.LOST)
 

@@ -287,4 +287,56 @@ class Rebatch(Reader):
         self.reader.close()
 
 
+class RetryReader(Reader):
+    """Re-opens the stream at the current row offset when a read fails.
+
+    ``opener(offset_rows) -> Reader``.  Failures are retried with exponential
+    backoff up to ``retries`` times per incident (reference ``retryReader``,
+    ``exec/bigmachine.go:1332-1402``: 5 tries, backoff x2).  Fatal errors and
+    integrity errors are not retried."""
+
+    def __init__(self, opener: Callable[[int], Reader], retries: int = 5,
+                 backoff: float = 0.01, max_backoff: float = 1.0):
+        self.opener = opener
+        self.retries, self.backoff, self.max_backoff = retries, backoff, max_backoff
+        self.offset = 0
+        self.r: Optional[Reader] = None
+        self.reopens = 0
+
+    def read(self, n=None):
+        import time
+        from .. import errors
+        tries, delay = 0, self.backoff
+        while True:
+            try:
+                if self.r is None:
+                    self.r = self.opener(self.offset)
+                f = self.r.read(n)
+                if f is not None:
+                    self.offset += len(f)
+                return f
+            except BaseException as e:
+                if errors.is_fatal(e) or errors.is_kind(e, errors.Kind.Integrity) \
+                        or errors.is_kind(e, errors.Kind.NotExist) or isinstance(e, (KeyboardInterrupt,)):
+                    raise
+                tries += 1
+                if tries > self.retries:
+                    raise errors.Error("read failed after %d retries" % self.retries,
+                                       errors.Kind.TooManyTries, cause=e)
+                if self.r is not None:
+                    try:
+                        self.r.close()
+                    except Exception:
+                        pass
+                    self.r = None
+                self.reopens += 1
+                time.sleep(delay)
+                delay = min(delay * 2, self.max_backoff)
+
+    def close(self):
+        if self.r is not None:
+            self.r.close()
+            self.r = None
+
+
 ReadAll, ReadFull = read_all, read_full
