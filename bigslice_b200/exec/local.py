@@ -202,7 +202,8 @@ class LocalExecutor(Executor):
     def _pid(self):
         return "local"
 
-    def _run(self, task: Task) -> None:
+    def _run(self, task: Task, device=None) -> None:
+        device = device if device is not None else self.device
         try:
             ins = self.dep_readers(task)
         except errors.TaskLostError:
@@ -216,7 +217,7 @@ class LocalExecutor(Executor):
             return
         task.set(TaskState.RUNNING)
         task.scope.reset()
-        ctx = slicefunc.Context(task.scope, task.name.shard, self.device)
+        ctx = slicefunc.Context(task.scope, task.name.shard, device)
         try:
             with _context.use(ctx):
                 out = task.do(ins)
@@ -231,6 +232,10 @@ class LocalExecutor(Executor):
                 task.set(TaskState.LOST)
             return
         except BaseException as e:
+            if self.is_device_error(e):
+                self.last_device_error = e
+                task.set(TaskState.LOST)
+                return
             # A panic in user code is an application error: fatal.
             tb = traceback.format_exc()
             task.error(errors.fatal("panic while evaluating slice: %s\n%s" % (e, tb), e))
@@ -250,6 +255,18 @@ class LocalExecutor(Executor):
         with self.lock:
             self.buffers[id(task)] = buf
         task.set(TaskState.OK)
+
+    last_device_error: Optional[BaseException] = None
+
+    @staticmethod
+    def is_device_error(e: BaseException) -> bool:
+        """Failures of the device rather than of the program: the task is LOST
+        (retried, possibly elsewhere), not failed."""
+        if isinstance(e, torch.cuda.OutOfMemoryError):
+            return True
+        msg = str(e)
+        return isinstance(e, RuntimeError) and ("CUDA error" in msg or "cudaError" in msg
+                                                or "device-side assert" in msg)
 
     def dep_readers(self, task: Task) -> List[Reader]:
         """Readers for every dependency (expanded deps contribute one reader
