@@ -155,6 +155,8 @@ class LocalExecutor(Executor):
         self.store = store
         self.parallelism = max(1, int(parallelism))
         self.device = torch.device(device) if device is not None else None
+        if self.device is not None and self.device.type == "cuda" and self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
         self.limiter = _Limiter(self.parallelism)
         self.lock = threading.Lock()
         self.buffers: Dict[int, TaskBuffer] = {}
@@ -180,9 +182,9 @@ class LocalExecutor(Executor):
         procs = task.pragma.procs()
         if task.pragma.exclusive():
             procs = self.parallelism
-        self.limiter.acquire(procs)
         if self.device is not None and self.device.type == "cuda":
             torch.cuda.set_device(self.device)  # CUDA's current device is per thread
+        self.limiter.acquire(procs)
         if self.tracer is not None:
             self.tracer.event(self._pid(), task, "B")
         try:

@@ -310,8 +310,8 @@ class SpmdExecutor(LocalExecutor):
             sent = len(k)
             mode = "table-local"
         else:
-            got = self.peers.exchange([table.keys, table.vals], nparts, nkeys=1, skip_empty=True,
-                                      zero_copy=True)
+            got = self.peers.exchange_raw(table.column_desc(), table.cap, nparts, nkeys=1,
+                                          skip_empty=True, zero_copy=True, keep=table)
             st = table.status.tolist()
             if st[0]:
                 raise errors.fatal("spmd: combine table overflow (%d rows); cardinality hint too low" % st[0])

@@ -165,39 +165,46 @@ def partition_frame(f: Frame, ids: torch.Tensor, npart: int) -> List[Frame]:
 # ---------------------------------------------------------------- hash combine
 
 class HashTable:
-    """HBM open-addressing table used by the combine kernels."""
+    """HBM open-addressing table used by the combine kernels.
+
+    Array-of-structs: ``slots[cap, 2]`` int64 — column 0 the key, column 1 the
+    value bits — so a probe touches one 32-byte sector."""
 
     def __init__(self, capacity: int, vdtype: torch.dtype, op: str, device):
-        lib = require()
+        require()
         cap = 1
         while cap < max(capacity, 1024):
             cap <<= 1
         self.cap, self.vdtype, self.op, self.device = cap, vdtype, op, device
-        self.keys = torch.empty(cap, dtype=torch.int64, device=device)
-        self.vals = torch.empty(cap, dtype=vdtype, device=device)
+        self.slots = torch.empty((cap, 2), dtype=torch.int64, device=device)
         self.status = torch.zeros(4, dtype=torch.int64, device=device)
         self.reset()
 
     def reset(self):
-        _chk(_lib.bs_table_init(_ptr(self.keys), _ptr(self.vals), c_ll(self.cap),
-                                c_int(VTYPE[self.vdtype]), c_int(OPS[self.op]), _ptr(self.status),
-                                _stream()), "table_init")
+        _chk(_lib.bs_table_init(_ptr(self.slots), c_ll(self.cap), c_int(VTYPE[self.vdtype]),
+                                c_int(OPS[self.op]), _ptr(self.status), _stream()), "table_init")
 
     def combine(self, keys: torch.Tensor, vals: torch.Tensor, force_simple: bool = False):
         keys, vals = keys.contiguous(), vals.contiguous()
         _chk(_lib.bs_hash_combine(_ptr(keys), _ptr(vals), c_ll(keys.numel()),
-                                  c_int(VTYPE[self.vdtype]), c_int(OPS[self.op]), _ptr(self.keys),
-                                  _ptr(self.vals), c_ll(self.cap), _ptr(self.status),
+                                  c_int(VTYPE[self.vdtype]), c_int(OPS[self.op]), _ptr(self.slots),
+                                  c_ll(self.cap), _ptr(self.status),
                                   c_int(1 if force_simple else 0), _stream()), "hash_combine")
+
+    def column_desc(self):
+        """(ptr, row_bytes, stride, dtype, tail) of the key and value fields for
+        PeerGroup.exchange_raw (shuffle the table in place, skipping EMPTY)."""
+        p = self.slots.data_ptr()
+        vb = torch.empty(0, dtype=self.vdtype).element_size()
+        return [(p, 8, 16, torch.int64, ()), (p + 8, vb, 16, self.vdtype, ())]
 
     def compact(self, max_rows: Optional[int] = None) -> Tuple[torch.Tensor, torch.Tensor]:
         """Dense (keys, vals) of the occupied slots; syncs once for the count."""
         cap_out = self.cap + 1 if max_rows is None else max_rows
         ok = torch.empty(cap_out, dtype=torch.int64, device=self.device)
         ov = torch.empty(cap_out, dtype=self.vdtype, device=self.device)
-        _chk(_lib.bs_table_compact(_ptr(self.keys), _ptr(self.vals), c_ll(self.cap),
-                                   c_int(VTYPE[self.vdtype]), _ptr(ok), _ptr(ov), _ptr(self.status),
-                                   _stream()), "table_compact")
+        _chk(_lib.bs_table_compact(_ptr(self.slots), c_ll(self.cap), c_int(VTYPE[self.vdtype]),
+                                   _ptr(ok), _ptr(ov), _ptr(self.status), _stream()), "table_compact")
         st = self.status.tolist()
         if st[0]:
             raise TableFull(st[0])

@@ -38,7 +38,7 @@ class XcPeers(ctypes.Structure):
 class XcSpec(ctypes.Structure):
     _fields_ = [("n", c_ll), ("nparts", c_int), ("ncols", c_int), ("nkeys", c_int),
                 ("skip_empty", c_int), ("ids", c_void_p), ("cols", c_void_p * MAXC),
-                ("es", c_int * MAXC)]
+                ("es", c_int * MAXC), ("stride", c_int * MAXC)]
 
 
 class _DevMem:
@@ -147,18 +147,28 @@ class PeerGroup:
             raise ExchangeError("exchange shape outside fused-kernel limits")
         cols = [c.contiguous() for c in cols]
         n = int(cols[0].shape[0]) if cols else 0
+        desc = []
+        for c in cols:
+            rb = c.element_size() * (c.numel() // c.shape[0] if c.shape[0] else
+                                     int(np.prod(c.shape[1:])) if c.dim() > 1 else 1)
+            desc.append((c.data_ptr(), rb, rb, c.dtype, tuple(c.shape[1:])))
+        return self.exchange_raw(desc, n, nparts, nkeys, ids, skip_empty, zero_copy, keep=cols)
+
+    def exchange_raw(self, desc, n: int, nparts: int, nkeys: int = 1,
+                     ids: Optional[torch.Tensor] = None, skip_empty: bool = False,
+                     zero_copy: bool = False, keep=None) -> Dict[int, List[torch.Tensor]]:
+        """Exchange columns described as ``(ptr, row_bytes, stride_bytes, dtype,
+        tail_shape)`` — lets strided views (the key/value fields of a hash-table
+        slot array) be shuffled without materialising them."""
         spec = XcSpec()
-        spec.n, spec.nparts, spec.ncols, spec.nkeys = n, nparts, len(cols), nkeys
+        spec.n, spec.nparts, spec.ncols, spec.nkeys = n, nparts, len(desc), nkeys
         spec.skip_empty = 1 if skip_empty else 0
         if ids is not None:
             ids = ids.to(torch.int64).contiguous()
             spec.ids = ids.data_ptr()
         row_bytes = []
-        for i, c in enumerate(cols):
-            spec.cols[i] = c.data_ptr()
-            rb = c.element_size() * (c.numel() // c.shape[0] if c.shape[0] else
-                                     int(np.prod(c.shape[1:])) if c.dim() > 1 else 1)
-            spec.es[i] = rb
+        for i, (ptr, rb, stride, dt, tail) in enumerate(desc):
+            spec.cols[i], spec.es[i], spec.stride[i] = ptr, rb, stride
             row_bytes.append(rb)
         if ids is None:
             for k in range(nkeys):
@@ -185,10 +195,10 @@ class PeerGroup:
         for d in range(self.rank, nparts, self.world):
             rows = int(recv_total[d])
             got = []
-            for i, c in enumerate(cols):
-                nb = rows * row_bytes[i]
+            for i, (ptr, rb, stride, dt, tail) in enumerate(desc):
+                nb = rows * rb
                 view = self.arena_view[int(recv_off[d, i]):int(recv_off[d, i]) + nb]
-                t = view.view(c.dtype).reshape((rows,) + tuple(c.shape[1:]))
+                t = view.view(dt).reshape((rows,) + tuple(tail))
                 got.append(t if zero_copy else t.clone())
             out[d] = got
         if not zero_copy:

@@ -61,6 +61,8 @@ struct XcSpec {
   const long long* ids;              // optional explicit destination per row
   const unsigned char* cols[XC_MAXC];
   int es[XC_MAXC];                   // bytes per row of each column
+  int stride[XC_MAXC];               // bytes between consecutive rows (== es when dense);
+                                     // larger for columns interleaved in a hash-table slot
 };
 
 // Per-exchange plan, written by xchg_plan, read by xchg_scatter and the host.
@@ -81,14 +83,15 @@ __device__ __forceinline__ int xc_dest(const XcSpec& sp, long long i) {
 #pragma unroll
   for (int k = 0; k < XC_MAXK; ++k) {
     if (k < sp.nkeys) {
-      if (sp.es[k] == 8) h ^= bs_murmur3_u64(((const uint64_t*)sp.cols[k])[i], 0u);
-      else h ^= bs_murmur3_u32(((const uint32_t*)sp.cols[k])[i], 0u);
+      const unsigned char* p = sp.cols[k] + (size_t)i * sp.stride[k];
+      if (sp.es[k] == 8) h ^= bs_murmur3_u64(*(const uint64_t*)p, 0u);
+      else h ^= bs_murmur3_u32(*(const uint32_t*)p, 0u);
     }
   }
   return (int)(h % (uint32_t)sp.nparts);
 }
 __device__ __forceinline__ bool xc_valid(const XcSpec& sp, long long i) {
-  return !sp.skip_empty || ((const long long*)sp.cols[0])[i] != BS_EMPTY_KEY;
+  return !sp.skip_empty || *(const long long*)(sp.cols[0] + (size_t)i * sp.stride[0]) != BS_EMPTY_KEY;
 }
 
 // ---------------------------------------------------------------------------
@@ -192,6 +195,7 @@ __device__ __forceinline__ void xc_move_column(const XcSpec& sp, const XcPlan* p
                                                unsigned char* stage) {
   constexpr int PER = XC_TILE / XC_THREADS;
   const int es = sp.es[c];
+  const int stride = sp.stride[c];
   const int nchunk = es / VW;
   for (int q = 0; q < nchunk; ++q) {
     // stage this chunk of the column in destination-sorted order
@@ -200,7 +204,7 @@ __device__ __forceinline__ void xc_move_column(const XcSpec& sp, const XcPlan* p
       int r = threadIdx.x + j * XC_THREADS;
       if (r < rows && sortpos[j] >= 0)
         xc_copy_chunk<VW>(stage + (size_t)sortpos[j] * VW,
-                          sp.cols[c] + (size_t)(row0 + r) * es + (size_t)q * VW);
+                          sp.cols[c] + (size_t)(row0 + r) * stride + (size_t)q * VW);
     }
     __syncthreads();
     const int nsorted = segstart[sp.nparts];
@@ -281,11 +285,12 @@ __global__ void __launch_bounds__(XC_THREADS) xchg_scatter_kernel(XcPeers pe, Xc
       __syncthreads();
       for (int c = 0; c < sp.ncols; ++c) {
         const int es = sp.es[c];
-        const bool a16 = ((uintptr_t)sp.cols[c] & 15) == 0;
+        const uintptr_t al = (uintptr_t)sp.cols[c] | (uintptr_t)sp.stride[c];
+        const bool a16 = (al & 15) == 0;
         if (es % 16 == 0 && a16) xc_move_column<16>(sp, plan, c, row0, rows, sortpos, pos_dest, segstart, base, stage);
-        else if (es % 8 == 0) xc_move_column<8>(sp, plan, c, row0, rows, sortpos, pos_dest, segstart, base, stage);
-        else if (es % 4 == 0) xc_move_column<4>(sp, plan, c, row0, rows, sortpos, pos_dest, segstart, base, stage);
-        else if (es % 2 == 0) xc_move_column<2>(sp, plan, c, row0, rows, sortpos, pos_dest, segstart, base, stage);
+        else if (es % 8 == 0 && (al & 7) == 0) xc_move_column<8>(sp, plan, c, row0, rows, sortpos, pos_dest, segstart, base, stage);
+        else if (es % 4 == 0 && (al & 3) == 0) xc_move_column<4>(sp, plan, c, row0, rows, sortpos, pos_dest, segstart, base, stage);
+        else if (es % 2 == 0 && (al & 1) == 0) xc_move_column<2>(sp, plan, c, row0, rows, sortpos, pos_dest, segstart, base, stage);
         else xc_move_column<1>(sp, plan, c, row0, rows, sortpos, pos_dest, segstart, base, stage);
       }
     }
@@ -413,6 +418,8 @@ BS_EXPORT int bs_xc_exchange(const void* peers_h, const void* spec_h, void* plan
                              cudaStream_t stream) {
   XcPeers pe = *(const XcPeers*)peers_h;
   XcSpec sp = *(const XcSpec*)spec_h;
+  for (int c = 0; c < XC_MAXC; ++c)
+    if (sp.stride[c] == 0) sp.stride[c] = sp.es[c];
   if (pe.world > XC_MAXW || sp.nparts > XC_MAXP || sp.ncols > XC_MAXC || sp.nkeys > XC_MAXK) return -1;
   XcPlan* plan = (XcPlan*)plan_d;
   cudaError_t e = cudaMemsetAsync(plan, 0, sizeof(XcPlan), stream);

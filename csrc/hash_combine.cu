@@ -18,6 +18,7 @@
 // of worker.runCombine (exec/bigmachine.go:1144-1209).
 #include "common.cuh"
 #include <type_traits>
+#include <string.h>
 
 struct BsCombineStatus {
   unsigned long long failed;      // rows that found no slot (table too small)
@@ -99,107 +100,127 @@ struct Combine<double, OP> {
   }
 };
 
-// ---- table init -------------------------------------------------------------
+// ---- HBM table: array-of-structs, one 16-byte slot per key ------------------
+// A probe touches a single 32-byte sector (key + value together), so a miss in
+// the shared-memory table costs one DRAM line instead of two.
+struct __align__(16) BsSlot {
+  long long key;
+  unsigned long long val;  // the value's bits live in the low sizeof(V) bytes
+};
+
+template <typename V>
+__device__ __forceinline__ V* slot_val(BsSlot* s) { return (V*)&s->val; }
+
 template <typename V, int OP>
-__global__ void __launch_bounds__(256) table_init_kernel(long long* __restrict__ tkeys,
-                                                         V* __restrict__ tvals, long long cap) {
+__global__ void __launch_bounds__(256) table_init_kernel(BsSlot* __restrict__ tab, long long cap) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   long long stride = (long long)gridDim.x * blockDim.x;
   V id = Combine<V, OP>::identity();
+  unsigned long long bits = 0;
+  memcpy(&bits, &id, sizeof(V));
   for (; i < cap; i += stride) {
-    tkeys[i] = BS_EMPTY_KEY;
-    tvals[i] = id;
+    BsSlot s;
+    s.key = BS_EMPTY_KEY;
+    s.val = bits;
+    tab[i] = s;  // one 16-byte store
   }
 }
 
 // ---- HBM table insert -------------------------------------------------------
+// `cur` is the already-loaded key of the home slot (the caller batches those
+// loads so several probes are in flight per thread).
 template <typename V, int OP>
-__device__ __forceinline__ void table_insert(long long* __restrict__ tkeys, V* __restrict__ tvals,
-                                             unsigned long long mask, long long key, V val,
-                                             uint32_t h, BsCombineStatus* st) {
+__device__ __forceinline__ void table_resolve(BsSlot* __restrict__ tab, unsigned long long mask,
+                                              long long key, V val, uint32_t h, long long cur,
+                                              BsCombineStatus* st) {
   unsigned long long slot = (unsigned long long)h & mask;
   // Linear probing; bounded so a full table cannot hang the GPU.
   for (int probe = 0; probe < 4096; ++probe) {
-    long long cur = __ldcg(&tkeys[slot]);
     if (cur == key) {
-      Combine<V, OP>::apply(&tvals[slot], val);
+      Combine<V, OP>::apply(slot_val<V>(&tab[slot]), val);
       return;
     }
     if (cur == BS_EMPTY_KEY) {
-      long long prev = (long long)atomicCAS((unsigned long long*)&tkeys[slot],
+      long long prev = (long long)atomicCAS((unsigned long long*)&tab[slot].key,
                                             (unsigned long long)BS_EMPTY_KEY, (unsigned long long)key);
       if (prev == BS_EMPTY_KEY || prev == key) {
-        Combine<V, OP>::apply(&tvals[slot], val);
+        Combine<V, OP>::apply(slot_val<V>(&tab[slot]), val);
         return;
       }
     }
     slot = (slot + 1) & mask;
+    cur = __ldcg(&tab[slot].key);
   }
   atomicAdd(&st->failed, 1ULL);
 }
 
 template <typename V, int OP>
+__device__ __forceinline__ void table_insert(BsSlot* __restrict__ tab, unsigned long long mask,
+                                             long long key, V val, uint32_t h, BsCombineStatus* st) {
+  table_resolve<V, OP>(tab, mask, key, val, h, __ldcg(&tab[(unsigned long long)h & mask].key), st);
+}
+
+template <typename V, int OP>
 __device__ __forceinline__ void special_insert(V val, BsCombineStatus* st) {
-  // The reserved EMPTY key itself: combined in a dedicated status slot.
-  if (atomicCAS(&st->has_special, 0ULL, 1ULL) == 0ULL) {
-    // first writer initialises to identity before combining
-  }
+  // The reserved EMPTY key itself: combined in a dedicated status slot
+  // (special_val starts at the identity, see bs_table_init).
+  atomicExch(&st->has_special, 1ULL);
   Combine<V, OP>::apply((V*)&st->special_val, val);
 }
 
-// ---- the combine kernel -------------------------------------------------------
-#define HC_CONSUMERS 512
-#define HC_THREADS (HC_CONSUMERS + 32)
-#define HC_TILE 2048
-#define HC_STAGES 3
-#define HC_SLOTS 4096  // shared hot-key table entries (power of two)
-
+// ---- shared-memory accumulators ------------------------------------------------
+// 64-bit shared atomics compile to CAS spin loops (ATOMS.CAST.SPIN.64); for the
+// common int64 sum the accumulator is split into two 32-bit words combined with
+// native ATOMS.ADD and a carry.
 template <typename V, int OP>
-__device__ __forceinline__ void combine_row(long long key, V val, long long* __restrict__ skeys,
-                                            V* __restrict__ svals, long long* __restrict__ tkeys,
-                                            V* __restrict__ tvals, unsigned long long mask,
-                                            BsCombineStatus* st) {
-  if (key == BS_EMPTY_KEY) {
-    special_insert<V, OP>(val, st);
-    return;
+struct SmemAcc {
+  __device__ static __forceinline__ void init(void* base, int s) { ((V*)base)[s] = Combine<V, OP>::identity(); }
+  __device__ static __forceinline__ void apply(void* base, int s, V v) { Combine<V, OP>::apply(&((V*)base)[s], v); }
+  __device__ static __forceinline__ V read(void* base, int s) { return ((V*)base)[s]; }
+};
+#define HC_SLOTS 4096  // shared hot-key table entries (power of two)
+template <>
+struct SmemAcc<long long, BS_ADD> {
+  __device__ static __forceinline__ void init(void* base, int s) {
+    ((unsigned int*)base)[s] = 0;
+    ((unsigned int*)base)[HC_SLOTS + s] = 0;
   }
-  uint32_t h = bs_mix_u64((uint64_t)key);
-  uint32_t s = (h >> 20) & (HC_SLOTS - 1);  // high bits: independent of the HBM slot bits
-  long long k0 = *(volatile long long*)&skeys[s];
-  if (k0 != key) {
-    if (k0 != BS_EMPTY_KEY) {
-      table_insert<V, OP>(tkeys, tvals, mask, key, val, h, st);
-      return;
-    }
-    long long prev = (long long)atomicCAS((unsigned long long*)&skeys[s],
-                                          (unsigned long long)BS_EMPTY_KEY, (unsigned long long)key);
-    if (prev != BS_EMPTY_KEY && prev != key) {
-      table_insert<V, OP>(tkeys, tvals, mask, key, val, h, st);
-      return;
-    }
+  __device__ static __forceinline__ void apply(void* base, int s, long long v) {
+    unsigned int lo = (unsigned int)v, hi = (unsigned int)((unsigned long long)v >> 32);
+    unsigned int old = atomicAdd(&((unsigned int*)base)[s], lo);
+    hi += ((unsigned int)(old + lo) < old) ? 1u : 0u;  // carry out of the low word
+    if (hi) atomicAdd(&((unsigned int*)base)[HC_SLOTS + s], hi);
   }
-  Combine<V, OP>::apply(&svals[s], val);
-}
+  __device__ static __forceinline__ long long read(void* base, int s) {
+    return (long long)(((unsigned long long)((unsigned int*)base)[HC_SLOTS + s] << 32) |
+                       ((unsigned int*)base)[s]);
+  }
+};
+
+// ---- the combine kernel -------------------------------------------------------
+#define HC_CONSUMERS 1024
+#define HC_THREADS (HC_CONSUMERS + 32)
+#define HC_ROWS 4
+#define HC_TILE (HC_CONSUMERS * HC_ROWS)
+#define HC_STAGES 2
 
 template <typename V, int OP>
 __global__ void __launch_bounds__(HC_THREADS, 1) hash_combine_tma_kernel(
     const long long* __restrict__ keys, const V* __restrict__ vals, long long n,
-    long long* __restrict__ tkeys, V* __restrict__ tvals, unsigned long long mask,
-    BsCombineStatus* __restrict__ st) {
+    BsSlot* __restrict__ tab, unsigned long long mask, BsCombineStatus* __restrict__ st) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   long long* stage_keys = (long long*)smem_raw;                                   // [STAGES][TILE]
   V* stage_vals = (V*)(smem_raw + (size_t)HC_STAGES * HC_TILE * sizeof(long long));  // [STAGES][TILE]
   long long* skeys = (long long*)((unsigned char*)stage_vals + (size_t)HC_STAGES * HC_TILE * sizeof(V));
-  V* svals = (V*)(skeys + HC_SLOTS);
-  uint64_t* full = (uint64_t*)(svals + HC_SLOTS);
+  void* sacc = (void*)(skeys + HC_SLOTS);  // HC_SLOTS * 8 bytes
+  uint64_t* full = (uint64_t*)((unsigned char*)sacc + (size_t)HC_SLOTS * 8);
   uint64_t* empty = full + HC_STAGES;
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31;
-  const V ident = Combine<V, OP>::identity();
   for (int s = tid; s < HC_SLOTS; s += HC_THREADS) {
     skeys[s] = BS_EMPTY_KEY;
-    svals[s] = ident;
+    SmemAcc<V, OP>::init(sacc, s);
   }
   if (tid == 0) {
     for (int s = 0; s < HC_STAGES; ++s) {
@@ -238,24 +259,55 @@ __global__ void __launch_bounds__(HC_THREADS, 1) hash_combine_tma_kernel(
       int rows = (int)(n - row0 < HC_TILE ? n - row0 : HC_TILE);
       const long long* sk = stage_keys + (size_t)s * HC_TILE;
       const V* sv = stage_vals + (size_t)s * HC_TILE;
-      long long k[HC_TILE / HC_CONSUMERS];
-      V v[HC_TILE / HC_CONSUMERS];
+      long long k[HC_ROWS];
+      V v[HC_ROWS];
 #pragma unroll
-      for (int j = 0; j < HC_TILE / HC_CONSUMERS; ++j) {
+      for (int j = 0; j < HC_ROWS; ++j) {
         int idx = tid + j * HC_CONSUMERS;
-        if (idx < rows) {
-          k[j] = sk[idx];
-          v[j] = sv[idx];
-        }
+        k[j] = idx < rows ? sk[idx] : 0;
+        v[j] = idx < rows ? sv[idx] : Combine<V, OP>::identity();
       }
       // stage drained into registers: hand the slot back before the atomics
       __syncwarp();
       if (lane == 0) bs_mbar_arrive(&empty[s]);
+      // --- phase A: shared-memory hot table ---
+      uint32_t h[HC_ROWS];
+      unsigned miss = 0;
 #pragma unroll
-      for (int j = 0; j < HC_TILE / HC_CONSUMERS; ++j) {
+      for (int j = 0; j < HC_ROWS; ++j) {
         int idx = tid + j * HC_CONSUMERS;
-        if (idx < rows) combine_row<V, OP>(k[j], v[j], skeys, svals, tkeys, tvals, mask, st);
+        if (idx >= rows) continue;
+        if (k[j] == BS_EMPTY_KEY) {
+          special_insert<V, OP>(v[j], st);
+          continue;
+        }
+        h[j] = bs_mix_u64((uint64_t)k[j]);
+        uint32_t sl = (h[j] >> 20) & (HC_SLOTS - 1);  // high bits: independent of the HBM slot bits
+        long long k0 = *(volatile long long*)&skeys[sl];
+        if (k0 != k[j]) {
+          if (k0 != BS_EMPTY_KEY) {
+            miss |= 1u << j;
+            continue;
+          }
+          long long prev = (long long)atomicCAS((unsigned long long*)&skeys[sl],
+                                                (unsigned long long)BS_EMPTY_KEY,
+                                                (unsigned long long)k[j]);
+          if (prev != BS_EMPTY_KEY && prev != k[j]) {
+            miss |= 1u << j;
+            continue;
+          }
+        }
+        SmemAcc<V, OP>::apply(sacc, (int)sl, v[j]);
       }
+      // --- phase B: issue all HBM probes of this thread back to back ---
+      long long cur[HC_ROWS];
+#pragma unroll
+      for (int j = 0; j < HC_ROWS; ++j)
+        cur[j] = (miss >> j) & 1u ? __ldcg(&tab[(unsigned long long)h[j] & mask].key) : 0;
+      // --- phase C: resolve ---
+#pragma unroll
+      for (int j = 0; j < HC_ROWS; ++j)
+        if ((miss >> j) & 1u) table_resolve<V, OP>(tab, mask, k[j], v[j], h[j], cur[j], st);
     }
   }
   __syncthreads();
@@ -263,7 +315,7 @@ __global__ void __launch_bounds__(HC_THREADS, 1) hash_combine_tma_kernel(
   for (int s = tid; s < HC_SLOTS; s += HC_THREADS) {
     long long key = skeys[s];
     if (key != BS_EMPTY_KEY)
-      table_insert<V, OP>(tkeys, tvals, mask, key, svals[s], bs_mix_u64((uint64_t)key), st);
+      table_insert<V, OP>(tab, mask, key, SmemAcc<V, OP>::read(sacc, s), bs_mix_u64((uint64_t)key), st);
   }
 }
 
@@ -272,8 +324,7 @@ __global__ void __launch_bounds__(HC_THREADS, 1) hash_combine_tma_kernel(
 template <typename V, int OP>
 __global__ void __launch_bounds__(512) hash_combine_simple_kernel(
     const long long* __restrict__ keys, const V* __restrict__ vals, long long n,
-    long long* __restrict__ tkeys, V* __restrict__ tvals, unsigned long long mask,
-    BsCombineStatus* __restrict__ st) {
+    BsSlot* __restrict__ tab, unsigned long long mask, BsCombineStatus* __restrict__ st) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   long long stride = (long long)gridDim.x * blockDim.x;
   for (; i < n; i += stride) {
@@ -283,36 +334,64 @@ __global__ void __launch_bounds__(512) hash_combine_simple_kernel(
       special_insert<V, OP>(val, st);
       continue;
     }
-    table_insert<V, OP>(tkeys, tvals, mask, key, val, bs_mix_u64((uint64_t)key), st);
+    table_insert<V, OP>(tab, mask, key, val, bs_mix_u64((uint64_t)key), st);
   }
 }
 
 // ---- compaction: table -> dense <key, value> ---------------------------------
+// One global atomic per 2048-slot chunk (block-aggregated), 16-byte coalesced
+// slot loads.  Output order is unspecified (as after any shuffle).
+#define TC_THREADS 256
+#define TC_ITEMS 8
 template <typename V>
-__global__ void __launch_bounds__(256) table_compact_kernel(const long long* __restrict__ tkeys,
-                                                            const V* __restrict__ tvals,
-                                                            long long cap,
-                                                            long long* __restrict__ out_keys,
-                                                            V* __restrict__ out_vals,
-                                                            BsCombineStatus* __restrict__ st) {
-  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  long long stride = (long long)gridDim.x * blockDim.x;
-  const int lane = threadIdx.x & 31;
-  // grid-stride over whole warps so the ballot is always convergent
-  long long limit = ((cap + 31) / 32) * 32;
-  for (; i < limit; i += stride) {
-    long long key = i < cap ? tkeys[i] : BS_EMPTY_KEY;
-    bool occ = key != BS_EMPTY_KEY;
-    unsigned m = __ballot_sync(0xffffffffu, occ);
-    if (m == 0) continue;
-    unsigned long long base = 0;
-    if (lane == 0) base = atomicAdd(&st->out_count, (unsigned long long)__popc(m));
-    base = __shfl_sync(0xffffffffu, base, 0);
-    if (occ) {
-      unsigned long long o = base + __popc(m & ((1u << lane) - 1));
-      out_keys[o] = key;
-      out_vals[o] = tvals[i];
+__global__ void __launch_bounds__(TC_THREADS) table_compact_kernel(const BsSlot* __restrict__ tab,
+                                                                   long long cap,
+                                                                   long long* __restrict__ out_keys,
+                                                                   V* __restrict__ out_vals,
+                                                                   BsCombineStatus* __restrict__ st) {
+  __shared__ unsigned int wcnt[TC_ITEMS][TC_THREADS / 32];
+  __shared__ unsigned long long chunk_base;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long chunk = (long long)TC_THREADS * TC_ITEMS;
+  const long long nchunks = (cap + chunk - 1) / chunk;
+  for (long long c = blockIdx.x; c < nchunks; c += gridDim.x) {
+    BsSlot sl[TC_ITEMS];
+    unsigned bal[TC_ITEMS];
+#pragma unroll
+    for (int j = 0; j < TC_ITEMS; ++j) {
+      long long i = c * chunk + (long long)j * TC_THREADS + threadIdx.x;
+      if (i < cap) {
+        const int4 raw = *(const int4*)&tab[i];
+        memcpy(&sl[j], &raw, 16);
+      } else {
+        sl[j].key = BS_EMPTY_KEY;
+      }
+      bal[j] = __ballot_sync(0xffffffffu, sl[j].key != BS_EMPTY_KEY);
+      if (lane == 0) wcnt[j][warp] = __popc(bal[j]);
     }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      unsigned run = 0;
+      for (int j = 0; j < TC_ITEMS; ++j)
+        for (int w = 0; w < TC_THREADS / 32; ++w) {
+          unsigned t = wcnt[j][w];
+          wcnt[j][w] = run;
+          run += t;
+        }
+      chunk_base = run ? atomicAdd(&st->out_count, (unsigned long long)run) : 0ULL;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < TC_ITEMS; ++j) {
+      if (sl[j].key != BS_EMPTY_KEY) {
+        unsigned long long o = chunk_base + wcnt[j][warp] + __popc(bal[j] & ((1u << lane) - 1u));
+        out_keys[o] = sl[j].key;
+        V vv;
+        memcpy(&vv, &sl[j].val, sizeof(V));
+        out_vals[o] = vv;
+      }
+    }
+    __syncthreads();
   }
   if (blockIdx.x == 0 && threadIdx.x == 0 && st->has_special) {
     unsigned long long o = atomicAdd(&st->out_count, 1ULL);
@@ -325,13 +404,12 @@ __global__ void __launch_bounds__(256) table_compact_kernel(const long long* __r
 template <typename V>
 static size_t hc_smem_bytes() {
   return (size_t)HC_STAGES * HC_TILE * (sizeof(long long) + sizeof(V)) +
-         (size_t)HC_SLOTS * (sizeof(long long) + sizeof(V)) + 2 * HC_STAGES * sizeof(uint64_t) + 16;
+         (size_t)HC_SLOTS * (sizeof(long long) + 8) + 2 * HC_STAGES * sizeof(uint64_t) + 16;
 }
 
 template <typename V, int OP>
-static int launch_combine(const long long* keys, const V* vals, long long n, long long* tkeys,
-                          V* tvals, long long cap, BsCombineStatus* st, int force_simple,
-                          cudaStream_t stream) {
+static int launch_combine(const long long* keys, const V* vals, long long n, BsSlot* tab,
+                          long long cap, BsCombineStatus* st, int force_simple, cudaStream_t stream) {
   if (n <= 0) return 0;
   unsigned long long mask = (unsigned long long)cap - 1;
   int sms = bs_num_sms();
@@ -351,8 +429,7 @@ static int launch_combine(const long long* keys, const V* vals, long long n, lon
     }
     long long ntiles = (n_main + HC_TILE - 1) / HC_TILE;
     int blocks = (int)(ntiles < sms ? ntiles : sms);
-    hash_combine_tma_kernel<V, OP><<<blocks, HC_THREADS, smem, stream>>>(keys, vals, n_main, tkeys,
-                                                                         tvals, mask, st);
+    hash_combine_tma_kernel<V, OP><<<blocks, HC_THREADS, smem, stream>>>(keys, vals, n_main, tab, mask, st);
     BS_LAUNCH_CHECK();
   }
   long long rest = n - n_main;
@@ -360,7 +437,7 @@ static int launch_combine(const long long* keys, const V* vals, long long n, lon
     long long want = (rest + 511) / 512;
     int blocks = (int)(want < (long long)sms * 4 ? want : (long long)sms * 4);
     hash_combine_simple_kernel<V, OP><<<blocks, 512, 0, stream>>>(keys + n_main, vals + n_main, rest,
-                                                                  tkeys, tvals, mask, st);
+                                                                  tab, mask, st);
     BS_LAUNCH_CHECK();
   }
   return 0;
@@ -384,18 +461,15 @@ static int launch_combine(const long long* keys, const V* vals, long long n, lon
   }
 
 template <typename V, int OP>
-static int launch_init(long long* tkeys, void* tvals, long long cap, BsCombineStatus* st,
-                       cudaStream_t stream) {
+static int launch_init(void* tab, long long cap, BsCombineStatus* st, cudaStream_t stream) {
   int blocks = (int)((cap + 255) / 256 < (long long)bs_num_sms() * 8 ? (cap + 255) / 256
                                                                     : (long long)bs_num_sms() * 8);
-  table_init_kernel<V, OP><<<blocks, 256, 0, stream>>>(tkeys, (V*)tvals, cap);
+  table_init_kernel<V, OP><<<blocks, 256, 0, stream>>>((BsSlot*)tab, cap);
   BS_LAUNCH_CHECK();
   BsCombineStatus z;
   z.failed = 0;
   z.has_special = 0;
   z.out_count = 0;
-  V id = OP == BS_ADD ? (V)0 : (V)0;
-  (void)id;
   // special_val starts at the identity bit pattern
   unsigned long long bits = 0;
   if (OP == BS_MIN) {
@@ -410,38 +484,38 @@ static int launch_init(long long* tkeys, void* tvals, long long cap, BsCombineSt
   return (int)e;
 }
 
-BS_EXPORT int bs_table_init(long long* tkeys, void* tvals, long long cap, int vtype, int op,
-                            void* status, cudaStream_t stream) {
+// `tab` is cap x 16 bytes (BsSlot); cap must be a power of two.
+BS_EXPORT int bs_table_init(void* tab, long long cap, int vtype, int op, void* status,
+                            cudaStream_t stream) {
   if (cap <= 0 || (cap & (cap - 1))) return -2;
-  DISPATCH_VOP(launch_init, tkeys, tvals, cap, (BsCombineStatus*)status, stream)
+  DISPATCH_VOP(launch_init, tab, cap, (BsCombineStatus*)status, stream)
 }
 
 template <typename V, int OP>
-static int combine_entry(const long long* keys, const void* vals, long long n, long long* tkeys,
-                         void* tvals, long long cap, void* st, int force_simple,
-                         cudaStream_t stream) {
-  return launch_combine<V, OP>(keys, (const V*)vals, n, tkeys, (V*)tvals, cap, (BsCombineStatus*)st,
+static int combine_entry(const long long* keys, const void* vals, long long n, void* tab,
+                         long long cap, void* st, int force_simple, cudaStream_t stream) {
+  return launch_combine<V, OP>(keys, (const V*)vals, n, (BsSlot*)tab, cap, (BsCombineStatus*)st,
                                force_simple, stream);
 }
 
 BS_EXPORT int bs_hash_combine(const long long* keys, const void* vals, long long n, int vtype, int op,
-                              long long* tkeys, void* tvals, long long cap, void* status,
-                              int force_simple, cudaStream_t stream) {
+                              void* tab, long long cap, void* status, int force_simple,
+                              cudaStream_t stream) {
   if (cap <= 0 || (cap & (cap - 1))) return -2;
-  DISPATCH_VOP(combine_entry, keys, vals, n, tkeys, tvals, cap, status, force_simple, stream)
+  DISPATCH_VOP(combine_entry, keys, vals, n, tab, cap, status, force_simple, stream)
 }
 
-BS_EXPORT int bs_table_compact(const long long* tkeys, const void* tvals, long long cap, int vtype,
-                               long long* out_keys, void* out_vals, void* status,
-                               cudaStream_t stream) {
-  int blocks = (int)((cap + 255) / 256 < (long long)bs_num_sms() * 8 ? (cap + 255) / 256
-                                                                    : (long long)bs_num_sms() * 8);
+BS_EXPORT int bs_table_compact(const void* tab, long long cap, int vtype, long long* out_keys,
+                               void* out_vals, void* status, cudaStream_t stream) {
+  long long nchunks = (cap + (long long)TC_THREADS * TC_ITEMS - 1) / ((long long)TC_THREADS * TC_ITEMS);
+  int blocks = (int)(nchunks < (long long)bs_num_sms() * 8 ? nchunks : (long long)bs_num_sms() * 8);
   BsCombineStatus* st = (BsCombineStatus*)status;
+  const BsSlot* t = (const BsSlot*)tab;
   switch (vtype) {
-    case BS_I32: table_compact_kernel<int><<<blocks, 256, 0, stream>>>(tkeys, (const int*)tvals, cap, out_keys, (int*)out_vals, st); break;
-    case BS_I64: table_compact_kernel<long long><<<blocks, 256, 0, stream>>>(tkeys, (const long long*)tvals, cap, out_keys, (long long*)out_vals, st); break;
-    case BS_F32: table_compact_kernel<float><<<blocks, 256, 0, stream>>>(tkeys, (const float*)tvals, cap, out_keys, (float*)out_vals, st); break;
-    case BS_F64: table_compact_kernel<double><<<blocks, 256, 0, stream>>>(tkeys, (const double*)tvals, cap, out_keys, (double*)out_vals, st); break;
+    case BS_I32: table_compact_kernel<int><<<blocks, TC_THREADS, 0, stream>>>(t, cap, out_keys, (int*)out_vals, st); break;
+    case BS_I64: table_compact_kernel<long long><<<blocks, TC_THREADS, 0, stream>>>(t, cap, out_keys, (long long*)out_vals, st); break;
+    case BS_F32: table_compact_kernel<float><<<blocks, TC_THREADS, 0, stream>>>(t, cap, out_keys, (float*)out_vals, st); break;
+    case BS_F64: table_compact_kernel<double><<<blocks, TC_THREADS, 0, stream>>>(t, cap, out_keys, (double*)out_vals, st); break;
     default: return -1;
   }
   BS_LAUNCH_CHECK();

@@ -69,11 +69,8 @@ def test_partition_perm_and_frame(gpu, npart):
 
 
 def zipf_keys(n, vocab, seed):
-    rng = np.random.default_rng(seed)
-    w = 1.0 / np.arange(1, vocab + 1)
-    cdf = np.cumsum(w) / w.sum()
-    r = np.searchsorted(cdf, rng.random(n))
-    return torch.from_numpy((r.astype(np.int64) * 0x9E3779B97F4A7C15) & 0x7FFFFFFFFFFFFFFF)
+    from bigslice_b200.models.wordcount import zipf_keys as zk
+    return zk(n, vocab, 1.0, seed)
 
 
 @pytest.mark.parametrize("vdtype", [torch.int64, torch.int32, torch.float32, torch.float64])
