@@ -142,6 +142,7 @@ class Session:
         self._shutdown: Optional[Callable[[], None]] = None
         self._status_lock = threading.Lock()
         self._results: List["Result"] = []
+        self._pool: Optional[ThreadPoolExecutor] = None
 
     # -- lifecycle -----------------------------------------------------------
     def _start(self) -> None:
@@ -156,8 +157,21 @@ class Session:
         self.eventer_.event("bigslice:sessionStart", "executorType", self.executor.name(),
                             "parallelism", self.p, "maxLoad", self.max_load_)
 
+    def _eval_pool(self) -> ThreadPoolExecutor:
+        """Worker threads shared by all evaluations of this session (thread
+        start-up would otherwise dominate short invocations)."""
+        with self._lock:
+            if self._pool is None:
+                self._pool = ThreadPoolExecutor(max_workers=max(4, self.executor.max_workers()),
+                                                thread_name_prefix="bigslice-eval")
+            return self._pool
+
     def shutdown(self) -> None:
         """Release executor resources and write the trace if configured."""
+        with self._lock:
+            pool, self._pool = self._pool, None
+        if pool is not None:
+            pool.shutdown(wait=False)
         if self._shutdown is not None:
             s, self._shutdown = self._shutdown, None
             s()
@@ -240,7 +254,7 @@ class Session:
         if begin is not None:
             begin(tasks)
         try:
-            evaluate(self.executor, tasks, group)
+            evaluate(self.executor, tasks, group, pool=self._eval_pool())
         finally:
             log.debug("invocation %d (%s) evaluated in %.3fs", inv.index, location, time.time() - t0)
             if group is not None:

@@ -100,13 +100,23 @@ def col_take(c, idx):
         total = int(new_off[-1])
         if total == 0:
             return ListColumn(new_off, col_slice(c.values, 0, 0), c.child_dtype)
-        row_of = torch.repeat_interleave(torch.arange(idx.numel(), device=idx.device), lens)
+        row_of = _expand_rows(new_off, lens)
         within = torch.arange(total, device=idx.device) - new_off[:-1].index_select(0, row_of)
         src = starts.index_select(0, row_of) + within
         return ListColumn(new_off, col_take(c.values, src), c.child_dtype)
     if isinstance(idx, torch.Tensor):
         idx = idx.cpu().numpy()
     return c[np.asarray(idx, dtype=np.int64)]
+
+
+def _expand_rows(offsets: torch.Tensor, lens: torch.Tensor) -> torch.Tensor:
+    """Row id of every element of a ragged column given its offsets (the
+    sm_100a expansion kernel on device, repeat_interleave on host)."""
+    if offsets.is_cuda:
+        from ..ops import gpu
+        if gpu.available():
+            return gpu.expand_indices(offsets)
+    return torch.repeat_interleave(torch.arange(lens.numel(), device=lens.device), lens)
 
 
 def col_zeros(dt: DType, n: int, device=None):

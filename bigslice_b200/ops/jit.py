@@ -1,0 +1,399 @@
+"""NVRTC-compiled fused elementwise kernels for expression Maps and Filters.
+
+``MapExpr(slice, ["c0 % 1000", "c1 * 2"], out=[int64, int64])`` and
+``FilterExpr(slice, "c0 % 2 == 0")`` describe row functions as C expressions
+over the input columns ``c0, c1, ...``.  Consecutive expression stages that the
+compiler pipelines into one task are **fused into a single sm_100a kernel**:
+the chain is composed symbolically, compiled once with NVRTC
+(``--gpu-architecture=sm_100a``) into a cubin, cached by source, loaded through
+the driver API and launched on the current stream.  One pass over the tile
+evaluates every stage; a Filter anywhere in the chain makes the kernel emit a
+keep-mask that feeds the stream-compaction kernel.
+
+On executors without a GPU the same expressions are evaluated with torch ops
+under C semantics (truncating integer division/modulo), so results agree.
+
+This is tier (b) of the user-function model in SURVEY §7.3 (tier (a): builtin
+functors; tier (c): vectorised python callables) and replaces the per-row
+reflective calls of ``mapReader``/``filterReader`` (reference
+``slice.go:621-632,700-720``).
+"""
+from __future__ import annotations
+
+import ctypes
+import hashlib
+import re
+import threading
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+
+from .. import slicetype
+from ..slicetype import DType
+
+CTYPE = {"int8": "signed char", "int16": "short", "int32": "int", "int64": "long long",
+         "uint8": "unsigned char", "uint16": "unsigned short", "uint32": "unsigned int",
+         "uint64": "unsigned long long", "float32": "float", "float64": "double",
+         "bool": "bool"}
+
+_VAR = re.compile(r"\bc(\d+)\b")
+
+
+class Stage:
+    """One Map (``exprs``/``out``) or Filter (``pred``) step."""
+
+    def __init__(self, exprs: Optional[Sequence[str]] = None, out: Optional[Sequence[DType]] = None,
+                 pred: Optional[str] = None):
+        self.exprs = list(exprs) if exprs is not None else None
+        self.out = [slicetype.dtype_of(o) for o in out] if out is not None else None
+        self.pred = pred
+
+
+def check_types(dts: Sequence[DType]) -> None:
+    for d in dts:
+        if d.name not in CTYPE or d.kind == "vec":
+            raise TypeError("expression stages support scalar numeric/bool columns, not %s" % d)
+
+
+def generate(in_types: Sequence[DType], stages: Sequence[Stage]) -> Tuple[str, List[DType], bool]:
+    """CUDA source of the fused kernel, its output dtypes, and whether it has
+    a predicate."""
+    check_types(in_types)
+    cur = list(in_types)
+    body = []
+    names = ["v0_%d" % j for j in range(len(cur))]
+    for j, t in enumerate(cur):
+        body.append("    const %s v0_%d = in%d[i];" % (CTYPE[t.name], j, j))
+    preds = []
+    for s, st in enumerate(stages, 1):
+        def sub(expr, names=names):
+            def rep(m):
+                k = int(m.group(1))
+                if k >= len(names):
+                    raise ValueError("expression refers to c%d but the stage has %d columns" % (k, len(names)))
+                return names[k]
+            return _VAR.sub(rep, expr)
+        if st.pred is not None:
+            body.append("    const bool p%d = (%s);" % (s, sub(st.pred)))
+            preds.append("p%d" % s)
+        else:
+            check_types(st.out)
+            new = []
+            for j, (e, t) in enumerate(zip(st.exprs, st.out)):
+                body.append("    const %s v%d_%d = (%s)(%s);" % (CTYPE[t.name], s, j, CTYPE[t.name], sub(e)))
+                new.append("v%d_%d" % (s, j))
+            names, cur = new, list(st.out)
+    params = ["long long n"]
+    params += ["const %s* __restrict__ in%d" % (CTYPE[t.name], j) for j, t in enumerate(in_types)]
+    params += ["%s* __restrict__ out%d" % (CTYPE[t.name], j) for j, t in enumerate(cur)]
+    if preds:
+        params.append("unsigned char* __restrict__ keep")
+    for j, nm in enumerate(names):
+        body.append("    out%d[i] = %s;" % (j, nm))
+    if preds:
+        body.append("    keep[i] = (%s) ? 1 : 0;" % " && ".join(preds))
+    src = ("extern \"C\" __global__ void __launch_bounds__(256) bs_fused(%s) {\n"
+           "  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;\n"
+           "       i += (long long)gridDim.x * blockDim.x) {\n%s\n  }\n}\n"
+           % (", ".join(params), "\n".join(body)))
+    return src, cur, bool(preds)
+
+
+# ---------------------------------------------------------------------------
+# NVRTC (compile) and driver API (load/launch) through ctypes
+
+_nvrtc = None
+_cuda = None
+_cache: Dict[str, bytes] = {}
+_funcs: Dict[Tuple[int, str], ctypes.c_void_p] = {}
+_lock = threading.Lock()
+
+
+def _load_nvrtc():
+    global _nvrtc
+    if _nvrtc is None:
+        for name in ("libnvrtc.so", "libnvrtc.so.12", "/usr/local/cuda/lib64/libnvrtc.so"):
+            try:
+                _nvrtc = ctypes.CDLL(name)
+                break
+            except OSError:
+                continue
+        if _nvrtc is None:
+            raise RuntimeError("NVRTC (libnvrtc) not found")
+    return _nvrtc
+
+
+def compile_cubin(src: str, arch: str = "sm_100a") -> bytes:
+    """Compile CUDA source to a cubin for ``arch`` with NVRTC (cached)."""
+    key = hashlib.sha1((arch + src).encode()).hexdigest()
+    with _lock:
+        if key in _cache:
+            return _cache[key]
+    rt = _load_nvrtc()
+    prog = ctypes.c_void_p()
+    rc = rt.nvrtcCreateProgram(ctypes.byref(prog), src.encode(), b"bs_fused.cu", 0, None, None)
+    if rc != 0:
+        raise RuntimeError("nvrtcCreateProgram failed: %d" % rc)
+    opts = [b"--gpu-architecture=" + arch.encode(), b"-lineinfo", b"--std=c++17"]
+    arr = (ctypes.c_char_p * len(opts))(*opts)
+    rc = rt.nvrtcCompileProgram(prog, len(opts), arr)
+    if rc != 0:
+        n = ctypes.c_size_t()
+        rt.nvrtcGetProgramLogSize(prog, ctypes.byref(n))
+        log = ctypes.create_string_buffer(n.value)
+        rt.nvrtcGetProgramLog(prog, log)
+        rt.nvrtcDestroyProgram(ctypes.byref(prog))
+        raise RuntimeError("expression does not compile:\n%s\n--- source ---\n%s"
+                           % (log.value.decode(errors="replace"), src))
+    n = ctypes.c_size_t()
+    rt.nvrtcGetCUBINSize(prog, ctypes.byref(n))
+    buf = ctypes.create_string_buffer(n.value)
+    rt.nvrtcGetCUBIN(prog, buf)
+    rt.nvrtcDestroyProgram(ctypes.byref(prog))
+    cubin = buf.raw
+    with _lock:
+        _cache[key] = cubin
+    return cubin
+
+
+def _driver():
+    global _cuda
+    if _cuda is None:
+        _cuda = ctypes.CDLL("libcuda.so.1")
+    return _cuda
+
+
+def _function(src: str) -> ctypes.c_void_p:
+    dev = torch.cuda.current_device()
+    key = (dev, hashlib.sha1(src.encode()).hexdigest())
+    with _lock:
+        if key in _funcs:
+            return _funcs[key]
+    cubin = compile_cubin(src)
+    cu = _driver()
+    torch.cuda.current_stream()  # make sure the primary context exists and is current
+    mod = ctypes.c_void_p()
+    rc = cu.cuModuleLoadData(ctypes.byref(mod), cubin)
+    if rc != 0:
+        raise RuntimeError("cuModuleLoadData failed: %d" % rc)
+    fn = ctypes.c_void_p()
+    rc = cu.cuModuleGetFunction(ctypes.byref(fn), mod, b"bs_fused")
+    if rc != 0:
+        raise RuntimeError("cuModuleGetFunction failed: %d" % rc)
+    with _lock:
+        _funcs[key] = fn
+    return fn
+
+
+launch_count = 0
+
+
+def run_fused(cols: Sequence[torch.Tensor], in_types: Sequence[DType], stages: Sequence[Stage]):
+    """Launch the fused kernel over device columns; returns (outputs, mask)."""
+    global launch_count
+    src, out_types, has_pred = generate(in_types, stages)
+    fn = _function(src)
+    n = int(cols[0].shape[0]) if cols else 0
+    dev = cols[0].device
+    outs = [torch.empty(n, dtype=t.torch_dtype, device=dev) for t in out_types]
+    mask = torch.empty(n, dtype=torch.uint8, device=dev) if has_pred else None
+    if n == 0:
+        return outs, mask
+    cols = [c.contiguous() for c in cols]
+    args = [ctypes.c_longlong(n)] + [ctypes.c_void_p(c.data_ptr()) for c in cols] + \
+           [ctypes.c_void_p(o.data_ptr()) for o in outs]
+    if mask is not None:
+        args.append(ctypes.c_void_p(mask.data_ptr()))
+    argv = (ctypes.c_void_p * len(args))(*[ctypes.cast(ctypes.pointer(a), ctypes.c_void_p) for a in args])
+    sms = torch.cuda.get_device_properties(dev).multi_processor_count
+    blocks = min((n + 255) // 256, sms * 16)
+    rc = _driver().cuLaunchKernel(fn, blocks, 1, 1, 256, 1, 1, 0,
+                                  ctypes.c_void_p(torch.cuda.current_stream().cuda_stream), argv, None)
+    if rc != 0:
+        raise RuntimeError("cuLaunchKernel failed: %d" % rc)
+    launch_count += 1
+    return outs, mask
+
+
+# ---------------------------------------------------------------------------
+# host evaluation with C semantics: a small expression parser (C precedence,
+# casts, && || ! ?:, truncating integer / and %) evaluated with torch ops.
+
+_TOK = re.compile(r"\s*(?:(\d+\.\d*(?:[eE][-+]?\d+)?[fF]?|\.\d+[fF]?|\d+[eE][-+]?\d+[fF]?|\d+[uUlL]*)"
+                  r"|([A-Za-z_][A-Za-z_0-9]*)|(<<|>>|<=|>=|==|!=|&&|\|\||[-+*/%<>&|^~!?:(),]))")
+_CAST = {"int": torch.int32, "long": torch.int64, "float": torch.float32, "double": torch.float64,
+         "bool": torch.bool, "short": torch.int16, "char": torch.int8, "unsigned": torch.int64,
+         "signed": torch.int64}
+_BIN = [("||",), ("&&",), ("|",), ("^",), ("&",), ("==", "!="), ("<", "<=", ">", ">="),
+        ("<<", ">>"), ("+", "-"), ("*", "/", "%")]
+_FUNCS = {"abs": torch.abs, "fabs": torch.abs, "sqrt": torch.sqrt, "floor": torch.floor,
+          "ceil": torch.ceil, "exp": torch.exp, "log": torch.log,
+          "min": torch.minimum, "max": torch.maximum, "fmin": torch.minimum, "fmax": torch.maximum}
+
+
+def _tokens(expr: str):
+    out, pos = [], 0
+    expr = expr.strip()
+    while pos < len(expr):
+        m = _TOK.match(expr, pos)
+        if not m or m.end() == pos:
+            raise ValueError("cannot parse expression %r at %r" % (expr, expr[pos:]))
+        num, ident, op = m.groups()
+        out.append(("num", num) if num else ("id", ident) if ident else ("op", op))
+        pos = m.end()
+    return out
+
+
+class _Parser:
+    def __init__(self, expr: str, env: Dict[str, torch.Tensor], n: int, device):
+        self.toks, self.i, self.env, self.n, self.device = _tokens(expr), 0, env, n, device
+
+    def peek(self):
+        return self.toks[self.i] if self.i < len(self.toks) else (None, None)
+
+    def take(self, val=None):
+        t = self.peek()
+        if val is not None and t[1] != val:
+            raise ValueError("expected %r, got %r" % (val, t[1]))
+        self.i += 1
+        return t
+
+    def tensor(self, v):
+        if isinstance(v, torch.Tensor):
+            return v
+        return torch.full((self.n,), v, device=self.device)
+
+    def parse(self):
+        v = self.ternary()
+        if self.i != len(self.toks):
+            raise ValueError("unexpected %r" % (self.peek()[1],))
+        return v
+
+    def ternary(self):
+        c = self.binary(0)
+        if self.peek()[1] == "?":
+            self.take()
+            a = self.ternary()
+            self.take(":")
+            b = self.ternary()
+            return torch.where(self.tensor(c).bool(), self.tensor(a), self.tensor(b))
+        return c
+
+    def binary(self, level):
+        if level == len(_BIN):
+            return self.unary()
+        left = self.binary(level + 1)
+        while self.peek()[0] == "op" and self.peek()[1] in _BIN[level]:
+            op = self.take()[1]
+            right = self.binary(level + 1)
+            left = self.apply(op, left, right)
+        return left
+
+    def apply(self, op, a, b):
+        ta, tb = isinstance(a, torch.Tensor), isinstance(b, torch.Tensor)
+        if not ta and not tb:
+            a = self.tensor(a)
+            ta = True
+        isint = lambda x: (isinstance(x, torch.Tensor) and not x.is_floating_point()) or \
+            (not isinstance(x, torch.Tensor) and isinstance(x, (int, bool)))  # noqa: E731
+        if op == "||":
+            return self.tensor(a).bool() | self.tensor(b).bool()
+        if op == "&&":
+            return self.tensor(a).bool() & self.tensor(b).bool()
+        if op == "/":
+            if isint(a) and isint(b):
+                return torch.div(self.tensor(a), b, rounding_mode="trunc")
+            return self.tensor(a) / b if ta else a / b
+        if op == "%":
+            return torch.fmod(self.tensor(a), b)
+        if ta and a.dtype == torch.bool and op in "+-*<<>>":
+            a = a.to(torch.int32)
+        if tb and b.dtype == torch.bool and op in "+-*<<>>":
+            b = b.to(torch.int32)
+        import operator as o
+        f = {"|": o.or_, "^": o.xor, "&": o.and_, "==": o.eq, "!=": o.ne, "<": o.lt, "<=": o.le,
+             ">": o.gt, ">=": o.ge, "<<": o.lshift, ">>": o.rshift, "+": o.add, "-": o.sub,
+             "*": o.mul}[op]
+        return f(a, b)
+
+    def unary(self):
+        kind, val = self.peek()
+        if kind == "op" and val in ("-", "+", "!", "~"):
+            self.take()
+            v = self.unary()
+            if val == "-":
+                return -v
+            if val == "+":
+                return v
+            if val == "!":
+                return ~self.tensor(v).bool()
+            return ~self.tensor(v)
+        if kind == "op" and val == "(":
+            # cast or parenthesised expression
+            j = self.i + 1
+            words = []
+            while j < len(self.toks) and self.toks[j][0] == "id" and self.toks[j][1] in _CAST:
+                words.append(self.toks[j][1])
+                j += 1
+            if words and j < len(self.toks) and self.toks[j][1] == ")":
+                self.i = j + 1
+                v = self.unary()
+                dt = torch.int64 if "long" in words else _CAST[words[-1] if words[-1] != "unsigned" else "long"]
+                v = self.tensor(v)
+                if not dt.is_floating_point and dt != torch.bool and v.is_floating_point():
+                    v = torch.trunc(v)
+                return v.to(dt)
+            self.take("(")
+            v = self.ternary()
+            self.take(")")
+            return v
+        if kind == "num":
+            self.take()
+            txt = val.rstrip("uUlLfF")
+            return float(txt) if any(c in txt for c in ".eE") else int(txt)
+        if kind == "id":
+            self.take()
+            if self.peek()[1] == "(" and val in _FUNCS:
+                self.take("(")
+                args = [self.ternary()]
+                while self.peek()[1] == ",":
+                    self.take()
+                    args.append(self.ternary())
+                self.take(")")
+                args = [self.tensor(a) for a in args]
+                if val in ("sqrt", "exp", "log", "floor", "ceil") and not args[0].is_floating_point():
+                    args[0] = args[0].to(torch.float64)
+                return _FUNCS[val](*args)
+            if val in ("true", "false"):
+                return val == "true"
+            if val not in self.env:
+                raise ValueError("unknown identifier %r" % val)
+            return self.env[val]
+        raise ValueError("unexpected token %r" % (val,))
+
+
+def eval_expr(expr: str, cols: Sequence[torch.Tensor]) -> torch.Tensor:
+    n = int(cols[0].shape[0]) if cols else 0
+    dev = cols[0].device if cols else None
+    env = {"c%d" % j: c for j, c in enumerate(cols)}
+    p = _Parser(expr, env, n, dev)
+    return p.tensor(p.parse())
+
+
+def eval_host(cols: Sequence[torch.Tensor], in_types: Sequence[DType], stages: Sequence[Stage]):
+    """Evaluate the stage chain with torch ops (CPU or any device)."""
+    cur = list(cols)
+    mask = None
+    for st in stages:
+        if st.pred is not None:
+            p = eval_expr(st.pred, cur).to(torch.bool)
+            mask = p if mask is None else (mask & p)
+        else:
+            new = []
+            for e, t in zip(st.exprs, st.out):
+                v = eval_expr(e, cur)
+                if v.is_floating_point() and not t.torch_dtype.is_floating_point and t.torch_dtype != torch.bool:
+                    v = torch.trunc(v)
+                new.append(v.to(t.torch_dtype))
+            cur = new
+    return cur, mask

@@ -127,16 +127,53 @@ def _encode_column(col, dt: DType, session: Session) -> bytes:
     return hdr.pack(3, _DT_INDEX["object"], 0, len(payload)) + payload
 
 
+#: Device tensors at least this large are checksummed on the GPU (the CRC of
+#: the batch is stitched together with crc32_combine) while their bytes stream
+#: to the host, instead of re-reading them on the CPU.
+DEVICE_CRC_MIN_BYTES = 1 << 20
+
+
 def encode_frame(f: Frame, session: Optional[Session] = None) -> bytes:
     """Encode one frame as one checksummed batch."""
     session = session or Session()
-    body = [struct.pack("<QI", len(f), f.num_out())]
+    pieces = [struct.pack("<QI", len(f), f.num_out())]
+    dev_crcs = {}  # piece index -> (crc, nbytes) computed on the device
+    hdr = struct.Struct("<BBIQ")
     for col, dt in zip(f.cols(), f.typ.cols):
-        body.append(_encode_column(col, dt, session))
-    b = b"".join(body)
+        if dt.is_tensor and isinstance(col, torch.Tensor) and col.is_cuda \
+                and col.numel() * col.element_size() >= DEVICE_CRC_MIN_BYTES:
+            crc = _device_crc(col)
+            payload = _tensor_bytes(col)
+            pieces.append(hdr.pack(0, _DT_INDEX[_base(dt).name], dt.width, len(payload)))
+            if crc is not None:
+                dev_crcs[len(pieces)] = (crc, len(payload))
+            pieces.append(payload)
+        else:
+            pieces.append(_encode_column(col, dt, session))
+    b = b"".join(pieces)
     head = struct.pack("<IQ", MAGIC, len(b))
-    crc = crc32(b, crc32(head))
+    if not dev_crcs:
+        crc = crc32(b, crc32(head))
+    else:
+        nat = _native.lib()
+        crc = crc32(head)
+        for i, p in enumerate(pieces):
+            if i in dev_crcs:
+                c2, n2 = dev_crcs[i]
+                crc = nat.crc32_combine(crc, c2, n2)
+            else:
+                crc = crc32(p, crc)
     return head + b + struct.pack("<I", crc)
+
+
+def _device_crc(col: torch.Tensor) -> Optional[int]:
+    try:
+        from ..ops import gpu
+        if _native.lib() is None or not gpu.available():
+            return None
+        return gpu.crc32(col)
+    except Exception:
+        return None
 
 
 class Encoder:

@@ -926,3 +926,105 @@ def default_partitioner(frame: Frame, nshard: int) -> torch.Tensor:
 
     Bit-exact with the reference placement (``exec/compile.go:20-24``)."""
     return frame.hash(0) % nshard
+
+
+# --------------------------------------------------------------------------
+# Expression stages (NVRTC-fused Map/Filter)
+
+
+class _ExprReader(Reader):
+    """Evaluates a chain of expression stages over each tile in one fused
+    kernel (device) or with torch ops under C semantics (host)."""
+
+    def __init__(self, src: Reader, in_typ: Type, stages: list, out_typ: Type):
+        self.src, self.in_typ, self.stages, self.out_typ = src, in_typ, stages, out_typ
+        self.started = False
+
+    def read(self, n=None):
+        from .ops import jit
+        self.started = True
+        while True:
+            f = self.src.read(n)
+            if f is None:
+                return None
+            cols = f.cols()
+            on_gpu = f.device.type == "cuda"
+            if on_gpu:
+                from .ops import gpu
+                on_gpu = gpu.available()
+            if on_gpu and len(f):
+                outs, mask = jit.run_fused(cols, self.in_typ.cols, self.stages)
+                if mask is not None:
+                    from .ops import gpu
+                    idx = gpu.compact_indices(mask.view(torch.bool))
+                    outs = [gpu.gather_rows(o, idx) if o.dtype != torch.bool else o[idx] for o in outs]
+            else:
+                outs, mask = jit.eval_host(cols, self.in_typ.cols, self.stages)
+                if mask is not None:
+                    outs = [o[mask] for o in outs]
+            out = Frame(list(outs), self.out_typ)
+            if len(out) or n is None:
+                return out
+
+    def close(self):
+        self.src.close()
+
+
+class _ExprSlice(Slice):
+    def __init__(self, op: str, s: Slice, stage, typ: Type, pragmas):
+        super().__init__(make_name(op), typ, s.num_shard(), [Dep(s)], pragmas)
+        self.stage = stage
+        self.in_typ = s.typ
+
+    def reader(self, shard, deps):
+        from .sliceio import LabelReader
+        src = deps[0]
+        inner = src.reader if isinstance(src, LabelReader) else src
+        if isinstance(inner, _ExprReader) and not inner.started:
+            # fuse with the upstream expression stage(s): one kernel for the chain
+            return _ExprReader(inner.src, inner.in_typ, inner.stages + [self.stage], self.typ)
+        return _ExprReader(src, self.in_typ, [self.stage], self.typ)
+
+
+def _check_expr_cols(op: str, s: Slice, exprs):
+    from .ops import jit
+    try:
+        jit.check_types(s.typ.cols)
+    except TypeError as e:
+        typecheck.panicf("%s: %s", op, e)
+    for e in exprs:
+        if not isinstance(e, str):
+            typecheck.panicf("%s: expression must be a string, got %s", op, type(e).__name__)
+        for m in jit._VAR.finditer(e):
+            if int(m.group(1)) >= s.num_out():
+                typecheck.panicf("%s: expression %r refers to c%s but the slice has %d columns",
+                                 op, e, m.group(1), s.num_out())
+
+
+def MapExpr(slice_: Slice, exprs: Sequence[str], out: Sequence, *pragmas) -> Slice:
+    """Map with C expressions over the input columns ``c0, c1, ...`` — compiled
+    with NVRTC and fused with adjacent expression stages into one sm_100a
+    kernel (see :mod:`bigslice_b200.ops.jit`)."""
+    from .ops import jit
+    _check_slice("mapexpr", slice_)
+    exprs = list(exprs)
+    outs = [slicetype.dtype_of(o) for o in out]
+    if len(exprs) == 0:
+        typecheck.panicf("map: need at least one output column")
+    if len(exprs) != len(outs):
+        typecheck.panicf("mapexpr: %d expressions but %d output types", len(exprs), len(outs))
+    _check_expr_cols("mapexpr", slice_, exprs)
+    try:
+        jit.check_types(outs)
+    except TypeError as e:
+        typecheck.panicf("mapexpr: %s", e)
+    return _ExprSlice("mapexpr", slice_, jit.Stage(exprs=exprs, out=outs), Type(outs, 1), pragmas)
+
+
+def FilterExpr(slice_: Slice, pred: str, *pragmas) -> Slice:
+    """Filter with a C boolean expression over ``c0, c1, ...`` (fused like
+    :func:`MapExpr`)."""
+    from .ops import jit
+    _check_slice("filterexpr", slice_)
+    _check_expr_cols("filterexpr", slice_, [pred])
+    return _ExprSlice("filterexpr", slice_, jit.Stage(pred=pred), slice_.typ, pragmas)

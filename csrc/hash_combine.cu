@@ -198,11 +198,13 @@ struct SmemAcc<long long, BS_ADD> {
 };
 
 // ---- the combine kernel -------------------------------------------------------
-#define HC_CONSUMERS 1024
+#define HC_CONSUMERS 992  // 31 consumer warps + 1 producer warp = 1024 threads (the CTA limit)
 #define HC_THREADS (HC_CONSUMERS + 32)
+static_assert(HC_THREADS <= 1024, "a CTA has at most 1024 threads");
 #define HC_ROWS 4
 #define HC_TILE (HC_CONSUMERS * HC_ROWS)
 #define HC_STAGES 2
+static_assert((HC_TILE * 4) % 16 == 0, "TMA sizes must be multiples of 16 bytes");
 
 template <typename V, int OP>
 __global__ void __launch_bounds__(HC_THREADS, 1) hash_combine_tma_kernel(

@@ -6,6 +6,7 @@ mkdir -p gpurun_out
 NG=$(nvidia-smi -L | wc -l)
 echo "gpus=$NG" > gpurun_out/gpu2.txt
 python -c "import __graft_entry__ as g; g.build(); print('build ok')" > gpurun_out/build.log 2>&1
+timeout 300 python scripts/debug_local.py > gpurun_out/debug_local.log 2>&1
 timeout 900 python -m pytest tests -m gpu -q --timeout 240 -p no:cacheprovider > gpurun_out/pytest_gpu.log 2>&1
 echo "pytest rc=$?" >> gpurun_out/pytest_gpu.log
 timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1
@@ -25,6 +26,7 @@ if [ "$NG" -ge 2 ]; then
   timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29563 \
      benchmarks/cogroup_join.py --large 33554432 --small 2097152 > gpurun_out/cogroup.log 2>&1
 fi
+cat gpurun_out/debug_local.log
 tail -4 gpurun_out/pytest_gpu.log gpurun_out/smoke.log gpurun_out/bench_n1.err gpurun_out/bench_n2.err
 cat gpurun_out/bench_n1.json gpurun_out/bench_n2.json
 tail -12 gpurun_out/reshard_bw.log

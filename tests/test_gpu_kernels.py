@@ -179,3 +179,26 @@ def test_local_device_session_end_to_end(gpu):
         f = bs.Fold(bs.Const(2, torch.tensor([1, 2, 1]), torch.tensor([1., 2., 3.])),
                     lambda acc, v: acc + v)
         assert sorted(bs.slicetest.run(f, session=sess).rows()) == [(1, 4.0), (2, 2.0)]
+
+
+def test_codec_device_crc_and_ragged_take(gpu):
+    """Large device columns are checksummed by the GPU CRC kernel (stitched with
+    crc32_combine) and still decode/verify on the host; ListColumn gathers use
+    the expansion kernel."""
+    import io
+    from bigslice_b200 import sliceio, slicetype
+    from bigslice_b200.frame import columns as C
+    n = 300000
+    f = Frame.of(torch.arange(n).cuda(), torch.rand(n, dtype=torch.float64).cuda(),
+                 np.array(["s%d" % (i % 7) for i in range(n)], dtype=object))
+    before = gpu.launches()
+    data = sliceio.encode_frame(f)
+    assert gpu.launches() > before
+    g = sliceio.read_all(sliceio.Decoder(io.BytesIO(data), f.typ), f.typ)
+    assert torch.equal(g.col(0), f.col(0).cpu()) and torch.equal(g.col(1), f.col(1).cpu())
+    bad = bytearray(data)
+    bad[len(bad) // 2] ^= 4
+    with pytest.raises(Exception):
+        sliceio.read_all(sliceio.Decoder(io.BytesIO(bytes(bad)), f.typ), f.typ)
+    lc = C.col_from_list([[1, 2], [], [3], [4, 5, 6]], slicetype.List(bs.int64), "cuda")
+    assert C.col_take(lc, torch.tensor([3, 0, 1])).tolist() == [[4, 5, 6], [1, 2], []]
