@@ -43,7 +43,17 @@ def main():
         g.manual_seed(rank * 1000 + mb)
         cols = [torch.rand(n, device=dev, generator=g) for _ in range(8)]
         row = {"mb_per_gpu": mb, "rows_per_gpu": n, "world": world, "nparts": nparts}
-        for mode in ("fused", "nccl"):
+        # pre-partitioned copy for the "library all_to_all only" lower bound of the baseline
+        from bigslice_b200.ops import gpu as _g
+        _h = (_g.hash_column(cols[0], 0) % nparts) % world
+        _order = torch.sort(_h, stable=True)[1]
+        _cnt = torch.bincount(_h, minlength=world)
+        _rc = torch.empty_like(_cnt)
+        dist.all_to_all_single(_rc, _cnt)
+        _sorted = [c.index_select(0, _order).contiguous() for c in cols]
+        _in, _out = _cnt.tolist(), _rc.tolist()
+        _recv = [torch.empty(int(_rc.sum()), dtype=c.dtype, device=dev) for c in cols]
+        for mode in ("fused", "nccl", "a2a_only"):
             times = []
             for it in range(a.iters + 2):
                 torch.cuda.synchronize()
@@ -53,9 +63,11 @@ def main():
                 if mode == "fused":
                     got = peers.exchange(cols, nparts, nkeys=1, zero_copy=True)
                     nrecv = sum(c[0].shape[0] for c in got.values())
+                elif mode == "a2a_only":
+                    for r_, s_ in zip(_recv, _sorted):
+                        dist.all_to_all_single(r_, s_, _out, _in)
+                    nrecv = _recv[0].shape[0]
                 else:
-                    ids = (hashing.hash_tensor(cols[0].view(torch.int32).to(torch.int64) & 0xFFFFFFFF, 0)
-                           if False else None)
                     from bigslice_b200.ops import gpu
                     h = gpu.hash_column(cols[0], 0) % nparts
                     got = collective_exchange_tensors(cols + [h], h % world, None)
