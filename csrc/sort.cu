@@ -83,13 +83,20 @@ __global__ void __launch_bounds__(1024) rs_scan_kernel(unsigned long long* __res
   }
 }
 
+// Scatter pass.  Items are first placed in shared memory in tile-sorted order
+// (digit-major, stable), then written out so that consecutive threads store to
+// consecutive addresses inside each digit's run: coalesced 8-byte stores
+// instead of 256-way scattered ones.
 __global__ void __launch_bounds__(RS_THREADS) rs_scatter_kernel(
     const long long* __restrict__ keys_in, const long long* __restrict__ vals_in,
     long long* __restrict__ keys_out, long long* __restrict__ vals_out, long long n,
     long long chunk_rows, int shift, const unsigned long long* __restrict__ offsets) {
   __shared__ unsigned long long run[256];           // next output slot per digit for this chunk
-  __shared__ unsigned long long nrun[256];          // ... after the current tile
+  __shared__ unsigned int tstart[257];              // tile-local start of each digit's run
   __shared__ unsigned int wcount[RS_WARPS][256];    // per-warp digit counts -> warp bases
+  extern __shared__ __align__(16) unsigned char rs_smem[];
+  long long* skey = (long long*)rs_smem;            // [RS_TILE]
+  long long* sval = skey + RS_TILE;                 // [RS_TILE]
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (tid < 256) run[tid] = offsets[(size_t)tid * gridDim.x + blockIdx.x];
   long long beg = (long long)blockIdx.x * chunk_rows;
@@ -120,7 +127,7 @@ __global__ void __launch_bounds__(RS_THREADS) rs_scatter_kernel(
       __syncwarp();
     }
     __syncthreads();
-    // per digit: exclusive scan over warps; the total advances the chunk offset
+    // per digit: exclusive scan over warps -> warp bases; digit totals in tstart[d+1]
     if (tid < 256) {
       unsigned acc = 0;
       for (int w = 0; w < RS_WARPS; ++w) {
@@ -128,19 +135,52 @@ __global__ void __launch_bounds__(RS_THREADS) rs_scatter_kernel(
         wcount[w][tid] = acc;
         acc += c;
       }
-      nrun[tid] = run[tid] + acc;
+      tstart[tid + 1] = acc;
+      if (tid == 0) tstart[0] = 0;
     }
     __syncthreads();
+    // exclusive scan of the 256 digit totals (one warp, 8 per lane)
+    if (tid < 32) {
+      unsigned loc[8], sum = 0;
 #pragma unroll
-    for (int j = 0; j < RS_ITEMS; ++j) {
-      if (dg[j] != 0xffffffffu) {
-        unsigned long long pos = run[dg[j]] + wcount[warp][dg[j]] + rk[j];
-        keys_out[pos] = k[j];
-        vals_out[pos] = v[j];
+      for (int q = 0; q < 8; ++q) {
+        loc[q] = tstart[tid * 8 + q + 1];
+        sum += loc[q];
+      }
+      unsigned incl = sum;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        unsigned t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+      }
+      unsigned runv = incl - sum;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        runv += loc[q];
+        tstart[tid * 8 + q + 1] = runv;  // inclusive end of digit (tid*8+q) == start of the next
       }
     }
     __syncthreads();
-    if (tid < 256) run[tid] = nrun[tid];
+    // place items at their tile-sorted position
+#pragma unroll
+    for (int j = 0; j < RS_ITEMS; ++j) {
+      if (dg[j] != 0xffffffffu) {
+        unsigned lpos = tstart[dg[j]] + wcount[warp][dg[j]] + rk[j];
+        skey[lpos] = k[j];
+        sval[lpos] = v[j];
+      }
+    }
+    __syncthreads();
+    const unsigned ntile = tstart[256];
+    for (unsigned p = tid; p < ntile; p += RS_THREADS) {
+      long long kk = skey[p];
+      unsigned d = rs_digit(kk, shift);
+      unsigned long long pos = run[d] + (p - tstart[d]);
+      keys_out[pos] = kk;
+      vals_out[pos] = sval[p];
+    }
+    __syncthreads();
+    if (tid < 256) run[tid] += tstart[tid + 1] - tstart[tid];
     // (the zeroing loop + barrier at the top of the next iteration orders this)
   }
 }
@@ -173,6 +213,12 @@ BS_EXPORT int bs_radix_sort_pairs(long long* keys_a, long long* vals_a, long lon
     rs_global_hist_kernel<<<blocks, RS_THREADS, 0, stream>>>(keys_a, n, ghist);
     BS_COUNT_LAUNCH();
   }
+  static bool attr_set = false;
+  if (!attr_set) {
+    e = cudaFuncSetAttribute(rs_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, RS_TILE * 16);
+    if (e != cudaSuccess) return -(int)e;
+    attr_set = true;
+  }
   unsigned long long h[8 * 256];
   e = cudaMemcpyAsync(h, ghist, sizeof(h), cudaMemcpyDeviceToHost, stream);
   if (e != cudaSuccess) return -(int)e;
@@ -192,7 +238,7 @@ BS_EXPORT int bs_radix_sort_pairs(long long* keys_a, long long* vals_a, long lon
     BS_COUNT_LAUNCH();
     rs_scan_kernel<<<1, 1024, 0, stream>>>(counts, 256LL * nchunks);
     BS_COUNT_LAUNCH();
-    rs_scatter_kernel<<<nchunks, RS_THREADS, 0, stream>>>(kin, vin, kout, vout, n, chunk_rows, p * 8, counts);
+    rs_scatter_kernel<<<nchunks, RS_THREADS, RS_TILE * 16, stream>>>(kin, vin, kout, vout, n, chunk_rows, p * 8, counts);
     BS_COUNT_LAUNCH();
     flip ^= 1;
   }
