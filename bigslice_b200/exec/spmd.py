@@ -310,7 +310,7 @@ class SpmdExecutor(LocalExecutor):
             sent = len(k)
             mode = "table-local"
         else:
-            got = self.peers.exchange_raw(table.column_desc(), table.cap, nparts, nkeys=1,
+            got = self.peers.exchange_raw(table.column_desc(), table.total, nparts, nkeys=1,
                                           skip_empty=True, zero_copy=True, keep=table)
             st = table.status.tolist()
             if st[0]:
@@ -322,7 +322,11 @@ class SpmdExecutor(LocalExecutor):
                     out[p] = []
                     continue
                 # rows from different ranks may share keys: combine on arrival
-                fk, fv = gpu.hash_combine(rk, rv, head.combiner.builtin, distinct_hint=rk.numel())
+                dkey = self._hint_key(head) + "/dest%d" % p
+                dh = self.card_hints.get(dkey)
+                fk, fv = gpu.hash_combine(rk, rv, head.combiner.builtin,
+                                          distinct_hint=min(rk.numel(), dh) if dh else rk.numel())
+                self.card_hints[dkey] = max(int(fk.numel() * 1.25), 1 << 12)
                 out[p] = [Frame([fk, fv], typ)]
             if st[1]:  # the reserved EMPTY key was present: route it on the host (rare)
                 self._route_special(head, st[2], nparts, out, typ)

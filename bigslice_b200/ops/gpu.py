@@ -170,25 +170,32 @@ class HashTable:
     Array-of-structs: ``slots[cap, 2]`` int64 — column 0 the key, column 1 the
     value bits — so a probe touches one 32-byte sector."""
 
-    def __init__(self, capacity: int, vdtype: torch.dtype, op: str, device):
+    #: Slots of the L2-resident warm level placed in front of large tables
+    #: (4 Mi slots = 64 MiB, about half of the B200's L2).
+    WARM_SLOTS = int(os.environ.get("BIGSLICE_WARM_SLOTS", 1 << 22))
+
+    def __init__(self, capacity: int, vdtype: torch.dtype, op: str, device, warm: Optional[int] = None):
         require()
         cap = 1
         while cap < max(capacity, 1024):
             cap <<= 1
-        self.cap, self.vdtype, self.op, self.device = cap, vdtype, op, device
-        self.slots = torch.empty((cap, 2), dtype=torch.int64, device=device)
+        if warm is None:
+            warm = self.WARM_SLOTS if cap >= 2 * self.WARM_SLOTS else 0
+        self.cap, self.warm, self.total = cap, warm, cap + warm
+        self.vdtype, self.op, self.device = vdtype, op, device
+        self.slots = torch.empty((self.total, 2), dtype=torch.int64, device=device)
         self.status = torch.zeros(4, dtype=torch.int64, device=device)
         self.reset()
 
     def reset(self):
-        _chk(_lib.bs_table_init(_ptr(self.slots), c_ll(self.cap), c_int(VTYPE[self.vdtype]),
+        _chk(_lib.bs_table_init(_ptr(self.slots), c_ll(self.total), c_int(VTYPE[self.vdtype]),
                                 c_int(OPS[self.op]), _ptr(self.status), _stream()), "table_init")
 
     def combine(self, keys: torch.Tensor, vals: torch.Tensor, force_simple: bool = False):
         keys, vals = keys.contiguous(), vals.contiguous()
         _chk(_lib.bs_hash_combine(_ptr(keys), _ptr(vals), c_ll(keys.numel()),
                                   c_int(VTYPE[self.vdtype]), c_int(OPS[self.op]), _ptr(self.slots),
-                                  c_ll(self.cap), _ptr(self.status),
+                                  c_ll(self.warm), c_ll(self.cap), _ptr(self.status),
                                   c_int(1 if force_simple else 0), _stream()), "hash_combine")
 
     def column_desc(self):
@@ -200,10 +207,10 @@ class HashTable:
 
     def compact(self, max_rows: Optional[int] = None) -> Tuple[torch.Tensor, torch.Tensor]:
         """Dense (keys, vals) of the occupied slots; syncs once for the count."""
-        cap_out = self.cap + 1 if max_rows is None else max_rows
+        cap_out = self.total + 1 if max_rows is None else max_rows
         ok = torch.empty(cap_out, dtype=torch.int64, device=self.device)
         ov = torch.empty(cap_out, dtype=self.vdtype, device=self.device)
-        _chk(_lib.bs_table_compact(_ptr(self.slots), c_ll(self.cap), c_int(VTYPE[self.vdtype]),
+        _chk(_lib.bs_table_compact(_ptr(self.slots), c_ll(self.total), c_int(VTYPE[self.vdtype]),
                                    _ptr(ok), _ptr(ov), _ptr(self.status), _stream()), "table_compact")
         st = self.status.tolist()
         if st[0]:

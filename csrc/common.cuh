@@ -167,6 +167,33 @@ __device__ __forceinline__ int4 bs_ldg_stream(const int4* p) {
   return r;
 }
 
+// ---- L2 cache-policy hints ----------------------------------------------------
+__device__ __forceinline__ unsigned long long bs_policy_evict_last() {
+  unsigned long long p;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ unsigned long long bs_policy_evict_first() {
+  unsigned long long p;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ long long bs_ld_hint_s64(const long long* p, unsigned long long pol) {
+  long long v;
+  asm volatile("ld.global.L2::cache_hint.s64 %0, [%1], %2;" : "=l"(v) : "l"(p), "l"(pol) : "memory");
+  return v;
+}
+// TMA 1-D bulk load with an L2 cache hint (streaming inputs use evict_first so
+// they do not displace the L2-resident hash-table level).
+__device__ __forceinline__ void bs_tma_load_1d_hint(void* smem_dst, const void* gsrc, uint32_t bytes,
+                                                    uint64_t* bar, unsigned long long pol) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint "
+      "[%0], [%1], %2, [%3], %4;" ::"r"(bs_smem_addr(smem_dst)),
+      "l"(gsrc), "r"(bytes), "r"(bs_smem_addr(bar)), "l"(pol)
+      : "memory");
+}
+
 // Value dtypes / combine ops shared by the combine, segmented-reduce kernels.
 enum BsVType { BS_I32 = 0, BS_I64 = 1, BS_F32 = 2, BS_F64 = 3 };
 enum BsOp { BS_ADD = 0, BS_MIN = 1, BS_MAX = 2 };

@@ -31,8 +31,8 @@
 #define XC_MAXP 256   // destination shards
 #define XC_MAXC 8     // columns per row
 #define XC_MAXK 4     // key columns hashed
-#define XC_TILE 2048
-#define XC_THREADS 512
+#define XC_TILE 1024
+#define XC_THREADS 256
 #define XC_TIMEOUT_NS 30000000000ULL
 
 // Symmetric control block, one per rank, mapped by every peer.
@@ -236,10 +236,13 @@ __device__ __forceinline__ int xc_vw(const XcSpec& sp, int c) {
   return 1;
 }
 
-#define XC_STAGE_BYTES (160 * 1024)  // dynamic shared memory for column staging
+#define XC_STAGE_MAX (64 * 1024)  // upper bound of the dynamic staging buffer per CTA
 
+// Small tiles (1024 rows) and 256-thread CTAs: several CTAs are resident per SM
+// so the load phase of one overlaps the NVLink store phase of another.
 __global__ void __launch_bounds__(XC_THREADS) xchg_scatter_kernel(XcPeers pe, XcSpec sp, XcPlan* plan,
-                                                                 unsigned long long epoch) {
+                                                                 unsigned long long epoch,
+                                                                 unsigned int stage_bytes) {
   __shared__ int hist[XC_MAXP];
   __shared__ int segstart[XC_MAXP + 1];
   __shared__ unsigned long long base[XC_MAXP];
@@ -310,7 +313,7 @@ __global__ void __launch_bounds__(XC_THREADS) xchg_scatter_kernel(XcPeers pe, Xc
       while (c0 < sp.ncols) {
         int c1 = c0;
         size_t used = 0;
-        while (c1 < sp.ncols && used + (size_t)XC_TILE * sp.es[c1] <= XC_STAGE_BYTES) {
+        while (c1 < sp.ncols && used + (size_t)XC_TILE * sp.es[c1] <= stage_bytes) {
           used += (size_t)XC_TILE * sp.es[c1];
           ++c1;
         }
@@ -484,18 +487,28 @@ BS_EXPORT int bs_xc_exchange(const void* peers_h, const void* spec_h, void* plan
   xchg_plan_kernel<<<1, 256, 0, stream>>>(pe, sp, plan, epoch, arena_base);
   BS_LAUNCH_CHECK();
   long long ntiles = (sp.n + XC_TILE - 1) / XC_TILE;
-  int blocks = (int)(ntiles < (long long)sms ? ntiles : (long long)sms);  // 1 CTA/SM (160 KB staging)
-  if (blocks < 1) blocks = 1;
-  for (int c = 0; c < sp.ncols; ++c)
-    if ((size_t)XC_TILE * sp.es[c] > XC_STAGE_BYTES) return -3;  // row wider than 80 bytes per column
+  size_t row_bytes = 0, widest = 0;
+  for (int c = 0; c < sp.ncols; ++c) {
+    row_bytes += (size_t)sp.es[c];
+    if ((size_t)sp.es[c] > widest) widest = (size_t)sp.es[c];
+  }
+  if (widest * XC_TILE > XC_STAGE_MAX) return -3;  // a single column wider than 64 bytes per row
+  size_t stage = row_bytes * XC_TILE;
+  if (stage > XC_STAGE_MAX) stage = XC_STAGE_MAX;  // wide rows: columns are staged in groups
+  if (stage < 1024) stage = 1024;
   static bool attr_set = false;
   if (!attr_set) {
     e = cudaFuncSetAttribute(xchg_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             XC_STAGE_BYTES);
+                             XC_STAGE_MAX);
     if (e != cudaSuccess) return (int)e;
     attr_set = true;
   }
-  xchg_scatter_kernel<<<blocks, XC_THREADS, XC_STAGE_BYTES, stream>>>(pe, sp, plan, epoch);
+  int per_sm = (int)((200 * 1024) / (stage + 8 * 1024));
+  if (per_sm < 1) per_sm = 1;
+  if (per_sm > 6) per_sm = 6;
+  int blocks = (int)(ntiles < (long long)sms * per_sm ? ntiles : (long long)sms * per_sm);
+  if (blocks < 1) blocks = 1;
+  xchg_scatter_kernel<<<blocks, XC_THREADS, stage, stream>>>(pe, sp, plan, epoch, (unsigned int)stage);
   BS_LAUNCH_CHECK();
   xchg_wait_kernel<<<1, 32, 0, stream>>>(pe, plan, epoch);
   BS_LAUNCH_CHECK();

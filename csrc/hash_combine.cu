@@ -126,38 +126,74 @@ __global__ void __launch_bounds__(256) table_init_kernel(BsSlot* __restrict__ ta
   }
 }
 
-// ---- HBM table insert -------------------------------------------------------
-// `cur` is the already-loaded key of the home slot (the caller batches those
-// loads so several probes are in flight per thread).
+// ---- two-level HBM table ----------------------------------------------------
+// slots = [ warm (warm_mask+1 slots) | main (main_mask+1 slots) ].
+//  * warm: direct-mapped, small enough to live in the 126 MB L2 (accessed with
+//    evict_last hints).  A key that finds its warm slot free claims it for good;
+//    a key whose warm slot belongs to another key always goes to `main`.  Hence
+//    every key lives in exactly one level and the union of both levels is the
+//    result — compaction and the exchange just scan the whole array.
+//  * main: open addressing with linear probing (random DRAM accesses), reached
+//    only by the cold tail of the key distribution.
+struct BsTable {
+  BsSlot* warm;
+  unsigned long long warm_mask;  // 0 when there is no warm level
+  BsSlot* main;
+  unsigned long long main_mask;
+  int has_warm;
+};
+
+__device__ __forceinline__ uint32_t bs_hash_main(uint32_t h) { return bs_fmix32(h + 0x9e3779b9u); }
+
 template <typename V, int OP>
-__device__ __forceinline__ void table_resolve(BsSlot* __restrict__ tab, unsigned long long mask,
-                                              long long key, V val, uint32_t h, long long cur,
-                                              BsCombineStatus* st) {
-  unsigned long long slot = (unsigned long long)h & mask;
+__device__ __forceinline__ void main_resolve(const BsTable& t, long long key, V val, uint32_t h2,
+                                             long long cur, BsCombineStatus* st) {
+  unsigned long long slot = (unsigned long long)h2 & t.main_mask;
   // Linear probing; bounded so a full table cannot hang the GPU.
   for (int probe = 0; probe < 4096; ++probe) {
     if (cur == key) {
-      Combine<V, OP>::apply(slot_val<V>(&tab[slot]), val);
+      Combine<V, OP>::apply(slot_val<V>(&t.main[slot]), val);
       return;
     }
     if (cur == BS_EMPTY_KEY) {
-      long long prev = (long long)atomicCAS((unsigned long long*)&tab[slot].key,
+      long long prev = (long long)atomicCAS((unsigned long long*)&t.main[slot].key,
                                             (unsigned long long)BS_EMPTY_KEY, (unsigned long long)key);
       if (prev == BS_EMPTY_KEY || prev == key) {
-        Combine<V, OP>::apply(slot_val<V>(&tab[slot]), val);
+        Combine<V, OP>::apply(slot_val<V>(&t.main[slot]), val);
         return;
       }
     }
-    slot = (slot + 1) & mask;
-    cur = __ldcg(&tab[slot].key);
+    slot = (slot + 1) & t.main_mask;
+    cur = __ldcg(&t.main[slot].key);
   }
   atomicAdd(&st->failed, 1ULL);
 }
 
+// Try the warm level given the already-loaded key of the warm slot; returns
+// true when the row was absorbed.
 template <typename V, int OP>
-__device__ __forceinline__ void table_insert(BsSlot* __restrict__ tab, unsigned long long mask,
-                                             long long key, V val, uint32_t h, BsCombineStatus* st) {
-  table_resolve<V, OP>(tab, mask, key, val, h, __ldcg(&tab[(unsigned long long)h & mask].key), st);
+__device__ __forceinline__ bool warm_resolve(const BsTable& t, long long key, V val, uint32_t h,
+                                             long long cur) {
+  BsSlot* s = &t.warm[(unsigned long long)h & t.warm_mask];
+  if (cur != key) {
+    if (cur != BS_EMPTY_KEY) return false;
+    long long prev = (long long)atomicCAS((unsigned long long*)&s->key,
+                                          (unsigned long long)BS_EMPTY_KEY, (unsigned long long)key);
+    if (prev != BS_EMPTY_KEY && prev != key) return false;
+  }
+  Combine<V, OP>::apply(slot_val<V>(s), val);
+  return true;
+}
+
+template <typename V, int OP>
+__device__ __forceinline__ void table_insert(const BsTable& t, long long key, V val, uint32_t h,
+                                             BsCombineStatus* st) {
+  if (t.has_warm) {
+    long long cur = __ldcg(&t.warm[(unsigned long long)h & t.warm_mask].key);
+    if (warm_resolve<V, OP>(t, key, val, h, cur)) return;
+  }
+  uint32_t h2 = bs_hash_main(h);
+  main_resolve<V, OP>(t, key, val, h2, __ldcg(&t.main[(unsigned long long)h2 & t.main_mask].key), st);
 }
 
 template <typename V, int OP>
@@ -209,7 +245,7 @@ static_assert((HC_TILE * 4) % 16 == 0, "TMA sizes must be multiples of 16 bytes"
 template <typename V, int OP>
 __global__ void __launch_bounds__(HC_THREADS, 1) hash_combine_tma_kernel(
     const long long* __restrict__ keys, const V* __restrict__ vals, long long n,
-    BsSlot* __restrict__ tab, unsigned long long mask, BsCombineStatus* __restrict__ st) {
+    BsTable tab, BsCombineStatus* __restrict__ st) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   long long* stage_keys = (long long*)smem_raw;                                   // [STAGES][TILE]
   V* stage_vals = (V*)(smem_raw + (size_t)HC_STAGES * HC_TILE * sizeof(long long));  // [STAGES][TILE]
@@ -237,6 +273,7 @@ __global__ void __launch_bounds__(HC_THREADS, 1) hash_combine_tma_kernel(
   if (warp == HC_CONSUMERS / 32) {
     // ===== producer warp: one elected lane issues the TMA bulk loads =====
     if (lane == 0) {
+      const unsigned long long stream_pol = bs_policy_evict_first();
       long long it = 0;
       for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
         int s = (int)(it % HC_STAGES);
@@ -246,12 +283,13 @@ __global__ void __launch_bounds__(HC_THREADS, 1) hash_combine_tma_kernel(
         long long rows = n - row0 < HC_TILE ? n - row0 : HC_TILE;
         uint32_t kb = (uint32_t)(rows * sizeof(long long)), vb = (uint32_t)(rows * sizeof(V));
         bs_mbar_expect_tx(&full[s], kb + vb);
-        bs_tma_load_1d(stage_keys + (size_t)s * HC_TILE, keys + row0, kb, &full[s]);
-        bs_tma_load_1d(stage_vals + (size_t)s * HC_TILE, vals + row0, vb, &full[s]);
+        bs_tma_load_1d_hint(stage_keys + (size_t)s * HC_TILE, keys + row0, kb, &full[s], stream_pol);
+        bs_tma_load_1d_hint(stage_vals + (size_t)s * HC_TILE, vals + row0, vb, &full[s], stream_pol);
       }
     }
   } else {
     // ===== consumer warps =====
+    const unsigned long long keep_pol = bs_policy_evict_last();
     long long it = 0;
     for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
       int s = (int)(it % HC_STAGES);
@@ -301,15 +339,29 @@ __global__ void __launch_bounds__(HC_THREADS, 1) hash_combine_tma_kernel(
         }
         SmemAcc<V, OP>::apply(sacc, (int)sl, v[j]);
       }
-      // --- phase B: issue all HBM probes of this thread back to back ---
+      // --- phase B: warm level (L2-resident): issue all probes back to back ---
       long long cur[HC_ROWS];
+      if (tab.has_warm) {
+#pragma unroll
+        for (int j = 0; j < HC_ROWS; ++j)
+          cur[j] = (miss >> j) & 1u
+                       ? bs_ld_hint_s64(&tab.warm[(unsigned long long)h[j] & tab.warm_mask].key, keep_pol)
+                       : 0;
+#pragma unroll
+        for (int j = 0; j < HC_ROWS; ++j)
+          if (((miss >> j) & 1u) && warm_resolve<V, OP>(tab, k[j], v[j], h[j], cur[j])) miss &= ~(1u << j);
+      }
+      // --- phase C: cold tail -> main level (DRAM): batched probes again ---
+#pragma unroll
+      for (int j = 0; j < HC_ROWS; ++j) {
+        if ((miss >> j) & 1u) {
+          h[j] = bs_hash_main(h[j]);
+          cur[j] = __ldcg(&tab.main[(unsigned long long)h[j] & tab.main_mask].key);
+        }
+      }
 #pragma unroll
       for (int j = 0; j < HC_ROWS; ++j)
-        cur[j] = (miss >> j) & 1u ? __ldcg(&tab[(unsigned long long)h[j] & mask].key) : 0;
-      // --- phase C: resolve ---
-#pragma unroll
-      for (int j = 0; j < HC_ROWS; ++j)
-        if ((miss >> j) & 1u) table_resolve<V, OP>(tab, mask, k[j], v[j], h[j], cur[j], st);
+        if ((miss >> j) & 1u) main_resolve<V, OP>(tab, k[j], v[j], h[j], cur[j], st);
     }
   }
   __syncthreads();
@@ -317,7 +369,7 @@ __global__ void __launch_bounds__(HC_THREADS, 1) hash_combine_tma_kernel(
   for (int s = tid; s < HC_SLOTS; s += HC_THREADS) {
     long long key = skeys[s];
     if (key != BS_EMPTY_KEY)
-      table_insert<V, OP>(tab, mask, key, SmemAcc<V, OP>::read(sacc, s), bs_mix_u64((uint64_t)key), st);
+      table_insert<V, OP>(tab, key, SmemAcc<V, OP>::read(sacc, s), bs_mix_u64((uint64_t)key), st);
   }
 }
 
@@ -326,7 +378,7 @@ __global__ void __launch_bounds__(HC_THREADS, 1) hash_combine_tma_kernel(
 template <typename V, int OP>
 __global__ void __launch_bounds__(512) hash_combine_simple_kernel(
     const long long* __restrict__ keys, const V* __restrict__ vals, long long n,
-    BsSlot* __restrict__ tab, unsigned long long mask, BsCombineStatus* __restrict__ st) {
+    BsTable tab, BsCombineStatus* __restrict__ st) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   long long stride = (long long)gridDim.x * blockDim.x;
   for (; i < n; i += stride) {
@@ -336,7 +388,7 @@ __global__ void __launch_bounds__(512) hash_combine_simple_kernel(
       special_insert<V, OP>(val, st);
       continue;
     }
-    table_insert<V, OP>(tab, mask, key, val, bs_mix_u64((uint64_t)key), st);
+    table_insert<V, OP>(tab, key, val, bs_mix_u64((uint64_t)key), st);
   }
 }
 
@@ -410,10 +462,16 @@ static size_t hc_smem_bytes() {
 }
 
 template <typename V, int OP>
-static int launch_combine(const long long* keys, const V* vals, long long n, BsSlot* tab,
-                          long long cap, BsCombineStatus* st, int force_simple, cudaStream_t stream) {
+static int launch_combine(const long long* keys, const V* vals, long long n, BsSlot* slots,
+                          long long warm_cap, long long cap, BsCombineStatus* st, int force_simple,
+                          cudaStream_t stream) {
   if (n <= 0) return 0;
-  unsigned long long mask = (unsigned long long)cap - 1;
+  BsTable tab;
+  tab.warm = slots;
+  tab.warm_mask = warm_cap > 0 ? (unsigned long long)warm_cap - 1 : 0;
+  tab.has_warm = warm_cap > 0;
+  tab.main = slots + warm_cap;
+  tab.main_mask = (unsigned long long)cap - 1;
   int sms = bs_num_sms();
   bool aligned = (((uintptr_t)keys | (uintptr_t)vals) & 15) == 0;
   // TMA sizes must be multiples of 16 bytes: peel a ragged tail.
@@ -431,7 +489,7 @@ static int launch_combine(const long long* keys, const V* vals, long long n, BsS
     }
     long long ntiles = (n_main + HC_TILE - 1) / HC_TILE;
     int blocks = (int)(ntiles < sms ? ntiles : sms);
-    hash_combine_tma_kernel<V, OP><<<blocks, HC_THREADS, smem, stream>>>(keys, vals, n_main, tab, mask, st);
+    hash_combine_tma_kernel<V, OP><<<blocks, HC_THREADS, smem, stream>>>(keys, vals, n_main, tab, st);
     BS_LAUNCH_CHECK();
   }
   long long rest = n - n_main;
@@ -439,7 +497,7 @@ static int launch_combine(const long long* keys, const V* vals, long long n, BsS
     long long want = (rest + 511) / 512;
     int blocks = (int)(want < (long long)sms * 4 ? want : (long long)sms * 4);
     hash_combine_simple_kernel<V, OP><<<blocks, 512, 0, stream>>>(keys + n_main, vals + n_main, rest,
-                                                                  tab, mask, st);
+                                                                  tab, st);
     BS_LAUNCH_CHECK();
   }
   return 0;
@@ -486,25 +544,27 @@ static int launch_init(void* tab, long long cap, BsCombineStatus* st, cudaStream
   return (int)e;
 }
 
-// `tab` is cap x 16 bytes (BsSlot); cap must be a power of two.
-BS_EXPORT int bs_table_init(void* tab, long long cap, int vtype, int op, void* status,
+// `tab` is `total` x 16 bytes (BsSlot): the warm level followed by the main level.
+BS_EXPORT int bs_table_init(void* tab, long long total, int vtype, int op, void* status,
                             cudaStream_t stream) {
-  if (cap <= 0 || (cap & (cap - 1))) return -2;
-  DISPATCH_VOP(launch_init, tab, cap, (BsCombineStatus*)status, stream)
+  if (total <= 0) return -2;
+  DISPATCH_VOP(launch_init, tab, total, (BsCombineStatus*)status, stream)
 }
 
 template <typename V, int OP>
 static int combine_entry(const long long* keys, const void* vals, long long n, void* tab,
-                         long long cap, void* st, int force_simple, cudaStream_t stream) {
-  return launch_combine<V, OP>(keys, (const V*)vals, n, (BsSlot*)tab, cap, (BsCombineStatus*)st,
-                               force_simple, stream);
+                         long long warm_cap, long long cap, void* st, int force_simple,
+                         cudaStream_t stream) {
+  return launch_combine<V, OP>(keys, (const V*)vals, n, (BsSlot*)tab, warm_cap, cap,
+                               (BsCombineStatus*)st, force_simple, stream);
 }
 
+// warm_cap: 0 or a power of two; cap: power of two.  tab holds warm_cap + cap slots.
 BS_EXPORT int bs_hash_combine(const long long* keys, const void* vals, long long n, int vtype, int op,
-                              void* tab, long long cap, void* status, int force_simple,
-                              cudaStream_t stream) {
-  if (cap <= 0 || (cap & (cap - 1))) return -2;
-  DISPATCH_VOP(combine_entry, keys, vals, n, tab, cap, status, force_simple, stream)
+                              void* tab, long long warm_cap, long long cap, void* status,
+                              int force_simple, cudaStream_t stream) {
+  if (cap <= 0 || (cap & (cap - 1)) || (warm_cap & (warm_cap - 1)) || warm_cap < 0) return -2;
+  DISPATCH_VOP(combine_entry, keys, vals, n, tab, warm_cap, cap, status, force_simple, stream)
 }
 
 BS_EXPORT int bs_table_compact(const void* tab, long long cap, int vtype, long long* out_keys,

@@ -6,7 +6,7 @@ mkdir -p gpurun_out
 NG=$(nvidia-smi -L | wc -l)
 echo "gpus=$NG" > gpurun_out/gpu2.txt
 python -c "import __graft_entry__ as g; g.build(); print('build ok')" > gpurun_out/build.log 2>&1
-timeout 300 python scripts/debug_local.py > gpurun_out/debug_local.log 2>&1
+PYTHONPATH=. timeout 300 python scripts/debug_local.py > gpurun_out/debug_local.log 2>&1
 timeout 900 python -m pytest tests -m gpu -q --timeout 240 -p no:cacheprovider > gpurun_out/pytest_gpu.log 2>&1
 echo "pytest rc=$?" >> gpurun_out/pytest_gpu.log
 timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1
@@ -15,7 +15,7 @@ timeout 600 python bench.py --steps 10 --warmup 3 > gpurun_out/bench_n1.json 2> 
 echo "bench rc=$?" >> gpurun_out/bench_n1.err
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 300 --csv --log-file gpurun_out/launches.csv \
    python bench.py --steps 2 --warmup 3 --no-e2e > gpurun_out/ncu_launches.log 2>&1
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:hash_combine_tma -s 3 -c 1 -f -o gpurun_out/prof_combine_v1 \
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:hash_combine_tma -s 3 -c 1 -f -o gpurun_out/prof_combine_v2 \
    python bench.py --steps 1 --warmup 3 --no-e2e > gpurun_out/ncu_full.log 2>&1
 if [ "$NG" -ge 2 ]; then
   timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29561 \

@@ -86,8 +86,8 @@ def test_hash_combine_matches_torch(gpu, vdtype, op):
     else:
         want = torch.empty(len(uk), dtype=torch.float64).scatter_reduce_(
             0, inv, vals.double(), "amin" if op == "min" else "amax", include_self=False)
-    for simple in (False, True):
-        t = gpu.HashTable(4 * len(uk), vdtype, op, "cuda")
+    for simple, warm in ((False, None), (True, None), (False, 1024), (True, 256)):
+        t = gpu.HashTable(4 * len(uk), vdtype, op, "cuda", warm=warm)
         t.combine(dev(keys), dev(vals), force_simple=simple)
         k, v = t.compact()
         order = torch.sort(k.cpu())[1]
