@@ -56,7 +56,13 @@ def init_process_group(device: Optional[str] = None) -> None:
     if dist.is_initialized():
         return
     os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-    os.environ.setdefault("MASTER_PORT", "29511")
+    if "MASTER_PORT" not in os.environ:
+        # single-process use (no torchrun): any free port will do
+        import socket
+        s = socket.socket()
+        s.bind(("127.0.0.1", 0))
+        os.environ["MASTER_PORT"] = str(s.getsockname()[1])
+        s.close()
     os.environ.setdefault("RANK", "0")
     os.environ.setdefault("WORLD_SIZE", "1")
     use_cuda = (device or "").startswith("cuda") or (device is None and torch.cuda.is_available())

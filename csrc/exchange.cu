@@ -31,8 +31,8 @@
 #define XC_MAXP 256   // destination shards
 #define XC_MAXC 8     // columns per row
 #define XC_MAXK 4     // key columns hashed
-#define XC_TILE 1024
-#define XC_THREADS 256
+#define XC_TILE 2048
+#define XC_THREADS 512
 #define XC_TIMEOUT_NS 30000000000ULL
 
 // Symmetric control block, one per rank, mapped by every peer.
@@ -187,67 +187,44 @@ __device__ __forceinline__ void xc_copy_chunk(unsigned char* dst, const unsigned
   else *dst = *src;
 }
 
-// Stage one column group: every thread copies its rows' bytes into shared
-// memory at the row's destination-sorted position.  All loads of a thread are
-// independent, so many are in flight before the single barrier that follows.
 template <int VW>
-__device__ __forceinline__ void xc_stage_column(const XcSpec& sp, int c, long long row0, int rows,
-                                                const int* sortpos, unsigned char* region) {
+__device__ __forceinline__ void xc_move_column(const XcSpec& sp, const XcPlan* plan, int c,
+                                               long long row0, int rows, const int* sortpos,
+                                               const unsigned short* pos_dest, const int* segstart,
+                                               const unsigned long long* base,
+                                               unsigned char* stage) {
   constexpr int PER = XC_TILE / XC_THREADS;
-  const int es = sp.es[c], stride = sp.stride[c];
-  const int nchunk = es / VW;
-#pragma unroll
-  for (int j = 0; j < PER; ++j) {
-    int r = threadIdx.x + j * XC_THREADS;
-    if (r < rows && sortpos[j] >= 0) {
-      const unsigned char* src = sp.cols[c] + (size_t)(row0 + r) * stride;
-      unsigned char* dst = region + (size_t)sortpos[j] * es;
-      for (int q = 0; q < nchunk; ++q) xc_copy_chunk<VW>(dst + q * VW, src + q * VW);
-    }
-  }
-}
-
-// Write one staged column out: consecutive threads store consecutive VW-byte
-// chunks, so every destination segment is written with full-width coalesced
-// stores that go straight to the owner GPU's memory.
-template <int VW>
-__device__ __forceinline__ void xc_flush_column(const XcSpec& sp, const XcPlan* plan, int c,
-                                                int nsorted, const unsigned short* pos_dest,
-                                                const int* segstart, const unsigned long long* base,
-                                                const unsigned char* region) {
   const int es = sp.es[c];
+  const int stride = sp.stride[c];
   const int nchunk = es / VW;
-  const int total = nsorted * nchunk;
-  for (int x = threadIdx.x; x < total; x += XC_THREADS) {
-    int pos = x / nchunk, q = x - pos * nchunk;
-    int d = pos_dest[pos];
-    unsigned long long slot = base[d] + (unsigned long long)(pos - segstart[d]);
-    xc_copy_chunk<VW>(plan->dst[d][c] + slot * (unsigned long long)es + (size_t)q * VW,
-                      region + (size_t)pos * es + (size_t)q * VW);
+  for (int q = 0; q < nchunk; ++q) {
+    // stage this chunk of the column in destination-sorted order
+#pragma unroll
+    for (int j = 0; j < PER; ++j) {
+      int r = threadIdx.x + j * XC_THREADS;
+      if (r < rows && sortpos[j] >= 0)
+        xc_copy_chunk<VW>(stage + (size_t)sortpos[j] * VW,
+                          sp.cols[c] + (size_t)(row0 + r) * stride + (size_t)q * VW);
+    }
+    __syncthreads();
+    const int nsorted = segstart[sp.nparts];
+    for (int pos = threadIdx.x; pos < nsorted; pos += XC_THREADS) {
+      int d = pos_dest[pos];
+      unsigned long long slot = base[d] + (unsigned long long)(pos - segstart[d]);
+      xc_copy_chunk<VW>(plan->dst[d][c] + slot * (unsigned long long)es + (size_t)q * VW,
+                        stage + (size_t)pos * VW);
+    }
+    __syncthreads();
   }
 }
 
-__device__ __forceinline__ int xc_vw(const XcSpec& sp, int c) {
-  const uintptr_t al = (uintptr_t)sp.cols[c] | (uintptr_t)sp.stride[c] | (uintptr_t)sp.es[c];
-  if ((al & 15) == 0) return 16;
-  if ((al & 7) == 0) return 8;
-  if ((al & 3) == 0) return 4;
-  if ((al & 1) == 0) return 2;
-  return 1;
-}
-
-#define XC_STAGE_MAX (64 * 1024)  // upper bound of the dynamic staging buffer per CTA
-
-// Small tiles (1024 rows) and 256-thread CTAs: several CTAs are resident per SM
-// so the load phase of one overlaps the NVLink store phase of another.
 __global__ void __launch_bounds__(XC_THREADS) xchg_scatter_kernel(XcPeers pe, XcSpec sp, XcPlan* plan,
-                                                                 unsigned long long epoch,
-                                                                 unsigned int stage_bytes) {
+                                                                 unsigned long long epoch) {
   __shared__ int hist[XC_MAXP];
   __shared__ int segstart[XC_MAXP + 1];
   __shared__ unsigned long long base[XC_MAXP];
   __shared__ unsigned short pos_dest[XC_TILE];
-  extern __shared__ __align__(16) unsigned char stage[];
+  __shared__ __align__(16) unsigned char stage[XC_TILE * 16];
   constexpr int PER = XC_TILE / XC_THREADS;
   const int P = sp.nparts;
   if (plan->error == 0) {
@@ -306,45 +283,15 @@ __global__ void __launch_bounds__(XC_THREADS) xchg_scatter_kernel(XcPeers pe, Xc
         }
       }
       __syncthreads();
-      const int nsorted = segstart[P];
-      // columns are staged in groups that fit the staging buffer (all of them
-      // at once for ordinary row widths): one barrier per group, not per column
-      int c0 = 0;
-      while (c0 < sp.ncols) {
-        int c1 = c0;
-        size_t used = 0;
-        while (c1 < sp.ncols && used + (size_t)XC_TILE * sp.es[c1] <= stage_bytes) {
-          used += (size_t)XC_TILE * sp.es[c1];
-          ++c1;
-        }
-        if (c1 == c0) c1 = c0 + 1;  // a single very wide column: rows*es may exceed; handled below
-        size_t off = 0;
-        for (int c = c0; c < c1; ++c) {
-          unsigned char* region = stage + off;
-          switch (xc_vw(sp, c)) {
-            case 16: xc_stage_column<16>(sp, c, row0, rows, sortpos, region); break;
-            case 8: xc_stage_column<8>(sp, c, row0, rows, sortpos, region); break;
-            case 4: xc_stage_column<4>(sp, c, row0, rows, sortpos, region); break;
-            case 2: xc_stage_column<2>(sp, c, row0, rows, sortpos, region); break;
-            default: xc_stage_column<1>(sp, c, row0, rows, sortpos, region); break;
-          }
-          off += (size_t)XC_TILE * sp.es[c];
-        }
-        __syncthreads();
-        off = 0;
-        for (int c = c0; c < c1; ++c) {
-          const unsigned char* region = stage + off;
-          switch (xc_vw(sp, c)) {
-            case 16: xc_flush_column<16>(sp, plan, c, nsorted, pos_dest, segstart, base, region); break;
-            case 8: xc_flush_column<8>(sp, plan, c, nsorted, pos_dest, segstart, base, region); break;
-            case 4: xc_flush_column<4>(sp, plan, c, nsorted, pos_dest, segstart, base, region); break;
-            case 2: xc_flush_column<2>(sp, plan, c, nsorted, pos_dest, segstart, base, region); break;
-            default: xc_flush_column<1>(sp, plan, c, nsorted, pos_dest, segstart, base, region); break;
-          }
-          off += (size_t)XC_TILE * sp.es[c];
-        }
-        __syncthreads();
-        c0 = c1;
+      for (int c = 0; c < sp.ncols; ++c) {
+        const int es = sp.es[c];
+        const uintptr_t al = (uintptr_t)sp.cols[c] | (uintptr_t)sp.stride[c];
+        const bool a16 = (al & 15) == 0;
+        if (es % 16 == 0 && a16) xc_move_column<16>(sp, plan, c, row0, rows, sortpos, pos_dest, segstart, base, stage);
+        else if (es % 8 == 0 && (al & 7) == 0) xc_move_column<8>(sp, plan, c, row0, rows, sortpos, pos_dest, segstart, base, stage);
+        else if (es % 4 == 0 && (al & 3) == 0) xc_move_column<4>(sp, plan, c, row0, rows, sortpos, pos_dest, segstart, base, stage);
+        else if (es % 2 == 0 && (al & 1) == 0) xc_move_column<2>(sp, plan, c, row0, rows, sortpos, pos_dest, segstart, base, stage);
+        else xc_move_column<1>(sp, plan, c, row0, rows, sortpos, pos_dest, segstart, base, stage);
       }
     }
   }
@@ -487,28 +434,9 @@ BS_EXPORT int bs_xc_exchange(const void* peers_h, const void* spec_h, void* plan
   xchg_plan_kernel<<<1, 256, 0, stream>>>(pe, sp, plan, epoch, arena_base);
   BS_LAUNCH_CHECK();
   long long ntiles = (sp.n + XC_TILE - 1) / XC_TILE;
-  size_t row_bytes = 0, widest = 0;
-  for (int c = 0; c < sp.ncols; ++c) {
-    row_bytes += (size_t)sp.es[c];
-    if ((size_t)sp.es[c] > widest) widest = (size_t)sp.es[c];
-  }
-  if (widest * XC_TILE > XC_STAGE_MAX) return -3;  // a single column wider than 64 bytes per row
-  size_t stage = row_bytes * XC_TILE;
-  if (stage > XC_STAGE_MAX) stage = XC_STAGE_MAX;  // wide rows: columns are staged in groups
-  if (stage < 1024) stage = 1024;
-  static bool attr_set = false;
-  if (!attr_set) {
-    e = cudaFuncSetAttribute(xchg_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             XC_STAGE_MAX);
-    if (e != cudaSuccess) return (int)e;
-    attr_set = true;
-  }
-  int per_sm = (int)((200 * 1024) / (stage + 8 * 1024));
-  if (per_sm < 1) per_sm = 1;
-  if (per_sm > 6) per_sm = 6;
-  int blocks = (int)(ntiles < (long long)sms * per_sm ? ntiles : (long long)sms * per_sm);
+  int blocks = (int)(ntiles < (long long)sms * 2 ? ntiles : (long long)sms * 2);
   if (blocks < 1) blocks = 1;
-  xchg_scatter_kernel<<<blocks, XC_THREADS, stage, stream>>>(pe, sp, plan, epoch, (unsigned int)stage);
+  xchg_scatter_kernel<<<blocks, XC_THREADS, 0, stream>>>(pe, sp, plan, epoch);
   BS_LAUNCH_CHECK();
   xchg_wait_kernel<<<1, 32, 0, stream>>>(pe, plan, epoch);
   BS_LAUNCH_CHECK();

@@ -15,8 +15,10 @@ timeout 600 python bench.py --steps 10 --warmup 3 > gpurun_out/bench_n1.json 2> 
 echo "bench rc=$?" >> gpurun_out/bench_n1.err
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 300 --csv --log-file gpurun_out/launches.csv \
    python bench.py --steps 2 --warmup 3 --no-e2e > gpurun_out/ncu_launches.log 2>&1
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:hash_combine_tma -s 3 -c 1 -f -o gpurun_out/prof_combine_v2 \
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:hash_combine_tma -s 3 -c 1 -f -o gpurun_out/prof_combine_v2b \
    python bench.py --steps 1 --warmup 3 --no-e2e > gpurun_out/ncu_full.log 2>&1
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:xchg_scatter -s 8 -c 1 -f -o gpurun_out/prof_scatter_v0 \
+   python benchmarks/reshard_bw.py --max-mb 256 --iters 2 --out gpurun_out/reshard_1gpu.jsonl > gpurun_out/ncu_scatter.log 2>&1
 if [ "$NG" -ge 2 ]; then
   timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29561 \
      bench.py --gpus 2 --steps 10 --warmup 3 > gpurun_out/bench_n2.json 2> gpurun_out/bench_n2.err

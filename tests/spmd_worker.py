@@ -56,6 +56,83 @@ def chain(prev: bs.Slice):
     return bs.Reduce(bs.Map(prev, lambda k, v: (k % 5, v)), bs.ops.add)
 
 
+def exchange_content_check(ex, world, rank):
+    """Rows pushed through the fused exchange must arrive exactly once, intact,
+    at the owner of hash(key) % nparts — checked column by column."""
+    import torch.distributed as dist
+    from bigslice_b200.frame import hashing
+    ok = True
+    for n, nparts in ((300007, 2 * world + 1), (2500000, world)):
+        g = torch.Generator().manual_seed(100 + rank)
+        k = torch.randint(-(1 << 40), 1 << 40, (n,), generator=g)
+        a = torch.randn(n, generator=g)
+        b = torch.randint(0, 1 << 20, (n,), generator=g, dtype=torch.int32)
+        for zero_copy in (True, False):
+            got = ex.peers.exchange([k.cuda(), a.cuda(), b.cuda()], nparts, nkeys=1, zero_copy=zero_copy)
+            mine = {d: [c.cpu().clone() for c in cols] for d, cols in got.items()}
+            everything = [None] * world
+            dist.all_gather_object(everything, (k, a, b), group=ex.ctrl_group)
+            K = torch.cat([e[0] for e in everything])
+            A = torch.cat([e[1] for e in everything])
+            B = torch.cat([e[2] for e in everything])
+            dest = hashing.hash64(K, 0) % nparts
+            for d in range(rank, nparts, world):
+                sel = dest == d
+                wk, order = torch.sort(K[sel], stable=True)
+                wa, wb = A[sel][order], B[sel][order]
+                rk, rorder = torch.sort(mine[d][0], stable=True)
+                ra, rb = mine[d][1][rorder], mine[d][2][rorder]
+                if not (torch.equal(wk, rk)):
+                    ok = False
+                    continue
+                # rows with equal keys may arrive in any order: compare per-key multisets
+                pa = torch.stack([wk.double(), wa.double(), wb.double()], 1)
+                pb = torch.stack([rk.double(), ra.double(), rb.double()], 1)
+                if not torch.equal(torch.unique(pa, dim=0), torch.unique(pb, dim=0)):
+                    ok = False
+    return ok
+
+
+def big_wordcount_check(sess, ex, world, rank):
+    """A few steps of a 6M-row/rank Zipf wordcount through the table path (warm
+    + main levels, in-place table exchange, combine on arrival): totals and the
+    per-key counts must be exact on every step."""
+    import torch.distributed as dist
+    from bigslice_b200.models import wordcount as wc
+    from bigslice_b200.ops import gpu
+    gpu.HashTable.WARM_SLOTS = 1 << 16  # force the two-level path at this scale
+    n = 6000000
+    keys = wc.zipf_keys(n, 1 << 21, 1.0, seed=77 + rank, device="cuda")
+    vals = torch.ones(n, dtype=torch.int64, device="cuda")
+    empty = (torch.empty(0, dtype=torch.int64, device="cuda"),) * 2
+    wc.register_source("big", wc.DeviceRows([(keys, vals) if r == rank else empty for r in range(world)]))
+    allk = [None] * world
+    dist.all_gather_object(allk, keys.cpu(), group=ex.ctrl_group)
+    uk, cnt = torch.unique(torch.cat(allk), return_counts=True)
+    ok = True
+    for step in range(3):
+        res = sess.run(wc.wordcount, "big")
+        f = res.to_frame()
+        local = dict(zip(f.col(0).tolist(), f.col(1).tolist())) if len(f) else {}
+        everyone = [None] * world
+        dist.all_gather_object(everyone, local, group=ex.ctrl_group)
+        merged = {}
+        for d in everyone:
+            for k, v in d.items():
+                if k in merged:
+                    ok = False  # a key must live on exactly one rank
+                merged[k] = v
+        if len(merged) != len(uk) or sum(merged.values()) != n * world:
+            ok = False
+        else:
+            mk = torch.tensor(sorted(merged))
+            mv = torch.tensor([merged[k] for k in mk.tolist()])
+            ok = ok and torch.equal(mk, uk) and torch.equal(mv, cnt)
+        res.discard()
+    gpu.HashTable.WARM_SLOTS = 1 << 22
+    return ok
+
+
 def main():
     device = os.environ.get("BS_TEST_DEVICE", "cpu")
     shuffle = os.environ.get("BS_TEST_SHUFFLE", "auto")
@@ -99,6 +176,9 @@ def main():
     out["reshard_placement_ok"] = all(
         int(hashing.hash64(torch.tensor([k]), 0)[0]) % (2 * world + 1) % world == rank
         for k, _ in local)
+    if device != "cpu" and ex.peers is not None:
+        out["exchange_content_ok"] = exchange_content_check(ex, world, rank)
+        out["bigcount_ok"] = big_wordcount_check(sess, ex, world, rank)
     out["modes"] = sorted(set(e["mode"] for e in ex.exchange_log))
     try:
         from bigslice_b200.ops import gpu

@@ -202,3 +202,23 @@ def test_codec_device_crc_and_ragged_take(gpu):
         sliceio.read_all(sliceio.Decoder(io.BytesIO(bytes(bad)), f.typ), f.typ)
     lc = C.col_from_list([[1, 2], [], [3], [4, 5, 6]], slicetype.List(bs.int64), "cuda")
     assert C.col_take(lc, torch.tensor([3, 0, 1])).tolist() == [[4, 5, 6], [1, 2], []]
+
+
+@pytest.mark.parametrize("warm", [0, 1 << 12, 1 << 18])
+def test_two_level_table_at_scale(gpu, warm):
+    """8M Zipf rows through the TMA kernel into a warm+main table: exact counts,
+    also when the same table is fed in several chunks (streaming combine)."""
+    from bigslice_b200.models.wordcount import zipf_keys as zk
+    n = 8 << 20
+    keys = zk(n, 1 << 20, 1.0, seed=5, device="cuda")
+    vals = torch.randint(1, 4, (n,), device="cuda")
+    uk, inv = torch.unique(keys, return_inverse=True)
+    want = torch.zeros(len(uk), dtype=torch.int64, device="cuda").index_add_(0, inv, vals)
+    for chunks in (1, 3):
+        t = gpu.HashTable(4 * len(uk), torch.int64, "add", "cuda", warm=warm)
+        step = (n + chunks - 1) // chunks
+        for i in range(0, n, step):
+            t.combine(keys[i:i + step], vals[i:i + step])
+        k, v = t.compact()
+        order = torch.sort(k)[1]
+        assert torch.equal(k[order], uk) and torch.equal(v[order], want)

@@ -40,6 +40,10 @@ def check(outs, world):
         for k in ("wordcount_ok", "chain_ok", "strcount_ok", "join_ok", "reshard_ok",
                   "reshard_placement_ok"):
             assert o[k], (k, o)
+    for o in outs:
+        for k in ("exchange_content_ok", "bigcount_ok"):
+            if k in o:
+                assert o[k], (k, o["rank"])
     if world > 1:
         allk = [set(o["wordcount_local_keys"]) for o in outs]
         assert not (allk[0] & allk[1])  # each key lives on exactly one rank
@@ -58,6 +62,7 @@ def test_spmd_single_gpu_fused_self_exchange(tmp_path):
     outs = launch(1, tmp_path, device="cuda", shuffle="fused")
     check(outs, 1)
     assert "fused" in outs[0]["modes"] and outs[0]["launches"] > 0
+    assert outs[0]["exchange_content_ok"] and outs[0]["bigcount_ok"]
 
 
 @pytest.mark.gpu
