@@ -45,6 +45,7 @@ def parse():
     ap.add_argument("--e2e-steps", type=int, default=0, help="0 = min(steps, 5)")
     ap.add_argument("--shuffle", default="fused")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--seed", type=int, default=1234)
     return ap.parse_args()
 
 
@@ -124,7 +125,7 @@ def main():
     rank, world = dist.get_rank(), dist.get_world_size()
     dev = torch.device("cuda", torch.cuda.current_device())
     n = args.rows_per_gpu
-    keys = wc.zipf_keys(n, args.vocab, args.zipf, seed=1234 + rank, device=dev)
+    keys = wc.zipf_keys(n, args.vocab, args.zipf, seed=args.seed + rank, device=dev)
     vals = torch.ones(n, dtype=torch.int64, device=dev)
     # every rank registers the same source *names*; shard r holds rank r's rows
     empty = (torch.empty(0, dtype=torch.int64, device=dev),) * 2

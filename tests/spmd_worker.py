@@ -8,6 +8,7 @@ import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import bigslice_b200 as bs  # noqa: E402
+from bigslice_b200.models import wordcount as _wc  # noqa: E402,F401  (registers its Funcs before the session)
 
 N = 4000
 rng = np.random.default_rng(7)
