@@ -192,11 +192,16 @@ __device__ __forceinline__ void xc_move_column(const XcSpec& sp, const XcPlan* p
                                                long long row0, int rows, const int* sortpos,
                                                const unsigned short* pos_dest, const int* segstart,
                                                const unsigned long long* base,
-                                               unsigned char* stage) {
+                                               unsigned char* stage, unsigned char** sptr) {
   constexpr int PER = XC_TILE / XC_THREADS;
   const int es = sp.es[c];
   const int stride = sp.stride[c];
   const int nchunk = es / VW;
+  // Per destination: where sorted position 0 of this tile would land in the
+  // destination column (one pointer per destination, computed once per column),
+  // so the flush loop is a table lookup + one multiply-add per element.
+  for (int d = threadIdx.x; d < sp.nparts; d += XC_THREADS)
+    sptr[d] = plan->dst[d][c] + ((long long)base[d] - (long long)segstart[d]) * (long long)es;
   for (int q = 0; q < nchunk; ++q) {
     // stage this chunk of the column in destination-sorted order
 #pragma unroll
@@ -208,22 +213,21 @@ __device__ __forceinline__ void xc_move_column(const XcSpec& sp, const XcPlan* p
     }
     __syncthreads();
     const int nsorted = segstart[sp.nparts];
-    for (int pos = threadIdx.x; pos < nsorted; pos += XC_THREADS) {
-      int d = pos_dest[pos];
-      unsigned long long slot = base[d] + (unsigned long long)(pos - segstart[d]);
-      xc_copy_chunk<VW>(plan->dst[d][c] + slot * (unsigned long long)es + (size_t)q * VW,
-                        stage + (size_t)pos * VW);
-    }
+    const int qoff = q * VW;
+#pragma unroll 2
+    for (int pos = threadIdx.x; pos < nsorted; pos += XC_THREADS)
+      xc_copy_chunk<VW>(sptr[pos_dest[pos]] + (long long)pos * es + qoff, stage + (size_t)pos * VW);
     __syncthreads();
   }
 }
 
-__global__ void __launch_bounds__(XC_THREADS) xchg_scatter_kernel(XcPeers pe, XcSpec sp, XcPlan* plan,
+__global__ void __launch_bounds__(XC_THREADS, 2) xchg_scatter_kernel(XcPeers pe, XcSpec sp, XcPlan* plan,
                                                                  unsigned long long epoch) {
   __shared__ int hist[XC_MAXP];
   __shared__ int segstart[XC_MAXP + 1];
   __shared__ unsigned long long base[XC_MAXP];
   __shared__ unsigned short pos_dest[XC_TILE];
+  __shared__ unsigned char* sptr[XC_MAXP];
   __shared__ __align__(16) unsigned char stage[XC_TILE * 16];
   constexpr int PER = XC_TILE / XC_THREADS;
   const int P = sp.nparts;
@@ -287,11 +291,11 @@ __global__ void __launch_bounds__(XC_THREADS) xchg_scatter_kernel(XcPeers pe, Xc
         const int es = sp.es[c];
         const uintptr_t al = (uintptr_t)sp.cols[c] | (uintptr_t)sp.stride[c];
         const bool a16 = (al & 15) == 0;
-        if (es % 16 == 0 && a16) xc_move_column<16>(sp, plan, c, row0, rows, sortpos, pos_dest, segstart, base, stage);
-        else if (es % 8 == 0 && (al & 7) == 0) xc_move_column<8>(sp, plan, c, row0, rows, sortpos, pos_dest, segstart, base, stage);
-        else if (es % 4 == 0 && (al & 3) == 0) xc_move_column<4>(sp, plan, c, row0, rows, sortpos, pos_dest, segstart, base, stage);
-        else if (es % 2 == 0 && (al & 1) == 0) xc_move_column<2>(sp, plan, c, row0, rows, sortpos, pos_dest, segstart, base, stage);
-        else xc_move_column<1>(sp, plan, c, row0, rows, sortpos, pos_dest, segstart, base, stage);
+        if (es % 16 == 0 && a16) xc_move_column<16>(sp, plan, c, row0, rows, sortpos, pos_dest, segstart, base, stage, sptr);
+        else if (es % 8 == 0 && (al & 7) == 0) xc_move_column<8>(sp, plan, c, row0, rows, sortpos, pos_dest, segstart, base, stage, sptr);
+        else if (es % 4 == 0 && (al & 3) == 0) xc_move_column<4>(sp, plan, c, row0, rows, sortpos, pos_dest, segstart, base, stage, sptr);
+        else if (es % 2 == 0 && (al & 1) == 0) xc_move_column<2>(sp, plan, c, row0, rows, sortpos, pos_dest, segstart, base, stage, sptr);
+        else xc_move_column<1>(sp, plan, c, row0, rows, sortpos, pos_dest, segstart, base, stage, sptr);
       }
     }
   }
