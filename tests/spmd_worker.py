@@ -106,7 +106,11 @@ def big_wordcount_check(sess, ex, world, rank):
     keys = wc.zipf_keys(n, 1 << 21, 1.0, seed=77 + rank, device="cuda")
     vals = torch.ones(n, dtype=torch.int64, device="cuda")
     empty = (torch.empty(0, dtype=torch.int64, device="cuda"),) * 2
-    wc.register_source("big", wc.DeviceRows([(keys, vals) if r == rank else empty for r in range(world)]))
+    # two shards per rank (s and s + world): the exchange + combine-on-arrival path
+    # runs even on a single GPU
+    half = n // 2
+    mine = {rank: (keys[:half], vals[:half]), rank + world: (keys[half:], vals[half:])}
+    wc.register_source("big", wc.DeviceRows([mine.get(s, empty) for s in range(2 * world)]))
     allk = [None] * world
     dist.all_gather_object(allk, keys.cpu(), group=ex.ctrl_group)
     uk, cnt = torch.unique(torch.cat(allk), return_counts=True)
