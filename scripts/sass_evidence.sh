@@ -1,0 +1,25 @@
+#!/bin/bash
+# Regenerates profiles/sass/*.txt: SASS mnemonic histograms and the TMA / mbarrier /
+# peer-store instruction lines of the flagship kernels (cuobjdump -sass on the in-tree .so).
+set -e
+SO=bigslice_b200/_bscuda.so
+mkdir -p profiles/sass
+dump() {  # $1 = mangled-name regex, $2 = output stem
+  cuobjdump -sass $SO 2>/dev/null | awk -v pat="$1" '
+    /Function :/ {keep = ($0 ~ pat)} keep {print}' > /tmp/sass_$2.txt
+  {
+    echo "# $2 — SASS evidence (cuobjdump -sass $SO, function ~ /$1/)"
+    echo "lines: $(wc -l < /tmp/sass_$2.txt)"
+    echo; echo "## mnemonic histogram (memory / sync / atomic classes)"
+    grep -oE "\b(UBLKCP[.A-Z0-9_]*|UTMA[.A-Z0-9_]*|SYNCS[.A-Z0-9_]*|ATOMS[.A-Z0-9_]*|ATOMG[.A-Z0-9_]*|REDG[.A-Z0-9_]*|RED[.A-Z0-9_]*|LDG[.A-Z0-9_]*|STG[.A-Z0-9_]*|LDS[.A-Z0-9_]*|STS[.A-Z0-9_]*|MEMBAR[.A-Z0-9_]*|FENCE[.A-Z0-9_]*|MATCH[.A-Z0-9_]*|BAR[.A-Z0-9_]*|NANOSLEEP|CCTL[.A-Z0-9_]*|ERRBAR|UTC[A-Z0-9.]*MMA|HMMA[.A-Z0-9_]*)" /tmp/sass_$2.txt | sort | uniq -c | sort -rn
+    echo; echo "## selected instruction lines"
+    grep -nE "UBLKCP|SYNCS|ATOMG|REDG|\.SYS|MEMBAR|MATCH|createpolicy|EVICT|LDG.*\.(EF|EL)|STG.*STRONG" /tmp/sass_$2.txt | head -60
+  } > profiles/sass/$2.txt
+}
+dump "hash_combine_tma_kernelIxLi0" hash_combine_tma_i64_add
+dump "xchg_scatter_kernel" xchg_scatter
+dump "xchg_plan_kernel" xchg_plan
+dump "xchg_wait_kernel" xchg_wait
+dump "rs_scatter_kernel" radix_scatter
+dump "table_compact_kernelIxE" table_compact_i64
+ls -la profiles/sass

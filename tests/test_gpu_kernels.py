@@ -222,3 +222,26 @@ def test_two_level_table_at_scale(gpu, warm):
         k, v = t.compact()
         order = torch.sort(k)[1]
         assert torch.equal(k[order], uk) and torch.equal(v[order], want)
+
+
+def test_combine_on_arrival_shape(gpu):
+    """Destination-side shape: every key occurs once or twice with large partial
+    counts (two ranks' tables meeting); exact totals per key, through the TMA
+    kernel and the two-level table, odd row count."""
+    g = torch.Generator(device="cuda").manual_seed(11)
+    nk = 5_000_001
+    base = torch.randperm(1 << 23, device="cuda", generator=g)[:nk] * 0x9E3779B97F4A7C15 & 0x7FFFFFFFFFFFFFFF
+    dup = base[torch.rand(nk, device="cuda", generator=g) < 0.6]
+    keys = torch.cat([base, dup])
+    keys = keys[torch.randperm(keys.numel(), device="cuda", generator=g)]
+    vals = torch.randint(1, 9_000_000, (keys.numel(),), device="cuda", generator=g)
+    uk, inv = torch.unique(keys, return_inverse=True)
+    want = torch.zeros(len(uk), dtype=torch.int64, device="cuda").index_add_(0, inv, vals)
+    for warm in (None, 1 << 16, 0):
+        for rep in range(2):
+            t = gpu.HashTable(2 * len(uk), torch.int64, "add", "cuda", warm=warm)
+            t.combine(keys, vals)
+            k, v = t.compact()
+            order = torch.sort(k)[1]
+            assert torch.equal(k[order], uk)
+            assert torch.equal(v[order], want), (warm, rep, int((v[order] - want).abs().sum()))
