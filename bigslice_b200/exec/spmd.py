@@ -43,6 +43,7 @@ from ..frame import columns as C
 from ..sliceio import EmptyReader, FrameReader, MultiReader, Reader, decode_batch, encode_frame
 from ..slices import default_partitioner
 from .combiner import combine_frame
+from .invocation import InvocationGraph, fingerprint
 from .local import LocalExecutor, TaskBuffer, split_by_partition
 from .task import Task, TaskState, iter_tasks
 
@@ -92,6 +93,7 @@ class SpmdExecutor(LocalExecutor):
         self.peers = None
         self.exchanged: Dict[Tuple[int, int], List[Frame]] = {}
         self.group_done: Dict[int, threading.Event] = {}
+        self.invocations = InvocationGraph()
         self.group_err: Dict[int, BaseException] = {}
         self._glock = threading.Lock()
         self.exchange_log: List[dict] = []
@@ -154,16 +156,25 @@ class SpmdExecutor(LocalExecutor):
         if einv.inv.func >= self.registry_size:
             raise errors.fatal("bigslice.Func #%d was registered after the session started; "
                                "ranks cannot agree on it" % einv.inv.func)
+        self.invocations.add(einv)
         if self.world == 1:
             return do_compile(einv)
+        fp = fingerprint(einv.inv)
         if self.rank == 0:
             out = do_compile(einv)
-            box = [pickle.dumps(einv.env)]
+            box = [(fp, pickle.dumps(einv.env))]
             dist.broadcast_object_list(box, src=0, group=self.ctrl_group)
             return out
         box = [None]
         dist.broadcast_object_list(box, src=0, group=self.ctrl_group)
-        einv.env = pickle.loads(box[0])
+        fp0, env = box[0]
+        if fp0 != fp:
+            # every rank must issue the same invocation (the reference's workers
+            # compile exactly the driver's invocation: bigmachine.go:546-640)
+            raise errors.fatal("rank %d issued a different invocation than rank 0 at %s "
+                               "(inv%d, func #%d): SPMD programs must run identical Session.run "
+                               "sequences" % (self.rank, einv.location, einv.index, einv.inv.func))
+        einv.env = pickle.loads(env)
         return do_compile(einv)
 
     def begin_invocation(self, roots: Sequence[Task]) -> None:

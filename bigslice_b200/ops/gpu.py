@@ -31,6 +31,8 @@ SEGREDUCE_DTYPES = tuple(VTYPE)
 
 
 def lib_path() -> str:
+    if os.environ.get("BIGSLICE_CUDA_LIB"):  # debugging aid: load an alternative build
+        return os.environ["BIGSLICE_CUDA_LIB"]
     return os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "_bscuda.so")
 
 

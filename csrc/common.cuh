@@ -180,7 +180,8 @@ __device__ __forceinline__ unsigned long long bs_policy_evict_first() {
 }
 __device__ __forceinline__ long long bs_ld_hint_s64(const long long* p, unsigned long long pol) {
   long long v;
-  asm volatile("ld.global.L2::cache_hint.s64 %0, [%1], %2;" : "=l"(v) : "l"(p), "l"(pol) : "memory");
+  // .cg: served by L2 only (L1 is not coherent with the atomics other SMs issue)
+  asm volatile("ld.global.cg.L2::cache_hint.s64 %0, [%1], %2;" : "=l"(v) : "l"(p), "l"(pol) : "memory");
   return v;
 }
 // TMA 1-D bulk load with an L2 cache hint (streaming inputs use evict_first so

@@ -307,9 +307,40 @@ __global__ void __launch_bounds__(HC_THREADS, 1) hash_combine_tma_kernel(
         k[j] = idx < rows ? sk[idx] : 0;
         v[j] = idx < rows ? sv[idx] : Combine<V, OP>::identity();
       }
-      // stage drained into registers: hand the slot back before the atomics
-      __syncwarp();
-      if (lane == 0) bs_mbar_arrive(&empty[s]);
+#ifndef HC_DBG_LATE_ARRIVE
+      // Stage drained into registers: hand the slot back before the atomics.
+      // The arrive must not become visible while any lane's LDS is still in
+      // flight (the refilling TMA write is an async-proxy access that the
+      // mbarrier release does not order against outstanding generic-proxy
+      // reads; measured: rows of the *next* tile were read when the LSU queue
+      // was backed up behind global atomics).  The arriving lane is therefore
+      // elected from a ballot over a predicate computed from every loaded
+      // register: the vote cannot issue before all eight loads of all lanes
+      // have landed, and the arrive depends on the vote.
+      {
+        unsigned long long x = 0;
+#pragma unroll
+        for (int j = 0; j < HC_ROWS; ++j) {
+          unsigned long long vb = 0;
+          memcpy(&vb, &v[j], sizeof(V));
+          x ^= (unsigned long long)k[j] ^ vb;
+        }
+        unsigned b = __ballot_sync(0xffffffffu, (unsigned)(x ^ (x >> 32)) & 1u);
+        int leader = b ? __ffs((int)b) - 1 : 0;
+        if (lane == leader) bs_mbar_arrive(&empty[s]);
+      }
+#endif
+#ifdef HC_DBG_SUMKEYS
+      {
+        unsigned long long ks = 0, nr = 0;
+#pragma unroll
+        for (int j = 0; j < HC_ROWS; ++j)
+          if (tid + j * HC_CONSUMERS < rows) { ks += (unsigned long long)k[j]; nr += 1; }
+        atomicAdd(&st->special_val, ks);
+        atomicAdd(&st->out_count, nr);
+        continue;
+      }
+#endif
       // --- phase A: shared-memory hot table ---
       uint32_t h[HC_ROWS];
       unsigned miss = 0;
@@ -323,6 +354,10 @@ __global__ void __launch_bounds__(HC_THREADS, 1) hash_combine_tma_kernel(
         }
         h[j] = bs_mix_u64((uint64_t)k[j]);
         uint32_t sl = (h[j] >> 20) & (HC_SLOTS - 1);  // high bits: independent of the HBM slot bits
+#ifdef HC_DBG_NO_SMEM
+        miss |= 1u << j;
+        continue;
+#endif
         long long k0 = *(volatile long long*)&skeys[sl];
         if (k0 != k[j]) {
           if (k0 != BS_EMPTY_KEY) {
@@ -362,6 +397,10 @@ __global__ void __launch_bounds__(HC_THREADS, 1) hash_combine_tma_kernel(
 #pragma unroll
       for (int j = 0; j < HC_ROWS; ++j)
         if ((miss >> j) & 1u) main_resolve<V, OP>(tab, k[j], v[j], h[j], cur[j], st);
+#ifdef HC_DBG_LATE_ARRIVE
+      __syncwarp();
+      if (lane == 0) bs_mbar_arrive(&empty[s]);
+#endif
     }
   }
   __syncthreads();

@@ -268,3 +268,73 @@ def test_cache_with_strings_and_shuffle_dep_dropped(tmp_path):
     res = slicetest.run(build())
     assert dict(res.rows()) == {"a": 2, "b": 1, "c": 1}
     assert all(t.deps == [] for t in res.tasks)  # cached: no upstream tasks at all
+
+
+# ---- invocation transport (exec/invocation.go, bigmachine_inv_disk_cache.go) ----
+@bs.Func
+def _inv_codec_func(n: int, label: str, prev=None):
+    return bs.Const(2, torch.arange(n))
+
+
+def test_invocation_codec_roundtrip_and_refs():
+    from bigslice_b200.exec.compile import ExecInvocation
+    from bigslice_b200.exec import invocation as I
+    with bs.start(bs.Local) as sess:
+        r = sess.run(_inv_codec_func, 4, "a")
+        inv = _inv_codec_func.invocation("here.py:1", 8, "b", r)
+        einv = ExecInvocation(inv)
+        data = I.encode_invocation(einv)
+        # without a resolver the Result travels as a reference
+        d0 = I.decode_invocation(data)
+        assert d0.inv.args[:2] == [8, "b"] and d0.inv.args[2] == I.InvocationRef(r.inv_index)
+        assert (d0.index, d0.inv.func, d0.location) == (inv.index, inv.func, "here.py:1")
+        assert d0.env.__class__ is einv.env.__class__
+        d1 = I.decode_invocation(data, resolve=lambda i: r if i == r.inv_index else None)
+        assert d1.inv.args[2] is r
+        # fingerprints: equal for equal invocations, sensitive to args and to Result identity
+        same = _inv_codec_func.invocation("elsewhere.py:9", 8, "b", r)
+        same.index = inv.index
+        assert I.fingerprint(same) == I.fingerprint(inv)
+        other = _inv_codec_func.invocation("here.py:1", 9, "b", r)
+        other.index = inv.index
+        assert I.fingerprint(other) != I.fingerprint(inv)
+        g = I.InvocationGraph()
+        first = ExecInvocation(_inv_codec_func.invocation("x", 4, "a"))
+        first.index = first.inv.index = r.inv_index
+        g.add(first)
+        g.add(einv)
+        assert g.deps(einv.index) == {r.inv_index}
+        assert g.closure(einv.index) == [r.inv_index, einv.index]
+
+
+def test_inv_disk_cache(tmp_path):
+    from bigslice_b200.exec.invocation import InvDiskCache
+    c = InvDiskCache()
+    calls = []
+
+    def create(w):
+        calls.append(1)
+        w.write(b"x" * 100000)
+        w.write(b"tail")
+    for _ in range(3):
+        rd = c.get_or_create(7, create)
+        data = rd.read()
+        rd.close()
+        assert data == b"x" * 100000 + b"tail"
+    assert len(calls) == 1 and 7 in c
+
+    def bad(w):
+        w.write(b"partial")
+        raise ValueError("boom")
+    with pytest.raises(bs.errors.Error):
+        c.get_or_create(8, bad)
+    assert 8 not in c
+    rd = c.get_or_create(8, lambda w: w.write(b"ok"))
+    assert rd.read(1) == b"o" and rd.read() == b"k"
+    rd.close()
+    d = c._dir
+    c.close()
+    import os
+    assert not os.path.exists(d)
+    with pytest.raises(RuntimeError):
+        c.get_or_create(1, create)
