@@ -192,7 +192,14 @@ def col_to(c, device):
     if device is None:
         return c
     if isinstance(c, torch.Tensor):
-        return c if c.device == torch.device(device) else c.to(device, non_blocking=True)
+        dev = torch.device(device)
+        if c.device == dev:
+            return c
+        # Only host->device copies may be asynchronous: the consumer is a kernel
+        # ordered after the copy on the same stream.  A non-blocking device->host
+        # copy lands in freshly pinned memory that the host would read before the
+        # copy has finished (observed: stale tails of sorted frames).
+        return c.to(dev, non_blocking=(dev.type == "cuda"))
     if isinstance(c, ListColumn):
         return ListColumn(c.offsets.to(device), col_to(c.values, device), c.child_dtype)
     return c

@@ -245,3 +245,24 @@ def test_combine_on_arrival_shape(gpu):
             order = torch.sort(k)[1]
             assert torch.equal(k[order], uk)
             assert torch.equal(v[order], want), (warm, rep, int((v[order] - want).abs().sum()))
+
+
+@pytest.mark.gpu
+def test_device_to_host_frame_copy_is_complete():
+    """Frame.to('cpu') must not hand back memory a pending async copy is still filling."""
+    from bigslice_b200.frame import Frame
+    from bigslice_b200 import slicetype
+    typ = slicetype.Type([torch.int64, torch.int64], 1)
+    for it in range(20):
+        n = 1 << 22
+        a = torch.arange(n, device="cuda") + it
+        # queue enough work ahead of the copy that an asynchronous D2H would lag the host
+        b = a
+        for _ in range(8):
+            b = b * 3 + 1
+        host = Frame([a, b], typ).to("cpu")
+        want = a.cpu()
+        for _ in range(8):
+            want = want * 3 + 1
+        assert torch.equal(host.col(0), a.cpu())
+        assert torch.equal(host.col(1), want)
