@@ -46,6 +46,9 @@ def parse():
     ap.add_argument("--shuffle", default="fused")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--seed", type=int, default=1234)
+    ap.add_argument("--shards-per-gpu", type=int, default=1,
+                    help="split every GPU's rows into this many shards (tasks); >1 also exercises "
+                         "the fused exchange on a single GPU")
     return ap.parse_args()
 
 
@@ -129,7 +132,17 @@ def main():
     vals = torch.ones(n, dtype=torch.int64, device=dev)
     # every rank registers the same source *names*; shard r holds rank r's rows
     empty = (torch.empty(0, dtype=torch.int64, device=dev),) * 2
-    shards_dev = [(keys, vals) if r == rank else empty for r in range(world)]
+    S = max(args.shards_per_gpu, 1)
+    per = (n + S - 1) // S
+
+    def split(cols, nothing):
+        """Shard i lives on rank i % world: rank r's j-th piece is shard r + j*world."""
+        out = []
+        for i in range(S * world):
+            j = i // world
+            out.append(tuple(c[j * per:(j + 1) * per] for c in cols) if i % world == rank else nothing)
+        return out
+    shards_dev = split((keys, vals), empty)
     wc.register_source("rows_hbm", wc.DeviceRows(shards_dev))
     sess = bs.start(bs.Spmd(device="cuda", shuffle=args.shuffle, arena_bytes=2 << 30),
                     bs.Parallelism(2))
@@ -181,7 +194,11 @@ def main():
     sampler = ClockSampler(torch.cuda.current_device())
     if rank == 0:
         sampler.start()
+    from bigslice_b200.utils import spans
+    m0 = spans.mark()
     ms, launches, _ = timed("rows_hbm", args.steps, False)
+    if spans.enabled() and rank == 0:
+        sys.stderr.write("host spans per step (rank 0):\n%s\n" % spans.format_summary(m0, args.steps))
     clocks = sampler.stop() if rank == 0 else None
     total_rows = n * world
     value = total_rows * args.steps / (ms / 1e3)
@@ -194,7 +211,7 @@ def main():
         hk.copy_(keys)
         hv.copy_(vals)
         hempty = (torch.empty(0, dtype=torch.int64),) * 2
-        src = wc.PinnedRows([(hk, hv) if r == rank else hempty for r in range(world)])
+        src = wc.PinnedRows(split((hk, hv), hempty))
         wc.register_source("rows_pinned", src)
         for _ in range(3):
             r = step("rows_pinned")
@@ -218,7 +235,7 @@ def main():
                     % (args.zipf, args.vocab),
             "config": {"model": "Reduce-by-key wordcount (int64,int64) rows, Zipf keys",
                        "global_rows": total_rows, "rows_per_gpu": n, "row_bytes": 16,
-                       "parallelism": "dp%d (1 shard per GPU)" % world,
+                       "parallelism": "dp%d (%d shard%s per GPU)" % (world, S, "" if S == 1 else "s"),
                        "shuffle": args.shuffle,
                        "l2_policy": "inputs (%.1f GB/GPU) larger than the 126 MB L2" % (n * 16 / 1e9)},
             "gpu_launches": launches,

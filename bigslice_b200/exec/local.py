@@ -30,6 +30,7 @@ from .. import errors, metrics, slicefunc
 from ..frame import Frame, concat
 from ..sliceio import EmptyReader, FrameReader, MultiReader, Reader
 from .combiner import Combiner
+from ..utils.spans import span
 from .eval import Executor
 from .task import Task, TaskState
 
@@ -205,6 +206,10 @@ class LocalExecutor(Executor):
         return "local"
 
     def _run(self, task: Task, device=None) -> None:
+        with span("task/run"):
+            self._run_task(task, device)
+
+    def _run_task(self, task: Task, device=None) -> None:
         device = device if device is not None else self.device
         try:
             ins = self.dep_readers(task)

@@ -23,6 +23,7 @@ from typing import Any, Callable, Dict, List, Optional, Sequence
 from .. import errors, metrics, typecheck
 from ..frame import Frame, concat
 from ..func import FuncValue, Invocation
+from ..utils.spans import span
 from ..sliceio import MultiReader, Reader, Scanner, read_all
 from ..slices import Slice, make_name
 from ..status import Status
@@ -218,7 +219,7 @@ class Session:
             raise typecheck.TypecheckError(
                 "session.run: %r is not a bigslice.Func" % (funcv,), file, line)
         location = "%s:%d" % (file, line)
-        with typecheck.location(file, line):
+        with typecheck.location(file, line), span("run/compile"):
             with self._status_lock:
                 inv = funcv.invocation(location, *args)
             einv = ExecInvocation(inv)
@@ -252,9 +253,11 @@ class Session:
         t0 = time.time()
         begin = getattr(self.executor, "begin_invocation", None)
         if begin is not None:
-            begin(tasks)
+            with span("run/begin_invocation"):
+                begin(tasks)
         try:
-            evaluate(self.executor, tasks, group, pool=self._eval_pool())
+            with span("run/evaluate"):
+                evaluate(self.executor, tasks, group, pool=self._eval_pool())
         finally:
             log.debug("invocation %d (%s) evaluated in %.3fs", inv.index, location, time.time() - t0)
             if group is not None:

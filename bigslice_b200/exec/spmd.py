@@ -44,6 +44,8 @@ from ..sliceio import EmptyReader, FrameReader, MultiReader, Reader, decode_batc
 from ..slices import default_partitioner
 from .combiner import combine_frame
 from .invocation import InvocationGraph, fingerprint
+from ..utils.spans import span
+
 from .local import LocalExecutor, TaskBuffer, split_by_partition
 from .task import Task, TaskState, iter_tasks
 
@@ -163,10 +165,12 @@ class SpmdExecutor(LocalExecutor):
         if self.rank == 0:
             out = do_compile(einv)
             box = [(fp, pickle.dumps(einv.env))]
-            dist.broadcast_object_list(box, src=0, group=self.ctrl_group)
+            with span("compile/broadcast_env"):
+                dist.broadcast_object_list(box, src=0, group=self.ctrl_group)
             return out
         box = [None]
-        dist.broadcast_object_list(box, src=0, group=self.ctrl_group)
+        with span("compile/broadcast_env"):
+            dist.broadcast_object_list(box, src=0, group=self.ctrl_group)
         fp0, env = box[0]
         if fp0 != fp:
             # every rank must issue the same invocation (the reference's workers
@@ -244,10 +248,12 @@ class SpmdExecutor(LocalExecutor):
         return 0
 
     def _exchange_group(self, gid: int, group: List[Task]) -> None:
-        bad = self._local_status(group)
+        with span("xchg/wait_producers"):
+            bad = self._local_status(group)
         if self.world > 1:
             flag = torch.tensor([bad], dtype=torch.int32)
-            dist.all_reduce(flag, op=dist.ReduceOp.MAX, group=self.ctrl_group)
+            with span("xchg/status_vote"):
+                dist.all_reduce(flag, op=dist.ReduceOp.MAX, group=self.ctrl_group)
             bad = int(flag[0])
         if bad:
             raise errors.fatal("spmd: a producer of %s failed on some rank" % group[0].name)
@@ -257,7 +263,8 @@ class SpmdExecutor(LocalExecutor):
         with self._glock:
             table = self.group_tables.pop(gid, None)
         if table is not None:
-            return self._exchange_table(gid, head, table, nparts)
+            with span("xchg/table_total"):
+                return self._exchange_table(gid, head, table, nparts)
         frames: List[Frame] = []
         for t in group:
             if self.owns(t):
@@ -310,8 +317,12 @@ class SpmdExecutor(LocalExecutor):
             if t is None:
                 hint = self.card_hints.get(self._hint_key(task))
                 cap = 2 * hint + 1024 if hint is not None else 2 * max(rows_hint, 1 << 16)
-                t = gpu.HashTable(cap, task.type.typ.out(1).torch_dtype, task.combiner.builtin,
-                                  self.device)
+                # pooled: a table emptied by its last reader (clearing exchange or
+                # compaction) is reused without an init pass
+                t = gpu.table_pool().get(cap, task.type.typ.out(1).torch_dtype, task.combiner.builtin,
+                                         self.device)
+                if not (self.world == 1 and task.num_partition == 1):
+                    t.track(task.num_partition)  # destinations counted while combining
                 self.group_tables[gid] = t
             return t
 
@@ -322,16 +333,21 @@ class SpmdExecutor(LocalExecutor):
         ev0 = self._cuda_event()
         out: Dict[int, List[Frame]] = {}
         if self.world == 1 and nparts == 1:
-            k, v = table.compact()  # the local table is already the answer
+            # the local table is already the answer
+            clear = gpu.RECYCLE == "clear"
+            k, v = table.compact(clear=clear)
+            gpu.table_pool().put(table, clean=clear)
             out[0] = [Frame([k, v], typ)]
             sent = len(k)
             mode = "table-local"
         else:
-            got = self.peers.exchange_raw(table.column_desc(), table.total, nparts, nkeys=1,
-                                          skip_empty=True, zero_copy=True, keep=table)
-            st = table.status.tolist()
+            with span("xchg/exchange_table"):
+                got = self.peers.exchange_table(table, nparts, clear=gpu.RECYCLE == "clear")
+            with span("xchg/status_sync"):
+                st = table.status.tolist()
             if st[0]:
                 raise errors.fatal("spmd: combine table overflow (%d rows); cardinality hint too low" % st[0])
+            gpu.table_pool().put(table, clean=gpu.RECYCLE == "clear")
             sent = 0
             for p, (rk, rv) in got.items():
                 sent += rk.numel()
@@ -341,8 +357,9 @@ class SpmdExecutor(LocalExecutor):
                 # rows from different ranks may share keys: combine on arrival
                 dkey = self._hint_key(head) + "/dest%d" % p
                 dh = self.card_hints.get(dkey)
-                fk, fv = gpu.hash_combine(rk, rv, head.combiner.builtin,
-                                          distinct_hint=min(rk.numel(), dh) if dh else rk.numel())
+                with span("xchg/dest_combine"):
+                    fk, fv = gpu.hash_combine(rk, rv, head.combiner.builtin,
+                                              distinct_hint=min(rk.numel(), dh) if dh else rk.numel())
                 self.card_hints[dkey] = max(int(fk.numel() * 1.25), 1 << 12)
                 out[p] = [Frame([fk, fv], typ)]
             if st[1]:  # the reserved EMPTY key was present: route it on the host (rare)
@@ -525,7 +542,8 @@ class SpmdExecutor(LocalExecutor):
         fast = self._table_path_ok(task)
         try:
             while True:
-                f = out.read(None)
+                with span("task/read"):
+                    f = out.read(None)
                 if f is None:
                     break
                 nrec += len(f)
@@ -536,8 +554,10 @@ class SpmdExecutor(LocalExecutor):
                         rh = getattr(src, "rows_hint", None)
                         if rh is not None:
                             hint_rows = int(rh(task.name.shard))
-                        table = self._group_table(task, max(hint_rows, len(f)))
-                    table.combine(f.col(0), f.col(1))  # async: overlaps the next read
+                        with span("task/group_table"):
+                            table = self._group_table(task, max(hint_rows, len(f)))
+                    with span("task/combine_launch"):
+                        table.combine(f.col(0), f.col(1))  # async: overlaps the next read
                 else:
                     buf.append(0, f)
         finally:

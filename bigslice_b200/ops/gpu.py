@@ -166,6 +166,13 @@ def partition_frame(f: Frame, ids: torch.Tensor, npart: int) -> List[Frame]:
 
 # ---------------------------------------------------------------- hash combine
 
+def _norm_dev(device) -> torch.device:
+    d = torch.device(device)
+    if d.type == "cuda" and d.index is None:
+        d = torch.device("cuda", torch.cuda.current_device())
+    return d
+
+
 class HashTable:
     """HBM open-addressing table used by the combine kernels.
 
@@ -184,12 +191,30 @@ class HashTable:
         if warm is None:
             warm = self.WARM_SLOTS if cap >= 2 * self.WARM_SLOTS else 0
         self.cap, self.warm, self.total = cap, warm, cap + warm
-        self.vdtype, self.op, self.device = vdtype, op, device
+        self.vdtype, self.op, self.device = vdtype, op, _norm_dev(device)
         self.slots = torch.empty((self.total, 2), dtype=torch.int64, device=device)
         self.status = torch.zeros(4, dtype=torch.int64, device=device)
+        # destination tracking (see track()): counts of first-time insertions per shard
+        self.nparts = 0
+        self.dest_counts: Optional[torch.Tensor] = None
+        self.ready: Optional[torch.cuda.Event] = None  # pending background re-init
         self.reset()
 
+    def track(self, nparts: int) -> None:
+        """Count, while combining, how many distinct keys fall in each of the
+        ``nparts`` shards of the default partitioner (``murmur3(key) % nparts``);
+        the table exchange then needs no counting pass.  0 disables."""
+        if nparts and nparts > 256:
+            nparts = 0
+        self.nparts = int(nparts or 0)
+        if self.nparts:
+            if self.dest_counts is None:
+                self.dest_counts = torch.zeros(256, dtype=torch.int64, device=self.device)
+            else:
+                self.dest_counts.zero_()
+
     def reset(self):
+        self.nparts = 0
         _chk(_lib.bs_table_init(_ptr(self.slots), c_ll(self.total), c_int(VTYPE[self.vdtype]),
                                 c_int(OPS[self.op]), _ptr(self.status), _stream()), "table_init")
 
@@ -198,7 +223,9 @@ class HashTable:
         _chk(_lib.bs_hash_combine(_ptr(keys), _ptr(vals), c_ll(keys.numel()),
                                   c_int(VTYPE[self.vdtype]), c_int(OPS[self.op]), _ptr(self.slots),
                                   c_ll(self.warm), c_ll(self.cap), _ptr(self.status),
-                                  c_int(1 if force_simple else 0), _stream()), "hash_combine")
+                                  c_int(1 if force_simple else 0), c_int(self.nparts),
+                                  _ptr(self.dest_counts if self.nparts else None), _stream()),
+             "hash_combine")
 
     def column_desc(self):
         """(ptr, row_bytes, stride, dtype, tail) of the key and value fields for
@@ -207,13 +234,28 @@ class HashTable:
         vb = torch.empty(0, dtype=self.vdtype).element_size()
         return [(p, 8, 16, torch.int64, ()), (p + 8, vb, 16, self.vdtype, ())]
 
-    def compact(self, max_rows: Optional[int] = None) -> Tuple[torch.Tensor, torch.Tensor]:
-        """Dense (keys, vals) of the occupied slots; syncs once for the count."""
+    def identity_bits(self) -> int:
+        _lib.bs_identity_bits.restype = ctypes.c_ulonglong
+        return int(_lib.bs_identity_bits(c_int(VTYPE[self.vdtype]), c_int(OPS[self.op])))
+
+    def reset_status(self):
+        """Prepare a *clean* table (every slot EMPTY, e.g. after ``compact(clear=True)``
+        or a clearing exchange) for reuse: only the 32-byte status block is rewritten."""
+        _chk(_lib.bs_table_status_reset(_ptr(self.status), c_int(VTYPE[self.vdtype]),
+                                        c_int(OPS[self.op]), _stream()), "table_status_reset")
+        self.nparts = 0
+
+    def compact(self, max_rows: Optional[int] = None, clear: bool = False
+                ) -> Tuple[torch.Tensor, torch.Tensor]:
+        """Dense (keys, vals) of the occupied slots; syncs once for the count.
+        ``clear=True`` empties the table in the same pass (scan-and-clear)."""
         cap_out = self.total + 1 if max_rows is None else max_rows
         ok = torch.empty(cap_out, dtype=torch.int64, device=self.device)
         ov = torch.empty(cap_out, dtype=self.vdtype, device=self.device)
         _chk(_lib.bs_table_compact(_ptr(self.slots), c_ll(self.total), c_int(VTYPE[self.vdtype]),
-                                   _ptr(ok), _ptr(ov), _ptr(self.status), _stream()), "table_compact")
+                                   _ptr(ok), _ptr(ov), _ptr(self.status), c_int(1 if clear else 0),
+                                   ctypes.c_ulonglong(self.identity_bits() if clear else 0),
+                                   _stream()), "table_compact")
         st = self.status.tolist()
         if st[0]:
             raise TableFull(st[0])
@@ -238,18 +280,137 @@ def can_hash_combine(f: Frame, op: str) -> bool:
             and isinstance(v, torch.Tensor) and v.dtype in VTYPE and v.dim() == 1)
 
 
+# How a used combine table gets ready for its next use: "clear" = the pass that
+# reads it out (compaction / table scatter) also empties it; "reinit" = it is
+# re-initialised on a side stream, off the critical path of the next user;
+# "init" = the next user re-initialises it on its own stream.
+RECYCLE = os.environ.get("BIGSLICE_TABLE_RECYCLE", "init")
+
+
+class TablePool:
+    """Clean hash tables kept between uses.
+
+    A table handed back with :meth:`put` must be *clean* (all slots EMPTY): its
+    last reader was a clearing pass (``compact(clear=True)`` or the clearing
+    table exchange), so :meth:`get` only resets the status block instead of
+    re-initialising hundreds of megabytes of slots."""
+
+    def __init__(self, max_bytes: int = 8 << 30):
+        self._lock = threading.Lock()
+        self._free: dict = {}
+        self._made: dict = {}
+        self.tables_per_key = 2
+        self._bytes = 0
+        self.max_bytes = max_bytes
+        self.hits = 0
+        self.misses = 0
+
+    @staticmethod
+    def _key(t: "HashTable"):
+        return (t.cap, t.warm, t.vdtype, t.op, str(t.device))
+
+    def get(self, capacity: int, vdtype: torch.dtype, op: str, device, warm: Optional[int] = None
+            ) -> "HashTable":
+        cap = 1
+        while cap < max(capacity, 1024):
+            cap <<= 1
+        if warm is None:
+            warm = HashTable.WARM_SLOTS if cap >= 2 * HashTable.WARM_SLOTS else 0
+        key = (cap, warm, vdtype, op, str(_norm_dev(device)))
+        with self._lock:
+            lst = self._free.get(key) or []
+            t = None
+            # prefer a table whose background re-init has finished; while the only
+            # candidate is still being re-initialised, grow to a second table so
+            # consecutive steps ping-pong instead of waiting for the init
+            for i, c in enumerate(lst):
+                if c.ready is None or c.ready == "dirty" or c.ready.query():
+                    t = lst.pop(i)
+                    break
+            if t is None and lst and self._made.get(key, 0) >= self.tables_per_key:
+                t = lst.pop(0)
+            if t is not None:
+                self._bytes -= t.total * 16
+                self.hits += 1
+            else:
+                self.misses += 1
+                self._made[key] = self._made.get(key, 0) + 1
+        if t is None:
+            return HashTable(cap, vdtype, op, device, warm=warm)
+        if t.ready == "dirty":
+            t.ready = None
+            t.reset()
+        elif t.ready is not None:
+            torch.cuda.current_stream().wait_event(t.ready)  # background re-init (device-side wait)
+            t.ready = None
+        else:
+            t.reset_status()
+        return t
+
+    def put(self, t: "HashTable", clean: bool = True) -> None:
+        """Return a table.  ``clean=False``: its slots still hold the last result;
+        they are re-initialised on a side stream (ordered after the work queued on
+        the current stream), off the critical path of the next user."""
+        with self._lock:
+            if self._bytes + t.total * 16 > self.max_bytes:
+                return
+        if not clean and RECYCLE == "init":
+            t.ready = "dirty"  # re-initialised by the next user, on its own stream
+        elif not clean:
+            side = self._side_stream(t.device)
+            done = torch.cuda.Event()
+            done.record()                    # everything queued so far reads the table
+            side.wait_event(done)
+            t.slots.record_stream(side)
+            t.status.record_stream(side)
+            with torch.cuda.stream(side):
+                t.reset()
+                ev = torch.cuda.Event()
+                ev.record()
+            t.ready = ev
+        with self._lock:
+            self._free.setdefault(self._key(t), []).append(t)
+            self._bytes += t.total * 16
+
+    def _side_stream(self, device) -> "torch.cuda.Stream":
+        with self._lock:
+            st = getattr(self, "_streams", None)
+            if st is None:
+                st = self._streams = {}
+            key = str(device)
+            if key not in st:
+                st[key] = torch.cuda.Stream(device=device)
+            return st[key]
+
+    def clear(self) -> None:
+        with self._lock:
+            self._free.clear()
+            self._made.clear()
+            self._bytes = 0
+
+
+_pool = TablePool()
+
+
+def table_pool() -> TablePool:
+    return _pool
+
+
 def hash_combine(keys: torch.Tensor, vals: torch.Tensor, op: str,
                  distinct_hint: Optional[int] = None) -> Tuple[torch.Tensor, torch.Tensor]:
     """Reduce ``vals`` by ``keys`` with the hash-aggregation kernels."""
     n = keys.numel()
     cap = 2 * (distinct_hint if distinct_hint is not None else min(n, 1 << 22))
     while True:
-        t = HashTable(max(cap, 2048), vals.dtype, op, keys.device)
+        t = _pool.get(max(cap, 2048), vals.dtype, op, keys.device)
         t.combine(keys, vals)
         try:
-            return t.compact()
+            clear = RECYCLE == "clear"
+            out = t.compact(clear=clear)
+            _pool.put(t, clean=clear)
+            return out
         except TableFull:
-            cap = t.cap * 4  # rare: grow and redo
+            cap = t.cap * 4  # rare: grow and redo (the overflowed table is dropped)
 
 
 def hash_combine_frame(f: Frame, op: str) -> Frame:

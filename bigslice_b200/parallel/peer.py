@@ -178,7 +178,30 @@ class PeerGroup:
         self._chk(self.lib.bs_xc_exchange(ctypes.byref(self.peers), ctypes.byref(spec),
                                           c_void_p(self.plan.data_ptr()), c_ull(self.epoch),
                                           c_ull(0), gpu._stream()), "exchange")
-        plan = self.plan.cpu().numpy()  # one small D2H; syncs the stream
+        return self._collect(desc, nparts, zero_copy)
+
+    def exchange_table(self, table, nparts: int, clear: bool = True) -> Dict[int, List[torch.Tensor]]:
+        """Shuffle a :class:`~bigslice_b200.ops.gpu.HashTable` in place with the
+        specialised table kernels: rows of shard ``murmur3(key) % nparts`` arrive
+        as ``[keys, values]`` views of this rank's arena (zero copy; valid until
+        the next exchange).  With ``clear`` the table is left empty — ready for
+        reuse after ``reset_status()`` — so no separate init pass is needed."""
+        vb = torch.empty(0, dtype=table.vdtype).element_size()
+        self.epoch += 1
+        self._chk(self.lib.bs_xc_exchange_table(
+            ctypes.byref(self.peers), c_void_p(table.slots.data_ptr()), ctypes.c_longlong(table.total),
+            ctypes.c_int(vb), ctypes.c_int(nparts), c_void_p(self.plan.data_ptr()), c_ull(self.epoch),
+            c_ull(0), ctypes.c_int(1 if clear else 0),
+            c_ull(table.identity_bits() if clear else 0),
+            c_void_p(table.dest_counts.data_ptr() if table.nparts == nparts and nparts else 0),
+            gpu._stream()), "exchange_table")
+        desc = [(0, 8, 16, torch.int64, ()), (0, vb, 16, table.vdtype, ())]
+        return self._collect(desc, nparts, zero_copy=True)
+
+    def _collect(self, desc, nparts: int, zero_copy: bool) -> Dict[int, List[torch.Tensor]]:
+        """Read the plan back (one small D2H, syncs the stream) and build the
+        per-shard column views of the receive arena."""
+        plan = self.plan.cpu().numpy()
         err = int(plan[self.off_error:self.off_error + 4].view(np.int32)[0])
         if err == 1:
             raise ExchangeError("receive arena overflow (%d bytes): raise arena_bytes" % self.arena_bytes)
@@ -187,10 +210,11 @@ class PeerGroup:
         recv_total = plan[self.off_recv_total:self.off_recv_total + 8 * MAXP].view(np.int64)
         recv_off = plan[self.off_recv_off:self.off_recv_off + 8 * MAXP * MAXC].view(np.uint64).reshape(MAXP, MAXC)
         send = plan[self.off_send_count:self.off_send_count + 8 * MAXP].view(np.int64)
+        row_bytes = sum(d[1] for d in desc)
         self.last_sent = int(send[:nparts].sum())
         self.stats["exchanges"] += 1
-        self.stats["rows_sent"] += int(send[:nparts].sum())
-        self.stats["bytes_sent"] += int(send[:nparts].sum()) * sum(row_bytes)
+        self.stats["rows_sent"] += self.last_sent
+        self.stats["bytes_sent"] += self.last_sent * row_bytes
         out: Dict[int, List[torch.Tensor]] = {}
         for d in range(self.rank, nparts, self.world):
             rows = int(recv_total[d])
@@ -201,10 +225,6 @@ class PeerGroup:
                 t = view.view(dt).reshape((rows,) + tuple(tail))
                 got.append(t if zero_copy else t.clone())
             out[d] = got
-        if not zero_copy:
-            # the arena may be overwritten by the next exchange only after every
-            # rank has copied its rows out: the next count exchange orders that.
-            pass
         return out
 
     def close(self) -> None:

@@ -328,6 +328,385 @@ __global__ void xchg_wait_kernel(XcPeers pe, XcPlan* plan, unsigned long long ep
   __threadfence_system();
 }
 
+// ---------------------------------------------------------------------------
+// Hash-table exchange: the Reduce path shuffles an open-addressing table of
+// 16-byte <key, value> slots in place.  Specialised kernels (one 16-byte load per
+// slot, warp-aggregated ranking, optional scan-and-clear so the table is ready
+// for its next use without an init pass) instead of the generic column mover.
+#define XT_THREADS 256
+#define XT_PER 4
+#define XT_TILE (XT_THREADS * XT_PER)
+#define XT_CTAS_PER_SM 4
+
+struct __align__(16) XtSlot {
+  long long key;
+  unsigned long long val;
+};
+
+__device__ __forceinline__ int xt_dest(long long key, int P) {
+  return (int)(bs_murmur3_u64((uint64_t)key, 0u) % (uint32_t)P);
+}
+
+// Adds 1 to hist[d] for every lane with a valid d, one shared atomic per
+// distinct destination in the warp; returns the lane's rank among the rows of
+// its destination seen so far in this CTA.
+__device__ __forceinline__ int xt_rank(int* hist, int d, bool ok) {
+  const unsigned lane = threadIdx.x & 31u;
+  unsigned m = __match_any_sync(0xffffffffu, ok ? d : -1 - (int)lane);
+  int basev = 0;
+  const int leader = __ffs((int)m) - 1;
+  if (ok && (int)lane == leader) basev = atomicAdd(&hist[d], __popc(m));
+  basev = __shfl_sync(0xffffffffu, basev, leader);
+  return basev + __popc(m & ((1u << lane) - 1u));
+}
+
+// Counting pass for tables whose combine kernels did not track destinations.
+__global__ void __launch_bounds__(512) xchg_table_count_kernel(const XtSlot* __restrict__ slots,
+                                                                long long total, int P, XcPlan* plan) {
+  __shared__ int hist[XC_MAXP];
+  for (int d = threadIdx.x; d < P; d += blockDim.x) hist[d] = 0;
+  __syncthreads();
+  const long long chunk = (long long)blockDim.x * 4;
+  const long long nchunks = (total + chunk - 1) / chunk;
+  for (long long c = blockIdx.x; c < nchunks; c += gridDim.x) {
+    long long key[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      long long i = c * chunk + (long long)j * blockDim.x + threadIdx.x;
+      key[j] = i < total ? slots[i].key : BS_EMPTY_KEY;
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      bool ok = key[j] != BS_EMPTY_KEY;
+      if (__any_sync(0xffffffffu, ok)) xt_rank(hist, ok ? xt_dest(key[j], P) : 0, ok);
+    }
+  }
+  __syncthreads();
+  for (int d = threadIdx.x; d < P; d += blockDim.x)
+    if (hist[d]) atomicAdd((unsigned long long*)&plan->send_count[d], (unsigned long long)hist[d]);
+}
+
+// Scatter pass.  Four 256-thread CTAs per SM, each streaming 1024-slot tiles:
+// the next tile's slots are loaded (one 16-byte load per slot) while the
+// current tile is ranked, staged and flushed, so the DRAM latency of the scan
+// is off the per-tile barrier chain.
+template <int VB>
+__global__ void __launch_bounds__(XT_THREADS, XT_CTAS_PER_SM) xchg_table_scatter_kernel(
+    XcPeers pe, XtSlot* __restrict__ slots, long long total, int P, XcPlan* plan,
+    unsigned long long epoch, int clear, unsigned long long clear_bits) {
+  __shared__ int hist[XC_MAXP];
+  __shared__ int segstart[XC_MAXP + 1];
+  __shared__ unsigned char* kptr[XC_MAXP];
+  __shared__ unsigned char* vptr[XC_MAXP];
+  __shared__ long long skey[XT_TILE];
+  __shared__ unsigned long long sval[XT_TILE];
+  __shared__ unsigned short sdest[XT_TILE];
+  if (plan->error == 0) {
+    const long long ntiles = (total + XT_TILE - 1) / XT_TILE;
+    int4 nxt[XT_PER];
+    auto load_tile = [&](long long tile) {
+#pragma unroll
+      for (int j = 0; j < XT_PER; ++j) {
+        const long long i = tile * XT_TILE + threadIdx.x + j * XT_THREADS;
+        if (tile < ntiles && i < total) {
+          nxt[j] = *(const int4*)&slots[i];
+        } else {
+          XtSlot e;
+          e.key = BS_EMPTY_KEY;
+          e.val = 0;
+          memcpy(&nxt[j], &e, 16);
+        }
+      }
+    };
+    load_tile(blockIdx.x);
+    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      for (int d = threadIdx.x; d < P; d += blockDim.x) hist[d] = 0;
+      __syncthreads();
+      const long long row0 = tile * XT_TILE;
+      long long key[XT_PER];
+      unsigned long long val[XT_PER];
+      int dest[XT_PER], rank[XT_PER];
+#pragma unroll
+      for (int j = 0; j < XT_PER; ++j) {
+        XtSlot sl;
+        memcpy(&sl, &nxt[j], 16);
+        key[j] = sl.key;
+        val[j] = sl.val;
+      }
+#pragma unroll
+      for (int j = 0; j < XT_PER; ++j) {
+        const bool ok = key[j] != BS_EMPTY_KEY;
+        dest[j] = -1;
+        if (__any_sync(0xffffffffu, ok)) {
+          const int d = ok ? xt_dest(key[j], P) : 0;
+          rank[j] = xt_rank(hist, d, ok);
+          if (ok) {
+            dest[j] = d;
+            if (clear) {
+              XtSlot z;
+              z.key = BS_EMPTY_KEY;
+              z.val = clear_bits;
+              slots[row0 + threadIdx.x + j * XT_THREADS] = z;
+            }
+          }
+        }
+      }
+      load_tile(tile + gridDim.x);  // prefetch: consumed in the next iteration
+      __syncthreads();
+      // exclusive scan of hist (P <= 256: one warp, <= 8 entries per lane)
+      if (threadIdx.x < 32) {
+        const int lane = threadIdx.x;
+        const int per = (P + 31) / 32;
+        int local = 0;
+        for (int k = 0; k < per; ++k) {
+          int d = lane * per + k;
+          if (d < P) local += hist[d];
+        }
+        int incl = local;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          int t = __shfl_up_sync(0xffffffffu, incl, o);
+          if (lane >= o) incl += t;
+        }
+        int run = incl - local;
+        for (int k = 0; k < per; ++k) {
+          int d = lane * per + k;
+          if (d < P) {
+            segstart[d] = run;
+            run += hist[d];
+          }
+        }
+        if (lane == 31) segstart[P] = incl;
+      }
+      __syncthreads();
+      // one local atomic per destination reserves this tile's slot range; the
+      // per-destination pointers already include the (-segstart) shift so the
+      // flush below is pointer[dest] + pos * width
+      for (int d = threadIdx.x; d < P; d += blockDim.x) {
+        if (hist[d]) {
+          const long long b = (long long)atomicAdd(&plan->cursor[d], (unsigned long long)hist[d]) -
+                              (long long)segstart[d];
+          kptr[d] = plan->dst[d][0] + b * 8;
+          vptr[d] = plan->dst[d][1] + b * VB;
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < XT_PER; ++j) {
+        if (dest[j] >= 0) {
+          const int pos = segstart[dest[j]] + rank[j];
+          skey[pos] = key[j];
+          sval[pos] = val[j];
+          sdest[pos] = (unsigned short)dest[j];
+        }
+      }
+      __syncthreads();
+      const int nsorted = segstart[P];
+      for (int pos = threadIdx.x; pos < nsorted; pos += XT_THREADS) {
+        const int d = sdest[pos];
+        *(long long*)(kptr[d] + (long long)pos * 8) = skey[pos];
+        if (VB == 8) *(unsigned long long*)(vptr[d] + (long long)pos * 8) = sval[pos];
+        else *(unsigned int*)(vptr[d] + (long long)pos * 4) = (unsigned int)sval[pos];
+      }
+      __syncthreads();
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence_system();
+    unsigned int prev = atomicAdd(&plan->done_ctas, 1u);
+    if (prev == gridDim.x - 1) {
+      __threadfence_system();
+      for (int p = 0; p < pe.world; ++p) bs_st_release_sys(&pe.ctrl[p]->data_flag[pe.rank], epoch);
+    }
+  }
+}
+
+// Buffered scatter for few destinations (P <= 8, the one-shard-per-GPU case).
+// Reserving a slot range per (tile, destination) costs one returning atomic on
+// the same P cursor addresses per tile; those serialise in L2 (measured ~7 ns
+// each: 35 k tiles -> 0.5 ms for a 36 M-slot table).  Here one persistent CTA per
+// SM appends the rows it finds to per-destination buffers in shared memory
+// (software write combining) and only reserves + writes out a destination's
+// buffer when the next tile might not fit: one atomic per ~B rows, long
+// coalesced stores over NVLink, and no global-latency operation on the
+// per-tile path (the next tile's slots are prefetched into registers).
+#define XB_THREADS 1024
+#define XB_PER 4
+#define XB_TILE (XB_THREADS * XB_PER)
+#define XB_ROWS 8192  // staged rows per CTA: 8192 x 16 B = 128 KB of shared memory
+
+template <int VB>
+__device__ __forceinline__ void xb_store(const XcPlan* plan, int d, unsigned long long at, long long k,
+                                         unsigned long long v) {
+  ((long long*)plan->dst[d][0])[at] = k;
+  if (VB == 8) ((unsigned long long*)plan->dst[d][1])[at] = v;
+  else ((unsigned int*)plan->dst[d][1])[at] = (unsigned int)v;
+}
+
+template <int VB>
+__global__ void __launch_bounds__(XB_THREADS, 1) xchg_table_scatter_buf_kernel(
+    XcPeers pe, XtSlot* __restrict__ slots, long long total, int P, XcPlan* plan,
+    unsigned long long epoch, int clear, unsigned long long clear_bits) {
+  extern __shared__ __align__(16) unsigned char xb_smem[];
+  long long* bkey = (long long*)xb_smem;                        // [P][B]
+  unsigned long long* bval = (unsigned long long*)(bkey + XB_ROWS);
+  __shared__ int hist[8], fill[8], off[8], flushn[8], direct[8];
+  __shared__ unsigned long long gbase[8], dbase[8];
+  const int B = XB_ROWS / P;
+  const int tid = threadIdx.x;
+  const unsigned lane = tid & 31u;
+  const unsigned lt = (1u << lane) - 1u;
+  if (tid < 8) fill[tid] = 0;
+  if (plan->error == 0) {
+    const long long ntiles = (total + XB_TILE - 1) / XB_TILE;
+    int4 nxt[XB_PER];
+    auto load_tile = [&](long long tile) {
+#pragma unroll
+      for (int j = 0; j < XB_PER; ++j) {
+        const long long i = tile * XB_TILE + tid + j * XB_THREADS;
+        if (tile < ntiles && i < total) {
+          nxt[j] = *(const int4*)&slots[i];
+        } else {
+          XtSlot e;
+          e.key = BS_EMPTY_KEY;
+          e.val = 0;
+          memcpy(&nxt[j], &e, 16);
+        }
+      }
+    };
+    load_tile(blockIdx.x);
+    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      if (tid < 8) hist[tid] = 0;
+      __syncthreads();
+      long long key[XB_PER];
+      unsigned long long val[XB_PER];
+      int dest[XB_PER], rank[XB_PER];
+#pragma unroll
+      for (int j = 0; j < XB_PER; ++j) {
+        XtSlot sl;
+        memcpy(&sl, &nxt[j], 16);
+        key[j] = sl.key;
+        val[j] = sl.val;
+      }
+      load_tile(tile + gridDim.x);  // prefetch: consumed in the next iteration
+      // Warp-local ranking with ballots only (P <= 8): every lane learns how many
+      // of the warp's rows so far went to each destination; one shared atomic per
+      // (warp, destination) for the whole tile reserves the warp's range.
+      int mine = 0;  // rows of lane-th destination in this warp's part of the tile
+#pragma unroll
+      for (int j = 0; j < XB_PER; ++j) {
+        const bool ok = key[j] != BS_EMPTY_KEY;
+        const int d = ok ? xt_dest(key[j], P) : -1;
+        dest[j] = d;
+        rank[j] = 0;
+        for (int q = 0; q < P; ++q) {
+          const unsigned bal = __ballot_sync(0xffffffffu, d == q);
+          // rows of destination q seen in earlier j's are tracked by lane q
+          const int before = __shfl_sync(0xffffffffu, mine, q);
+          if (d == q) rank[j] = before + __popc(bal & lt);
+          if ((int)lane == q) mine += __popc(bal);
+        }
+        if (ok && clear) {
+          XtSlot z;
+          z.key = BS_EMPTY_KEY;
+          z.val = clear_bits;
+          slots[tile * XB_TILE + tid + j * XB_THREADS] = z;
+        }
+      }
+      int wbase = 0;
+      if ((int)lane < P && mine) wbase = atomicAdd(&hist[lane], mine);
+#pragma unroll
+      for (int j = 0; j < XB_PER; ++j) {
+        const int bq = __shfl_sync(0xffffffffu, wbase, dest[j] < 0 ? 0 : dest[j]);
+        rank[j] += bq;
+      }
+      __syncthreads();
+      // per destination: append behind what is buffered, flush first if it would
+      // not fit, or (a tile with more rows for one destination than a whole
+      // buffer) write this tile's rows directly
+      int need = 0;
+      if (tid < P) {
+        const int f = fill[tid], h = hist[tid];
+        const int dir = h > B;             // does not fit even in an empty buffer
+        need = (f + h > B) && f > 0;       // flush what is buffered first
+        flushn[tid] = need ? f : 0;
+        if (need) gbase[tid] = atomicAdd(&plan->cursor[tid], (unsigned long long)f);
+        direct[tid] = dir;
+        if (dir) dbase[tid] = atomicAdd(&plan->cursor[tid], (unsigned long long)h);
+        off[tid] = need ? 0 : f;
+        fill[tid] = dir ? 0 : (need ? 0 : f) + h;
+      }
+      if (__syncthreads_or(need)) {
+        for (int d = 0; d < P; ++d) {
+          const int n = flushn[d];
+          if (n == 0) continue;
+          const long long* ks = bkey + (size_t)d * B;
+          const unsigned long long* vs = bval + (size_t)d * B;
+          for (int i = tid; i < n; i += XB_THREADS) xb_store<VB>(plan, d, gbase[d] + i, ks[i], vs[i]);
+        }
+        __syncthreads();
+      }
+#pragma unroll
+      for (int j = 0; j < XB_PER; ++j) {
+        const int d = dest[j];
+        if (d >= 0) {
+          if (direct[d]) {
+            xb_store<VB>(plan, d, dbase[d] + rank[j], key[j], val[j]);
+          } else {
+            const int pos = d * B + off[d] + rank[j];
+            bkey[pos] = key[j];
+            bval[pos] = val[j];
+          }
+        }
+      }
+    }
+    // drain what is still buffered
+    __syncthreads();
+    if (tid < P) {
+      flushn[tid] = fill[tid];
+      if (fill[tid]) gbase[tid] = atomicAdd(&plan->cursor[tid], (unsigned long long)fill[tid]);
+    }
+    __syncthreads();
+    for (int d = 0; d < P; ++d) {
+      const int n = flushn[d];
+      if (n == 0) continue;
+      const long long* ks = bkey + (size_t)d * B;
+      const unsigned long long* vs = bval + (size_t)d * B;
+      for (int i = tid; i < n; i += XB_THREADS) xb_store<VB>(plan, d, gbase[d] + i, ks[i], vs[i]);
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence_system();
+    unsigned int prev = atomicAdd(&plan->done_ctas, 1u);
+    if (prev == gridDim.x - 1) {
+      __threadfence_system();
+      for (int p = 0; p < pe.world; ++p) bs_st_release_sys(&pe.ctrl[p]->data_flag[pe.rank], epoch);
+    }
+  }
+}
+
+template <int VB>
+static int xb_launch(const XcPeers& pe, XtSlot* tab, long long total, int nparts, XcPlan* plan,
+                     unsigned long long epoch, int clear, unsigned long long clear_bits, int sms,
+                     cudaStream_t stream) {
+  const int smem = XB_ROWS * 16;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(xchg_table_scatter_buf_kernel<VB>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return (int)e;
+    attr_set = true;
+  }
+  long long ntiles = (total + XB_TILE - 1) / XB_TILE;
+  int blocks = (int)(ntiles < sms ? ntiles : sms);
+  if (blocks < 1) blocks = 1;
+  xchg_table_scatter_buf_kernel<VB><<<blocks, XB_THREADS, smem, stream>>>(pe, tab, total, nparts, plan, epoch,
+                                                                           clear, clear_bits);
+  BS_LAUNCH_CHECK();
+  return 0;
+}
+
 // In-kernel barrier across ranks (flag all-to-all), used to fence arena reuse
 // and for device-side timing alignment.  No NCCL.
 __global__ void xchg_barrier_kernel(XcPeers pe, unsigned long long epoch, int* err) {
@@ -442,6 +821,69 @@ BS_EXPORT int bs_xc_exchange(const void* peers_h, const void* spec_h, void* plan
   if (blocks < 1) blocks = 1;
   xchg_scatter_kernel<<<blocks, XC_THREADS, 0, stream>>>(pe, sp, plan, epoch);
   BS_LAUNCH_CHECK();
+  xchg_wait_kernel<<<1, 32, 0, stream>>>(pe, plan, epoch);
+  BS_LAUNCH_CHECK();
+  return 0;
+}
+
+// Exchange of a hash table of `total` 16-byte slots (key, value bits): rows of
+// shard d = murmur3(key) % nparts land in the owner's arena as two dense columns
+// (int64 keys, vbytes-wide values) exactly like bs_xc_exchange with
+// skip_empty.  clear != 0 resets every occupied slot to <EMPTY, clear_bits>.
+// precounts (optional, device): exact per-shard row counts gathered while the
+// table was built; without them a counting pass scans the table first.
+BS_EXPORT int bs_xc_exchange_table(const void* peers_h, void* slots, long long total, int vbytes,
+                                   int nparts, void* plan_d, unsigned long long epoch,
+                                   unsigned long long arena_base, int clear,
+                                   unsigned long long clear_bits,
+                                   const unsigned long long* precounts, cudaStream_t stream) {
+  XcPeers pe = *(const XcPeers*)peers_h;
+  if (pe.world > XC_MAXW || nparts > XC_MAXP || nparts < 1 || (vbytes != 4 && vbytes != 8)) return -1;
+  XcSpec sp;
+  memset(&sp, 0, sizeof(sp));
+  sp.n = total;
+  sp.nparts = nparts;
+  sp.ncols = 2;
+  sp.nkeys = 1;
+  sp.skip_empty = 1;
+  sp.cols[0] = (const unsigned char*)slots;
+  sp.cols[1] = (const unsigned char*)slots + 8;
+  sp.es[0] = 8;
+  sp.es[1] = vbytes;
+  sp.stride[0] = sp.stride[1] = 16;
+  XcPlan* plan = (XcPlan*)plan_d;
+  cudaError_t e = cudaMemsetAsync(plan, 0, sizeof(XcPlan), stream);
+  if (e != cudaSuccess) return (int)e;
+  int sms = bs_num_sms();
+  XtSlot* tab = (XtSlot*)slots;
+  if (precounts != nullptr) {
+    // destinations were counted while the table was built (bs_hash_combine)
+    e = cudaMemcpyAsync(&plan->send_count[0], precounts, (size_t)nparts * sizeof(long long),
+                        cudaMemcpyDeviceToDevice, stream);
+    if (e != cudaSuccess) return (int)e;
+  } else if (total > 0) {
+    long long want = (total + 2047) / 2048;
+    int blocks = (int)(want < (long long)sms * 4 ? want : (long long)sms * 4);
+    xchg_table_count_kernel<<<blocks, 512, 0, stream>>>(tab, total, nparts, plan);
+    BS_LAUNCH_CHECK();
+  }
+  xchg_plan_kernel<<<1, 256, 0, stream>>>(pe, sp, plan, epoch, arena_base);
+  BS_LAUNCH_CHECK();
+  if (nparts <= 8) {
+    // few destinations: software write-combining in shared memory
+    int rc = vbytes == 8 ? xb_launch<8>(pe, tab, total, nparts, plan, epoch, clear, clear_bits, sms, stream)
+                         : xb_launch<4>(pe, tab, total, nparts, plan, epoch, clear, clear_bits, sms, stream);
+    if (rc != 0) return rc;
+  } else {
+    long long ntiles = (total + XT_TILE - 1) / XT_TILE;
+    int blocks = (int)(ntiles < (long long)sms * XT_CTAS_PER_SM ? ntiles : (long long)sms * XT_CTAS_PER_SM);
+    if (blocks < 1) blocks = 1;
+    if (vbytes == 8)
+      xchg_table_scatter_kernel<8><<<blocks, XT_THREADS, 0, stream>>>(pe, tab, total, nparts, plan, epoch, clear, clear_bits);
+    else
+      xchg_table_scatter_kernel<4><<<blocks, XT_THREADS, 0, stream>>>(pe, tab, total, nparts, plan, epoch, clear, clear_bits);
+    BS_LAUNCH_CHECK();
+  }
   xchg_wait_kernel<<<1, 32, 0, stream>>>(pe, plan, epoch);
   BS_LAUNCH_CHECK();
   return 0;

@@ -141,13 +141,24 @@ struct BsTable {
   BsSlot* main;
   unsigned long long main_mask;
   int has_warm;
+  // Optional: count newly inserted keys per destination shard
+  // (murmur3(key) % nparts, the exchange's partition function) while combining,
+  // so the table exchange needs no counting pass over the slot array.
+  int nparts;                       // 0: disabled
+  unsigned long long* dest_counts;  // [nparts], accumulated across launches
 };
+
+// A key was inserted for the first time: bump its destination's counter in the
+// CTA's shared histogram (flushed once per CTA).
+__device__ __forceinline__ void count_claim(const BsTable& t, int* dhist, long long key) {
+  if (t.nparts > 0) atomicAdd(&dhist[bs_murmur3_u64((uint64_t)key, 0u) % (uint32_t)t.nparts], 1);
+}
 
 __device__ __forceinline__ uint32_t bs_hash_main(uint32_t h) { return bs_fmix32(h + 0x9e3779b9u); }
 
 template <typename V, int OP>
 __device__ __forceinline__ void main_resolve(const BsTable& t, long long key, V val, uint32_t h2,
-                                             long long cur, BsCombineStatus* st) {
+                                             long long cur, BsCombineStatus* st, int* dhist) {
   unsigned long long slot = (unsigned long long)h2 & t.main_mask;
   // Linear probing; bounded so a full table cannot hang the GPU.
   for (int probe = 0; probe < 4096; ++probe) {
@@ -159,6 +170,7 @@ __device__ __forceinline__ void main_resolve(const BsTable& t, long long key, V 
       long long prev = (long long)atomicCAS((unsigned long long*)&t.main[slot].key,
                                             (unsigned long long)BS_EMPTY_KEY, (unsigned long long)key);
       if (prev == BS_EMPTY_KEY || prev == key) {
+        if (prev == BS_EMPTY_KEY) count_claim(t, dhist, key);
         Combine<V, OP>::apply(slot_val<V>(&t.main[slot]), val);
         return;
       }
@@ -173,13 +185,14 @@ __device__ __forceinline__ void main_resolve(const BsTable& t, long long key, V 
 // true when the row was absorbed.
 template <typename V, int OP>
 __device__ __forceinline__ bool warm_resolve(const BsTable& t, long long key, V val, uint32_t h,
-                                             long long cur) {
+                                             long long cur, int* dhist) {
   BsSlot* s = &t.warm[(unsigned long long)h & t.warm_mask];
   if (cur != key) {
     if (cur != BS_EMPTY_KEY) return false;
     long long prev = (long long)atomicCAS((unsigned long long*)&s->key,
                                           (unsigned long long)BS_EMPTY_KEY, (unsigned long long)key);
     if (prev != BS_EMPTY_KEY && prev != key) return false;
+    if (prev == BS_EMPTY_KEY) count_claim(t, dhist, key);
   }
   Combine<V, OP>::apply(slot_val<V>(s), val);
   return true;
@@ -187,13 +200,13 @@ __device__ __forceinline__ bool warm_resolve(const BsTable& t, long long key, V 
 
 template <typename V, int OP>
 __device__ __forceinline__ void table_insert(const BsTable& t, long long key, V val, uint32_t h,
-                                             BsCombineStatus* st) {
+                                             BsCombineStatus* st, int* dhist) {
   if (t.has_warm) {
     long long cur = __ldcg(&t.warm[(unsigned long long)h & t.warm_mask].key);
-    if (warm_resolve<V, OP>(t, key, val, h, cur)) return;
+    if (warm_resolve<V, OP>(t, key, val, h, cur, dhist)) return;
   }
   uint32_t h2 = bs_hash_main(h);
-  main_resolve<V, OP>(t, key, val, h2, __ldcg(&t.main[(unsigned long long)h2 & t.main_mask].key), st);
+  main_resolve<V, OP>(t, key, val, h2, __ldcg(&t.main[(unsigned long long)h2 & t.main_mask].key), st, dhist);
 }
 
 template <typename V, int OP>
@@ -240,6 +253,7 @@ static_assert(HC_THREADS <= 1024, "a CTA has at most 1024 threads");
 #define HC_ROWS 4
 #define HC_TILE (HC_CONSUMERS * HC_ROWS)
 #define HC_STAGES 2
+#define HC_DEST 256  // max destination shards tracked (XC_MAXP of the exchange)
 static_assert((HC_TILE * 4) % 16 == 0, "TMA sizes must be multiples of 16 bytes");
 
 template <typename V, int OP>
@@ -253,6 +267,7 @@ __global__ void __launch_bounds__(HC_THREADS, 1) hash_combine_tma_kernel(
   void* sacc = (void*)(skeys + HC_SLOTS);  // HC_SLOTS * 8 bytes
   uint64_t* full = (uint64_t*)((unsigned char*)sacc + (size_t)HC_SLOTS * 8);
   uint64_t* empty = full + HC_STAGES;
+  int* dhist = (int*)(empty + HC_STAGES);  // [HC_DEST] destination histogram of new keys
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31;
@@ -260,6 +275,7 @@ __global__ void __launch_bounds__(HC_THREADS, 1) hash_combine_tma_kernel(
     skeys[s] = BS_EMPTY_KEY;
     SmemAcc<V, OP>::init(sacc, s);
   }
+  if (tid < HC_DEST) dhist[tid] = 0;
   if (tid == 0) {
     for (int s = 0; s < HC_STAGES; ++s) {
       bs_mbar_init(&full[s], 1);
@@ -384,7 +400,7 @@ __global__ void __launch_bounds__(HC_THREADS, 1) hash_combine_tma_kernel(
                        : 0;
 #pragma unroll
         for (int j = 0; j < HC_ROWS; ++j)
-          if (((miss >> j) & 1u) && warm_resolve<V, OP>(tab, k[j], v[j], h[j], cur[j])) miss &= ~(1u << j);
+          if (((miss >> j) & 1u) && warm_resolve<V, OP>(tab, k[j], v[j], h[j], cur[j], dhist)) miss &= ~(1u << j);
       }
       // --- phase C: cold tail -> main level (DRAM): batched probes again ---
 #pragma unroll
@@ -396,7 +412,7 @@ __global__ void __launch_bounds__(HC_THREADS, 1) hash_combine_tma_kernel(
       }
 #pragma unroll
       for (int j = 0; j < HC_ROWS; ++j)
-        if ((miss >> j) & 1u) main_resolve<V, OP>(tab, k[j], v[j], h[j], cur[j], st);
+        if ((miss >> j) & 1u) main_resolve<V, OP>(tab, k[j], v[j], h[j], cur[j], st, dhist);
 #ifdef HC_DBG_LATE_ARRIVE
       __syncwarp();
       if (lane == 0) bs_mbar_arrive(&empty[s]);
@@ -408,7 +424,11 @@ __global__ void __launch_bounds__(HC_THREADS, 1) hash_combine_tma_kernel(
   for (int s = tid; s < HC_SLOTS; s += HC_THREADS) {
     long long key = skeys[s];
     if (key != BS_EMPTY_KEY)
-      table_insert<V, OP>(tab, key, SmemAcc<V, OP>::read(sacc, s), bs_mix_u64((uint64_t)key), st);
+      table_insert<V, OP>(tab, key, SmemAcc<V, OP>::read(sacc, s), bs_mix_u64((uint64_t)key), st, dhist);
+  }
+  if (tab.nparts > 0) {
+    __syncthreads();
+    if (tid < tab.nparts && dhist[tid]) atomicAdd(&tab.dest_counts[tid], (unsigned long long)dhist[tid]);
   }
 }
 
@@ -418,6 +438,11 @@ template <typename V, int OP>
 __global__ void __launch_bounds__(512) hash_combine_simple_kernel(
     const long long* __restrict__ keys, const V* __restrict__ vals, long long n,
     BsTable tab, BsCombineStatus* __restrict__ st) {
+  __shared__ int dhist[HC_DEST];
+  if (tab.nparts > 0) {
+    for (int d = threadIdx.x; d < HC_DEST; d += blockDim.x) dhist[d] = 0;
+    __syncthreads();
+  }
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   long long stride = (long long)gridDim.x * blockDim.x;
   for (; i < n; i += stride) {
@@ -427,7 +452,12 @@ __global__ void __launch_bounds__(512) hash_combine_simple_kernel(
       special_insert<V, OP>(val, st);
       continue;
     }
-    table_insert<V, OP>(tab, key, val, bs_mix_u64((uint64_t)key), st);
+    table_insert<V, OP>(tab, key, val, bs_mix_u64((uint64_t)key), st, dhist);
+  }
+  if (tab.nparts > 0) {
+    __syncthreads();
+    for (int d = threadIdx.x; d < tab.nparts; d += blockDim.x)
+      if (dhist[d]) atomicAdd(&tab.dest_counts[d], (unsigned long long)dhist[d]);
   }
 }
 
@@ -437,11 +467,13 @@ __global__ void __launch_bounds__(512) hash_combine_simple_kernel(
 #define TC_THREADS 256
 #define TC_ITEMS 8
 template <typename V>
-__global__ void __launch_bounds__(TC_THREADS) table_compact_kernel(const BsSlot* __restrict__ tab,
+__global__ void __launch_bounds__(TC_THREADS) table_compact_kernel(BsSlot* __restrict__ tab,
                                                                    long long cap,
                                                                    long long* __restrict__ out_keys,
                                                                    V* __restrict__ out_vals,
-                                                                   BsCombineStatus* __restrict__ st) {
+                                                                   BsCombineStatus* __restrict__ st,
+                                                                   int clear,
+                                                                   unsigned long long clear_bits) {
   __shared__ unsigned int wcnt[TC_ITEMS][TC_THREADS / 32];
   __shared__ unsigned long long chunk_base;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -456,6 +488,14 @@ __global__ void __launch_bounds__(TC_THREADS) table_compact_kernel(const BsSlot*
       if (i < cap) {
         const int4 raw = *(const int4*)&tab[i];
         memcpy(&sl[j], &raw, 16);
+        // scan-and-clear: leave the table ready for its next use, so a pooled
+        // table never needs a separate init pass
+        if (clear && sl[j].key != BS_EMPTY_KEY) {
+          BsSlot z;
+          z.key = BS_EMPTY_KEY;
+          z.val = clear_bits;
+          tab[i] = z;
+        }
       } else {
         sl[j].key = BS_EMPTY_KEY;
       }
@@ -497,13 +537,13 @@ __global__ void __launch_bounds__(TC_THREADS) table_compact_kernel(const BsSlot*
 template <typename V>
 static size_t hc_smem_bytes() {
   return (size_t)HC_STAGES * HC_TILE * (sizeof(long long) + sizeof(V)) +
-         (size_t)HC_SLOTS * (sizeof(long long) + 8) + 2 * HC_STAGES * sizeof(uint64_t) + 16;
+         (size_t)HC_SLOTS * (sizeof(long long) + 8) + 2 * HC_STAGES * sizeof(uint64_t) + HC_DEST * sizeof(int) + 16;
 }
 
 template <typename V, int OP>
 static int launch_combine(const long long* keys, const V* vals, long long n, BsSlot* slots,
                           long long warm_cap, long long cap, BsCombineStatus* st, int force_simple,
-                          cudaStream_t stream) {
+                          int nparts, unsigned long long* dest_counts, cudaStream_t stream) {
   if (n <= 0) return 0;
   BsTable tab;
   tab.warm = slots;
@@ -511,6 +551,8 @@ static int launch_combine(const long long* keys, const V* vals, long long n, BsS
   tab.has_warm = warm_cap > 0;
   tab.main = slots + warm_cap;
   tab.main_mask = (unsigned long long)cap - 1;
+  tab.nparts = dest_counts != nullptr ? nparts : 0;
+  tab.dest_counts = dest_counts;
   int sms = bs_num_sms();
   bool aligned = (((uintptr_t)keys | (uintptr_t)vals) & 15) == 0;
   // TMA sizes must be multiples of 16 bytes: peel a ragged tail.
@@ -559,6 +601,27 @@ static int launch_combine(const long long* keys, const V* vals, long long n, BsS
     default: return -1;                                                                \
   }
 
+// Bit pattern of the combine identity (low sizeof(V) bytes), as stored in empty slots.
+BS_EXPORT unsigned long long bs_identity_bits(int vtype, int op) {
+  const bool wide = vtype == BS_I64 || vtype == BS_F64;
+  const bool fp = vtype == BS_F32 || vtype == BS_F64;
+  if (op == BS_MIN) return wide ? (fp ? 0x7ff0000000000000ULL : 0x7fffffffffffffffULL)
+                                : (fp ? 0x7f800000ULL : 0x7fffffffULL);
+  if (op == BS_MAX) return wide ? (fp ? 0xfff0000000000000ULL : 0x8000000000000000ULL)
+                                : (fp ? 0xff800000ULL : 0x80000000ULL);
+  return 0ULL;
+}
+
+// Reset the status block of a (clean) table before it is reused.
+BS_EXPORT int bs_table_status_reset(void* status, int vtype, int op, cudaStream_t stream) {
+  BsCombineStatus z;
+  z.failed = 0;
+  z.has_special = 0;
+  z.out_count = 0;
+  z.special_val = bs_identity_bits(vtype, op);
+  return (int)cudaMemcpyAsync(status, &z, sizeof(z), cudaMemcpyHostToDevice, stream);
+}
+
 template <typename V, int OP>
 static int launch_init(void* tab, long long cap, BsCombineStatus* st, cudaStream_t stream) {
   int blocks = (int)((cap + 255) / 256 < (long long)bs_num_sms() * 8 ? (cap + 255) / 256
@@ -593,30 +656,36 @@ BS_EXPORT int bs_table_init(void* tab, long long total, int vtype, int op, void*
 template <typename V, int OP>
 static int combine_entry(const long long* keys, const void* vals, long long n, void* tab,
                          long long warm_cap, long long cap, void* st, int force_simple,
-                         cudaStream_t stream) {
+                         int nparts, unsigned long long* dest_counts, cudaStream_t stream) {
   return launch_combine<V, OP>(keys, (const V*)vals, n, (BsSlot*)tab, warm_cap, cap,
-                               (BsCombineStatus*)st, force_simple, stream);
+                               (BsCombineStatus*)st, force_simple, nparts, dest_counts, stream);
 }
 
 // warm_cap: 0 or a power of two; cap: power of two.  tab holds warm_cap + cap slots.
+// nparts/dest_counts (optional): accumulate, per destination shard
+// murmur3(key) % nparts, the number of keys inserted for the first time.
 BS_EXPORT int bs_hash_combine(const long long* keys, const void* vals, long long n, int vtype, int op,
                               void* tab, long long warm_cap, long long cap, void* status,
-                              int force_simple, cudaStream_t stream) {
+                              int force_simple, int nparts, unsigned long long* dest_counts,
+                              cudaStream_t stream) {
   if (cap <= 0 || (cap & (cap - 1)) || (warm_cap & (warm_cap - 1)) || warm_cap < 0) return -2;
-  DISPATCH_VOP(combine_entry, keys, vals, n, tab, warm_cap, cap, status, force_simple, stream)
+  if (dest_counts != nullptr && (nparts < 1 || nparts > HC_DEST)) return -2;
+  DISPATCH_VOP(combine_entry, keys, vals, n, tab, warm_cap, cap, status, force_simple, nparts,
+               dest_counts, stream)
 }
 
-BS_EXPORT int bs_table_compact(const void* tab, long long cap, int vtype, long long* out_keys,
-                               void* out_vals, void* status, cudaStream_t stream) {
+BS_EXPORT int bs_table_compact(void* tab, long long cap, int vtype, long long* out_keys,
+                               void* out_vals, void* status, int clear, unsigned long long clear_bits,
+                               cudaStream_t stream) {
   long long nchunks = (cap + (long long)TC_THREADS * TC_ITEMS - 1) / ((long long)TC_THREADS * TC_ITEMS);
   int blocks = (int)(nchunks < (long long)bs_num_sms() * 8 ? nchunks : (long long)bs_num_sms() * 8);
   BsCombineStatus* st = (BsCombineStatus*)status;
-  const BsSlot* t = (const BsSlot*)tab;
+  BsSlot* t = (BsSlot*)tab;
   switch (vtype) {
-    case BS_I32: table_compact_kernel<int><<<blocks, TC_THREADS, 0, stream>>>(t, cap, out_keys, (int*)out_vals, st); break;
-    case BS_I64: table_compact_kernel<long long><<<blocks, TC_THREADS, 0, stream>>>(t, cap, out_keys, (long long*)out_vals, st); break;
-    case BS_F32: table_compact_kernel<float><<<blocks, TC_THREADS, 0, stream>>>(t, cap, out_keys, (float*)out_vals, st); break;
-    case BS_F64: table_compact_kernel<double><<<blocks, TC_THREADS, 0, stream>>>(t, cap, out_keys, (double*)out_vals, st); break;
+    case BS_I32: table_compact_kernel<int><<<blocks, TC_THREADS, 0, stream>>>(t, cap, out_keys, (int*)out_vals, st, clear, clear_bits); break;
+    case BS_I64: table_compact_kernel<long long><<<blocks, TC_THREADS, 0, stream>>>(t, cap, out_keys, (long long*)out_vals, st, clear, clear_bits); break;
+    case BS_F32: table_compact_kernel<float><<<blocks, TC_THREADS, 0, stream>>>(t, cap, out_keys, (float*)out_vals, st, clear, clear_bits); break;
+    case BS_F64: table_compact_kernel<double><<<blocks, TC_THREADS, 0, stream>>>(t, cap, out_keys, (double*)out_vals, st, clear, clear_bits); break;
     default: return -1;
   }
   BS_LAUNCH_CHECK();

@@ -94,6 +94,54 @@ def exchange_content_check(ex, world, rank):
     return ok
 
 
+def table_exchange_check(ex, world, rank):
+    """The specialised in-place table exchange: every <key, value> of every rank's
+    table arrives exactly once at the owner of hash(key) % nparts, and the clearing
+    scatter leaves the source table empty (reusable without an init pass)."""
+    import torch.distributed as dist
+    from bigslice_b200.frame import hashing
+    from bigslice_b200.ops import gpu
+    ok = True
+    for vdtype, nparts, warm in ((torch.int64, 2 * world + 1, None), (torch.int32, world, 1 << 12),
+                                 (torch.float32, 3 * world, 0), (torch.int64, 12 * world + 1, None),
+                                 (torch.int32, 1, None)):
+        g = torch.Generator().manual_seed(500 + rank)
+        n = 400000
+        k = torch.randint(-(1 << 40), 1 << 40, (n,), generator=g)
+        v = torch.randint(1, 1000, (n,), generator=g).to(vdtype)
+        t = gpu.HashTable(2 * n, vdtype, "add", "cuda", warm=warm)
+        for rep in range(2):  # second round reuses the cleared table ...
+            if rep == 1:
+                t.track(nparts)  # ... with destinations counted while combining
+            t.combine(k.cuda(), v.cuda())
+            got = ex.peers.exchange_table(t, nparts, clear=True)
+            mine = {d: [c.cpu().clone() for c in cols] for d, cols in got.items()}
+            if int((t.slots[:, 0] != -(1 << 63)).sum()) != 0:
+                ok = False  # not cleared
+            if int((t.slots[:, 1] != 0).sum()) != 0:
+                ok = False  # values not reset to the identity
+            t.reset_status()
+            uk, inv = torch.unique(k, return_inverse=True)
+            uv = torch.zeros(len(uk), dtype=torch.float64).index_add_(0, inv, v.double())
+            everything = [None] * world
+            dist.all_gather_object(everything, (uk, uv), group=ex.ctrl_group)
+            for d in range(rank, nparts, world):
+                want = []
+                for ek, ev in everything:
+                    sel = hashing.hash64(ek, 0) % nparts == d
+                    want.append(torch.stack([ek[sel].double(), ev[sel]], 1))
+                want = torch.cat(want)
+                have = torch.stack([mine[d][0].double(), mine[d][1].double()], 1)
+                if want.shape != have.shape:
+                    ok = False
+                    continue
+                w = want[torch.argsort(want[:, 0] * 1e6 + want[:, 1])]
+                h = have[torch.argsort(have[:, 0] * 1e6 + have[:, 1])]
+                if not torch.equal(torch.unique(w, dim=0), torch.unique(h, dim=0)):
+                    ok = False
+    return ok
+
+
 def big_wordcount_check(sess, ex, world, rank):
     """A few steps of a 6M-row/rank Zipf wordcount through the table path (warm
     + main levels, in-place table exchange, combine on arrival): totals and the
@@ -183,6 +231,7 @@ def main():
         for k, _ in local)
     if device != "cpu" and ex.peers is not None:
         out["exchange_content_ok"] = exchange_content_check(ex, world, rank)
+        out["table_exchange_ok"] = table_exchange_check(ex, world, rank)
         out["bigcount_ok"] = big_wordcount_check(sess, ex, world, rank)
     out["modes"] = sorted(set(e["mode"] for e in ex.exchange_log))
     try:

@@ -266,3 +266,38 @@ def test_device_to_host_frame_copy_is_complete():
             want = want * 3 + 1
         assert torch.equal(host.col(0), a.cpu())
         assert torch.equal(host.col(1), want)
+
+
+@pytest.mark.gpu
+def test_scan_and_clear_compaction_and_table_pool(gpu):
+    """compact(clear=True) returns the same rows and leaves every slot <EMPTY, identity>,
+    so a pooled table is reusable after a 32-byte status reset."""
+    g = torch.Generator(device="cuda").manual_seed(3)
+    for vdtype, op in ((torch.int64, "add"), (torch.float32, "max"), (torch.int32, "min")):
+        keys = torch.randint(-5000, 5000, (300000,), device="cuda", generator=g)
+        keys[::1000] = -(1 << 63)  # the reserved key takes the special path
+        vals = torch.randint(-100, 100, (300000,), device="cuda", generator=g).to(vdtype)
+        t = gpu.HashTable(1 << 15, vdtype, op, "cuda", warm=1 << 10)
+        ident = t.identity_bits()
+        ref = None
+        for rep in range(3):
+            t.combine(keys, vals)
+            k, v = t.compact(clear=True)
+            order = torch.argsort(k)
+            cur = (k[order].cpu(), v[order].cpu())
+            if ref is None:
+                ref = cur
+                uk = torch.unique(keys)
+                assert torch.equal(cur[0], uk.cpu())
+            assert torch.equal(cur[0], ref[0]) and torch.equal(cur[1], ref[1])
+            assert bool((t.slots[:, 0] == -(1 << 63)).all())
+            want_bits = ident if ident < (1 << 63) else ident - (1 << 64)
+            assert bool((t.slots[:, 1] == want_bits).all())
+            t.reset_status()
+    pool = gpu.table_pool()
+    h0 = pool.hits
+    a = gpu.hash_combine(keys, vals.to(torch.int64), "add")
+    b = gpu.hash_combine(keys, vals.to(torch.int64), "add")
+    assert pool.hits > h0
+    oa, ob = torch.argsort(a[0]), torch.argsort(b[0])
+    assert torch.equal(a[0][oa], b[0][ob]) and torch.equal(a[1][oa], b[1][ob])

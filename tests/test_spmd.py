@@ -41,7 +41,7 @@ def check(outs, world):
                   "reshard_placement_ok"):
             assert o[k], (k, o)
     for o in outs:
-        for k in ("exchange_content_ok", "bigcount_ok"):
+        for k in ("exchange_content_ok", "table_exchange_ok", "bigcount_ok"):
             if k in o:
                 assert o[k], (k, o["rank"])
     if world > 1:
@@ -62,7 +62,7 @@ def test_spmd_single_gpu_fused_self_exchange(tmp_path):
     outs = launch(1, tmp_path, device="cuda", shuffle="fused")
     check(outs, 1)
     assert "fused" in outs[0]["modes"] and outs[0]["launches"] > 0
-    assert outs[0]["exchange_content_ok"] and outs[0]["bigcount_ok"]
+    assert outs[0]["exchange_content_ok"] and outs[0]["bigcount_ok"] and outs[0]["table_exchange_ok"]
 
 
 @pytest.mark.gpu
