@@ -199,6 +199,15 @@ def main():
     ms, launches, _ = timed("rows_hbm", args.steps, False)
     if spans.enabled() and rank == 0:
         sys.stderr.write("host spans per step (rank 0):\n%s\n" % spans.format_summary(m0, args.steps))
+        raw = spans.raw(m0)
+        # timeline of the last step (ms relative to its Session.run start)
+        starts = [t0 for (nm, th, t0, t1) in raw if nm == "run/compile"]
+        if starts:
+            z = starts[-1]
+            sys.stderr.write("timeline of the last step (ms from run start):\n")
+            for nm, th, t0, t1 in sorted(raw, key=lambda r: r[2]):
+                if t0 >= z:
+                    sys.stderr.write("  %7.3f .. %7.3f  %-26s %s\n" % ((t0 - z) * 1e3, (t1 - z) * 1e3, nm, th))
     clocks = sampler.stop() if rank == 0 else None
     total_rows = n * world
     value = total_rows * args.steps / (ms / 1e3)

@@ -78,7 +78,31 @@ class ExecInvocation:
         self.env = env or CompileEnv.make()
 
     def invoke(self) -> Slice:
-        return self.inv.invoke()
+        """The invocation's slice graph (the Func body runs once per ExecInvocation)."""
+        if getattr(self, "_slice", None) is None:
+            self._slice = self.inv.invoke()
+        return self._slice
+
+    def uses_cache(self) -> bool:
+        """Whether any slice of the graph consults a shard cache at compile time —
+        the only thing a CompileEnv records, so only such invocations need their
+        environment shipped to the other ranks."""
+        from .session import Result
+        seen = set()
+        stack = [self.invoke()]
+        while stack:
+            sl = stack.pop()
+            if id(sl) in seen:
+                continue
+            seen.add(id(sl))
+            inner = Unwrap(sl)
+            if isinstance(sl, slicecache.Cacheable) or isinstance(inner, slicecache.Cacheable):
+                return True
+            if isinstance(inner, Result):
+                continue
+            for i in range(sl.num_dep()):
+                stack.append(sl.dep(i).slice)
+        return False
 
 
 def pipeline(slice_: Slice) -> List[Slice]:

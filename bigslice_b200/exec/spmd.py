@@ -29,6 +29,7 @@ from __future__ import annotations
 
 import os
 import pickle
+import queue
 import threading
 import time
 from typing import Any, Dict, List, Optional, Sequence, Tuple
@@ -96,6 +97,9 @@ class SpmdExecutor(LocalExecutor):
         self.exchanged: Dict[Tuple[int, int], List[Frame]] = {}
         self.group_done: Dict[int, threading.Event] = {}
         self.invocations = InvocationGraph()
+        self._pending_fp: List[Tuple[int, str, int, int]] = []
+        self._coll_thread: Optional[threading.Thread] = None
+        self._coll_q: Optional[queue.Queue] = None
         self.group_err: Dict[int, BaseException] = {}
         self._glock = threading.Lock()
         self.exchange_log: List[dict] = []
@@ -134,6 +138,10 @@ class SpmdExecutor(LocalExecutor):
             self.peers = PeerGroup(self.ctrl_group, self.arena_bytes, self.device)
 
         def shutdown():
+            if self._coll_thread is not None:
+                self._coll_q.put(None)
+                self._coll_thread.join(timeout=5)
+                self._coll_thread = None
             if self.peers is not None:
                 self.peers.close()
         return shutdown
@@ -161,25 +169,41 @@ class SpmdExecutor(LocalExecutor):
         self.invocations.add(einv)
         if self.world == 1:
             return do_compile(einv)
-        fp = fingerprint(einv.inv)
+        # Every rank must issue the same invocation (the reference's workers compile
+        # exactly the driver's invocation, bigmachine.go:546-640): the fingerprint
+        # rides on the next control-plane vote instead of costing a collective here.
+        self._pending_fp.append((einv.index, einv.location, einv.inv.func,
+                                 int(fingerprint(einv.inv)[:15], 16)))
+        if not einv.uses_cache():
+            return do_compile(einv)  # nothing in a CompileEnv to agree on
         if self.rank == 0:
             out = do_compile(einv)
-            box = [(fp, pickle.dumps(einv.env))]
+            box = [pickle.dumps(einv.env)]
             with span("compile/broadcast_env"):
                 dist.broadcast_object_list(box, src=0, group=self.ctrl_group)
             return out
         box = [None]
         with span("compile/broadcast_env"):
             dist.broadcast_object_list(box, src=0, group=self.ctrl_group)
-        fp0, env = box[0]
-        if fp0 != fp:
-            # every rank must issue the same invocation (the reference's workers
-            # compile exactly the driver's invocation: bigmachine.go:546-640)
-            raise errors.fatal("rank %d issued a different invocation than rank 0 at %s "
-                               "(inv%d, func #%d): SPMD programs must run identical Session.run "
-                               "sequences" % (self.rank, einv.location, einv.index, einv.inv.func))
-        einv.env = pickle.loads(env)
+        einv.env = pickle.loads(box[0])
         return do_compile(einv)
+
+    def _vote(self, bad: int) -> int:
+        """Control-plane agreement before an exchange: did every rank's producers
+        succeed, and did every rank issue the same invocations since the last vote."""
+        fps, self._pending_fp = self._pending_fp, []
+        acc = 0
+        for _, _, _, fp in fps:
+            acc = (acc * 1000003 + fp) & ((1 << 61) - 1)
+        flag = torch.tensor([bad, acc, -acc], dtype=torch.int64)
+        with span("xchg/status_vote"):
+            dist.all_reduce(flag, op=dist.ReduceOp.MAX, group=self.ctrl_group)
+        if int(flag[1]) != -int(flag[2]):
+            where = ", ".join("inv%d at %s (func #%d)" % f[:3] for f in fps) or "an earlier invocation"
+            raise errors.fatal("ranks issued different invocations: %s on rank %d does not match the "
+                               "other ranks; SPMD programs must run identical Session.run sequences"
+                               % (where, self.rank))
+        return int(flag[0])
 
     def begin_invocation(self, roots: Sequence[Task]) -> None:
         """Start the collective thread that performs this invocation's group
@@ -217,14 +241,28 @@ class SpmdExecutor(LocalExecutor):
         todo.sort(key=lambda x: (x[0], x[1]))
         if not todo:
             return
-        th = threading.Thread(target=self._collective_loop, args=(todo,), daemon=True,
-                              name="bigslice-spmd-collective")
-        th.start()
+        # One long-lived collective thread serves every invocation, in submission
+        # order: exchanges of different invocations never interleave differently
+        # on different ranks, and no thread is created per run.
+        with self._glock:
+            if self._coll_thread is None:
+                self._coll_q = queue.Queue()
+                self._coll_thread = threading.Thread(target=self._collective_main, daemon=True,
+                                                     name="bigslice-spmd-collective")
+                self._coll_thread.start()
+        self._coll_q.put(todo)
 
     # -- the collective thread ---------------------------------------------------
-    def _collective_loop(self, todo) -> None:
+    def _collective_main(self) -> None:
         if self.device is not None and self.device.type == "cuda":
             torch.cuda.set_device(self.device)
+        while True:
+            todo = self._coll_q.get()
+            if todo is None:
+                return
+            self._collective_loop(todo)
+
+    def _collective_loop(self, todo) -> None:
         failed: Optional[BaseException] = None
         for _, _, gid, group in todo:
             ev = self.group_done[gid]
@@ -251,10 +289,7 @@ class SpmdExecutor(LocalExecutor):
         with span("xchg/wait_producers"):
             bad = self._local_status(group)
         if self.world > 1:
-            flag = torch.tensor([bad], dtype=torch.int32)
-            with span("xchg/status_vote"):
-                dist.all_reduce(flag, op=dist.ReduceOp.MAX, group=self.ctrl_group)
-            bad = int(flag[0])
+            bad = self._vote(bad)
         if bad:
             raise errors.fatal("spmd: a producer of %s failed on some rank" % group[0].name)
         head = group[0]

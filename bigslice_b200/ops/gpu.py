@@ -299,7 +299,7 @@ class TablePool:
         self._lock = threading.Lock()
         self._free: dict = {}
         self._made: dict = {}
-        self.tables_per_key = 2
+        self.tables_per_key = int(os.environ.get("BIGSLICE_POOL_TABLES", 2))
         self._bytes = 0
         self.max_bytes = max_bytes
         self.hits = 0

@@ -24,6 +24,7 @@ import torch
 import torch.distributed as dist
 
 from ..ops import gpu
+from ..utils.spans import span
 
 c_void_p, c_int, c_ll, c_ull = ctypes.c_void_p, ctypes.c_int, ctypes.c_longlong, ctypes.c_ulonglong
 
@@ -201,7 +202,8 @@ class PeerGroup:
     def _collect(self, desc, nparts: int, zero_copy: bool) -> Dict[int, List[torch.Tensor]]:
         """Read the plan back (one small D2H, syncs the stream) and build the
         per-shard column views of the receive arena."""
-        plan = self.plan.cpu().numpy()
+        with span("xchg/plan_d2h_sync"):
+            plan = self.plan.cpu().numpy()
         err = int(plan[self.off_error:self.off_error + 4].view(np.int32)[0])
         if err == 1:
             raise ExchangeError("receive arena overflow (%d bytes): raise arena_bytes" % self.arena_bytes)
