@@ -351,7 +351,7 @@ class SpmdExecutor(LocalExecutor):
             t = self.group_tables.get(gid)
             if t is None:
                 hint = self.card_hints.get(self._hint_key(task))
-                cap = 2 * hint + 1024 if hint is not None else 2 * max(rows_hint, 1 << 16)
+                cap = gpu.table_capacity(hint) if hint is not None else 2 * max(rows_hint, 1 << 16)
                 # pooled: a table emptied by its last reader (clearing exchange or
                 # compaction) is reused without an init pass
                 t = gpu.table_pool().get(cap, task.type.typ.out(1).torch_dtype, task.combiner.builtin,
@@ -381,7 +381,10 @@ class SpmdExecutor(LocalExecutor):
             with span("xchg/status_sync"):
                 st = table.status.tolist()
             if st[0]:
-                raise errors.fatal("spmd: combine table overflow (%d rows); cardinality hint too low" % st[0])
+                self.card_hints[self._hint_key(head)] = 4 * max(self.card_hints.get(self._hint_key(head), 0), 1 << 16)
+                raise errors.fatal("spmd: combine table overflow (%d rows): the number of distinct keys "
+                                   "more than doubled since the last run of this slice; the estimate has "
+                                   "been raised, re-run the invocation" % st[0])
             gpu.table_pool().put(table, clean=gpu.RECYCLE == "clear")
             sent = 0
             for p, (rk, rv) in got.items():
@@ -395,13 +398,13 @@ class SpmdExecutor(LocalExecutor):
                 with span("xchg/dest_combine"):
                     fk, fv = gpu.hash_combine(rk, rv, head.combiner.builtin,
                                               distinct_hint=min(rk.numel(), dh) if dh else rk.numel())
-                self.card_hints[dkey] = max(int(fk.numel() * 1.25), 1 << 12)
+                self.card_hints[dkey] = max(int(fk.numel() * 1.15), 1 << 12)
                 out[p] = [Frame([fk, fv], typ)]
             if st[1]:  # the reserved EMPTY key was present: route it on the host (rare)
                 self._route_special(head, st[2], nparts, out, typ)
             mode = "fused-table"
-        self.card_hints[self._hint_key(head)] = max(int(sent * 1.25), 1 << 12) if self.world == 1 \
-            else max(int(self.peers.last_sent * 1.25), 1 << 12)
+        self.card_hints[self._hint_key(head)] = max(int(sent * 1.15), 1 << 12) if self.world == 1 \
+            else max(int(self.peers.last_sent * 1.15), 1 << 12)
         with self._glock:
             for p in range(self.rank, nparts, self.world):
                 self.exchanged[(gid, p)] = [x for x in out.get(p, []) if len(x)]

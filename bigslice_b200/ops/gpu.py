@@ -166,6 +166,21 @@ def partition_frame(f: Frame, ids: torch.Tensor, npart: int) -> List[Frame]:
 
 # ---------------------------------------------------------------- hash combine
 
+def quantise_capacity(n: int) -> int:
+    """Round ``n`` up to five significant bits (<= 6 % above ``n``): table sizes
+    follow the cardinality closely — every scan of the slot array (init,
+    compaction, exchange) is proportional to it — while slightly different
+    estimates still map to the same pooled table."""
+    n = max(int(n), 1024)
+    k = n.bit_length() - 5
+    return n if k <= 0 else ((n + (1 << k) - 1) >> k) << k
+
+
+def table_capacity(distinct_estimate: int) -> int:
+    """Main-level slots for an expected number of distinct keys (load <= ~0.55)."""
+    return quantise_capacity(int(1.8 * distinct_estimate) + 1024)
+
+
 def _norm_dev(device) -> torch.device:
     d = torch.device(device)
     if d.type == "cuda" and d.index is None:
@@ -185,9 +200,7 @@ class HashTable:
 
     def __init__(self, capacity: int, vdtype: torch.dtype, op: str, device, warm: Optional[int] = None):
         require()
-        cap = 1
-        while cap < max(capacity, 1024):
-            cap <<= 1
+        cap = quantise_capacity(capacity)
         if warm is None:
             warm = self.WARM_SLOTS if cap >= 2 * self.WARM_SLOTS else 0
         self.cap, self.warm, self.total = cap, warm, cap + warm
@@ -311,9 +324,7 @@ class TablePool:
 
     def get(self, capacity: int, vdtype: torch.dtype, op: str, device, warm: Optional[int] = None
             ) -> "HashTable":
-        cap = 1
-        while cap < max(capacity, 1024):
-            cap <<= 1
+        cap = quantise_capacity(capacity)
         if warm is None:
             warm = HashTable.WARM_SLOTS if cap >= 2 * HashTable.WARM_SLOTS else 0
         key = (cap, warm, vdtype, op, str(_norm_dev(device)))
@@ -400,7 +411,7 @@ def hash_combine(keys: torch.Tensor, vals: torch.Tensor, op: str,
                  distinct_hint: Optional[int] = None) -> Tuple[torch.Tensor, torch.Tensor]:
     """Reduce ``vals`` by ``keys`` with the hash-aggregation kernels."""
     n = keys.numel()
-    cap = 2 * (distinct_hint if distinct_hint is not None else min(n, 1 << 22))
+    cap = table_capacity(distinct_hint if distinct_hint is not None else min(n, 1 << 22))
     while True:
         t = _pool.get(max(cap, 2048), vals.dtype, op, keys.device)
         t.combine(keys, vals)

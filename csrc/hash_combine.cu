@@ -127,7 +127,7 @@ __global__ void __launch_bounds__(256) table_init_kernel(BsSlot* __restrict__ ta
 }
 
 // ---- two-level HBM table ----------------------------------------------------
-// slots = [ warm (warm_mask+1 slots) | main (main_mask+1 slots) ].
+// slots = [ warm (warm_mask+1 slots, a power of two) | main (main_cap slots, any size) ].
 //  * warm: direct-mapped, small enough to live in the 126 MB L2 (accessed with
 //    evict_last hints).  A key that finds its warm slot free claims it for good;
 //    a key whose warm slot belongs to another key always goes to `main`.  Hence
@@ -139,7 +139,7 @@ struct BsTable {
   BsSlot* warm;
   unsigned long long warm_mask;  // 0 when there is no warm level
   BsSlot* main;
-  unsigned long long main_mask;
+  unsigned long long main_cap;   // any size < 2^32: slots are picked by fast range reduction
   int has_warm;
   // Optional: count newly inserted keys per destination shard
   // (murmur3(key) % nparts, the exchange's partition function) while combining,
@@ -155,11 +155,17 @@ __device__ __forceinline__ void count_claim(const BsTable& t, int* dhist, long l
 }
 
 __device__ __forceinline__ uint32_t bs_hash_main(uint32_t h) { return bs_fmix32(h + 0x9e3779b9u); }
+// First probe slot in the main level: (h2 * cap) >> 32 — uniform over [0, cap) for
+// any capacity, so tables are sized to the cardinality instead of the next power
+// of two (init, compaction and the exchange all scan the whole slot array).
+__device__ __forceinline__ unsigned long long bs_main_slot(const BsTable& t, uint32_t h2) {
+  return ((unsigned long long)h2 * t.main_cap) >> 32;
+}
 
 template <typename V, int OP>
 __device__ __forceinline__ void main_resolve(const BsTable& t, long long key, V val, uint32_t h2,
                                              long long cur, BsCombineStatus* st, int* dhist) {
-  unsigned long long slot = (unsigned long long)h2 & t.main_mask;
+  unsigned long long slot = bs_main_slot(t, h2);
   // Linear probing; bounded so a full table cannot hang the GPU.
   for (int probe = 0; probe < 4096; ++probe) {
     if (cur == key) {
@@ -175,7 +181,7 @@ __device__ __forceinline__ void main_resolve(const BsTable& t, long long key, V 
         return;
       }
     }
-    slot = (slot + 1) & t.main_mask;
+    slot = slot + 1 == t.main_cap ? 0 : slot + 1;
     cur = __ldcg(&t.main[slot].key);
   }
   atomicAdd(&st->failed, 1ULL);
@@ -206,7 +212,7 @@ __device__ __forceinline__ void table_insert(const BsTable& t, long long key, V 
     if (warm_resolve<V, OP>(t, key, val, h, cur, dhist)) return;
   }
   uint32_t h2 = bs_hash_main(h);
-  main_resolve<V, OP>(t, key, val, h2, __ldcg(&t.main[(unsigned long long)h2 & t.main_mask].key), st, dhist);
+  main_resolve<V, OP>(t, key, val, h2, __ldcg(&t.main[bs_main_slot(t, h2)].key), st, dhist);
 }
 
 template <typename V, int OP>
@@ -429,7 +435,7 @@ __global__ void __launch_bounds__(HC_THREADS, 1) hash_combine_tma_kernel(
       for (int j = 0; j < HC_ROWS; ++j) {
         if ((miss >> j) & 1u) {
           h[j] = bs_hash_main(h[j]);
-          cur[j] = __ldcg(&tab.main[(unsigned long long)h[j] & tab.main_mask].key);
+          cur[j] = __ldcg(&tab.main[bs_main_slot(tab, h[j])].key);
         }
       }
       {
@@ -441,7 +447,7 @@ __global__ void __launch_bounds__(HC_THREADS, 1) hash_combine_tma_kernel(
           if (((miss >> j) & 1u) && cur[j] == BS_EMPTY_KEY) {
             claim |= 1u << j;
             prev[j] = (long long)atomicCAS(
-                (unsigned long long*)&tab.main[(unsigned long long)h[j] & tab.main_mask].key,
+                (unsigned long long*)&tab.main[bs_main_slot(tab, h[j])].key,
                 (unsigned long long)BS_EMPTY_KEY, (unsigned long long)k[j]);
           }
         }
@@ -451,7 +457,7 @@ __global__ void __launch_bounds__(HC_THREADS, 1) hash_combine_tma_kernel(
           const bool won = ((claim >> j) & 1u) && prev[j] == BS_EMPTY_KEY;
           if (won) count_claim(tab, dhist, k[j]);
           if (won || prev[j] == k[j]) {
-            Combine<V, OP>::apply(slot_val<V>(&tab.main[(unsigned long long)h[j] & tab.main_mask]), v[j]);
+            Combine<V, OP>::apply(slot_val<V>(&tab.main[bs_main_slot(tab, h[j])]), v[j]);
           } else {
             // first slot belongs to another key: continue the probe sequence
             main_resolve<V, OP>(tab, k[j], v[j], h[j], prev[j], st, dhist);
@@ -595,7 +601,7 @@ static int launch_combine(const long long* keys, const V* vals, long long n, BsS
   tab.warm_mask = warm_cap > 0 ? (unsigned long long)warm_cap - 1 : 0;
   tab.has_warm = warm_cap > 0;
   tab.main = slots + warm_cap;
-  tab.main_mask = (unsigned long long)cap - 1;
+  tab.main_cap = (unsigned long long)cap;
   tab.nparts = dest_counts != nullptr ? nparts : 0;
   tab.dest_counts = dest_counts;
   int sms = bs_num_sms();
@@ -706,14 +712,14 @@ static int combine_entry(const long long* keys, const void* vals, long long n, v
                                (BsCombineStatus*)st, force_simple, nparts, dest_counts, stream);
 }
 
-// warm_cap: 0 or a power of two; cap: power of two.  tab holds warm_cap + cap slots.
+// warm_cap: 0 or a power of two; cap: any size below 2^32.  tab holds warm_cap + cap slots.
 // nparts/dest_counts (optional): accumulate, per destination shard
 // murmur3(key) % nparts, the number of keys inserted for the first time.
 BS_EXPORT int bs_hash_combine(const long long* keys, const void* vals, long long n, int vtype, int op,
                               void* tab, long long warm_cap, long long cap, void* status,
                               int force_simple, int nparts, unsigned long long* dest_counts,
                               cudaStream_t stream) {
-  if (cap <= 0 || (cap & (cap - 1)) || (warm_cap & (warm_cap - 1)) || warm_cap < 0) return -2;
+  if (cap <= 0 || cap >= (1LL << 32) || (warm_cap & (warm_cap - 1)) || warm_cap < 0) return -2;
   if (dest_counts != nullptr && (nparts < 1 || nparts > HC_DEST)) return -2;
   DISPATCH_VOP(combine_entry, keys, vals, n, tab, warm_cap, cap, status, force_simple, nparts,
                dest_counts, stream)
