@@ -73,6 +73,9 @@ def init_process_group(device: Optional[str] = None) -> None:
     if use_cuda:
         local = int(os.environ.get("LOCAL_RANK", os.environ.get("RANK", "0")))
         torch.cuda.set_device(local % max(torch.cuda.device_count(), 1))
+        # threads + pinned staging buffers stay on the GPU's NUMA node
+        from ..utils import topology
+        topology.bind_to_gpu(torch.cuda.current_device())
         dist.init_process_group("nccl", device_id=torch.device("cuda", torch.cuda.current_device()))
     else:
         dist.init_process_group("gloo")
@@ -191,10 +194,7 @@ class SpmdExecutor(LocalExecutor):
     def _vote(self, bad: int) -> int:
         """Control-plane agreement before an exchange: did every rank's producers
         succeed, and did every rank issue the same invocations since the last vote."""
-        fps, self._pending_fp = self._pending_fp, []
-        acc = 0
-        for _, _, _, fp in fps:
-            acc = (acc * 1000003 + fp) & ((1 << 61) - 1)
+        acc, fps = self._take_fingerprint()
         flag = torch.tensor([bad, acc, -acc], dtype=torch.int64)
         with span("xchg/status_vote"):
             dist.all_reduce(flag, op=dist.ReduceOp.MAX, group=self.ctrl_group)
@@ -288,18 +288,25 @@ class SpmdExecutor(LocalExecutor):
     def _exchange_group(self, gid: int, group: List[Task]) -> None:
         with span("xchg/wait_producers"):
             bad = self._local_status(group)
-        if self.world > 1:
-            bad = self._vote(bad)
-        if bad:
-            raise errors.fatal("spmd: a producer of %s failed on some rank" % group[0].name)
         head = group[0]
         nparts = head.num_partition
         typ = head.type.typ
         with self._glock:
             table = self.group_tables.pop(gid, None)
-        if table is not None:
+        # The table path is a static property of the task (same answer on every
+        # rank, also on ranks whose shards were empty or whose producers failed).
+        if self._table_path_ok(head) and (table is not None or self.world > 1):
+            if table is None:
+                from ..ops import gpu
+                table = gpu.table_pool().get(1024, head.type.typ.out(1).torch_dtype,
+                                             head.combiner.builtin, self.device)
+                table.track(nparts)
             with span("xchg/table_total"):
-                return self._exchange_table(gid, head, table, nparts)
+                return self._exchange_table(gid, head, table, nparts, bad)
+        if self.world > 1:
+            bad = self._vote(bad)
+        if bad:
+            raise errors.fatal("spmd: a producer of %s failed on some rank" % group[0].name)
         frames: List[Frame] = []
         for t in group:
             if self.owns(t):
@@ -361,12 +368,22 @@ class SpmdExecutor(LocalExecutor):
                 self.group_tables[gid] = t
             return t
 
-    def _exchange_table(self, gid: int, head: Task, table, nparts: int) -> None:
+    def _take_fingerprint(self) -> Tuple[int, List]:
+        fps, self._pending_fp = self._pending_fp, []
+        acc = 0
+        for _, _, _, fp in fps:
+            acc = (acc * 1000003 + fp) & ((1 << 61) - 1)
+        return acc, fps
+
+    def _exchange_table(self, gid: int, head: Task, table, nparts: int, bad: int = 0) -> None:
         from ..ops import gpu
+        from ..parallel.peer import ExchangeVoteError
         typ = head.type.typ
         t0 = time.perf_counter()
         ev0 = self._cuda_event()
         out: Dict[int, List[Frame]] = {}
+        if self.world == 1 and bad:
+            raise errors.fatal("spmd: a producer of %s failed" % head.name)
         if self.world == 1 and nparts == 1:
             # the local table is already the answer
             clear = gpu.RECYCLE == "clear"
@@ -376,8 +393,19 @@ class SpmdExecutor(LocalExecutor):
             sent = len(k)
             mode = "table-local"
         else:
-            with span("xchg/exchange_table"):
-                got = self.peers.exchange_table(table, nparts, clear=gpu.RECYCLE == "clear")
+            # the producer status and the invocation fingerprint travel with the
+            # counts: all ranks agree on device, without a host collective
+            acc, fps = self._take_fingerprint()
+            try:
+                with span("xchg/exchange_table"):
+                    got = self.peers.exchange_table(table, nparts, clear=gpu.RECYCLE == "clear",
+                                                    vote=(1 if bad else 0, acc))
+            except ExchangeVoteError as e:
+                if e.kind == 3:
+                    raise errors.fatal("spmd: a producer of %s failed on some rank" % head.name) from e
+                where = ", ".join("inv%d at %s (func #%d)" % f[:3] for f in fps) or "an earlier invocation"
+                raise errors.fatal("ranks issued different invocations (%s, rank %d); SPMD programs must "
+                                   "run identical Session.run sequences" % (where, self.rank)) from e
             with span("xchg/status_sync"):
                 st = table.status.tolist()
             if st[0]:

@@ -59,6 +59,16 @@ def device_view(ptr: int, nbytes: int, device, owner=None) -> torch.Tensor:
     return torch.as_tensor(_DevMem(ptr, nbytes, owner), device=device)
 
 
+class ExchangeVoteError(RuntimeError):
+    """The vote carried by an exchange failed on some rank (raised on all ranks):
+    kind 3 = a rank's producers failed, 4 = ranks issued different invocations."""
+
+    def __init__(self, kind: int):
+        super().__init__("a rank reported failed producers" if kind == 3
+                         else "ranks issued different invocations")
+        self.kind = kind
+
+
 class ExchangeError(RuntimeError):
     pass
 
@@ -157,8 +167,13 @@ class PeerGroup:
 
     def exchange_raw(self, desc, n: int, nparts: int, nkeys: int = 1,
                      ids: Optional[torch.Tensor] = None, skip_empty: bool = False,
-                     zero_copy: bool = False, keep=None) -> Dict[int, List[torch.Tensor]]:
-        """Exchange columns described as ``(ptr, row_bytes, stride_bytes, dtype,
+                     zero_copy: bool = False, keep=None, vote: Tuple[int, int] = (0, 0)
+                     ) -> Dict[int, List[torch.Tensor]]:
+        """``vote = (status, fingerprint)`` travels with the counts: if any rank
+        reports a non-zero status, or fingerprints differ, *every* rank's call
+        raises :class:`ExchangeVoteError` (no host collective needed).
+
+        Exchange columns described as ``(ptr, row_bytes, stride_bytes, dtype,
         tail_shape)`` — lets strided views (the key/value fields of a hash-table
         slot array) be shuffled without materialising them."""
         spec = XcSpec()
@@ -178,10 +193,12 @@ class PeerGroup:
         self.epoch += 1
         self._chk(self.lib.bs_xc_exchange(ctypes.byref(self.peers), ctypes.byref(spec),
                                           c_void_p(self.plan.data_ptr()), c_ull(self.epoch),
-                                          c_ull(0), gpu._stream()), "exchange")
+                                          c_ull(0), c_ull(vote[0]), c_ull(vote[1]), gpu._stream()),
+                  "exchange")
         return self._collect(desc, nparts, zero_copy)
 
-    def exchange_table(self, table, nparts: int, clear: bool = True) -> Dict[int, List[torch.Tensor]]:
+    def exchange_table(self, table, nparts: int, clear: bool = True, vote: Tuple[int, int] = (0, 0)
+                       ) -> Dict[int, List[torch.Tensor]]:
         """Shuffle a :class:`~bigslice_b200.ops.gpu.HashTable` in place with the
         specialised table kernels: rows of shard ``murmur3(key) % nparts`` arrive
         as ``[keys, values]`` views of this rank's arena (zero copy; valid until
@@ -195,7 +212,7 @@ class PeerGroup:
             c_ull(0), ctypes.c_int(1 if clear else 0),
             c_ull(table.identity_bits() if clear else 0),
             c_void_p(table.dest_counts.data_ptr() if table.nparts == nparts and nparts else 0),
-            gpu._stream()), "exchange_table")
+            c_ull(vote[0]), c_ull(vote[1]), gpu._stream()), "exchange_table")
         desc = [(0, 8, 16, torch.int64, ()), (0, vb, 16, table.vdtype, ())]
         return self._collect(desc, nparts, zero_copy=True)
 
@@ -207,6 +224,8 @@ class PeerGroup:
         err = int(plan[self.off_error:self.off_error + 4].view(np.int32)[0])
         if err == 1:
             raise ExchangeError("receive arena overflow (%d bytes): raise arena_bytes" % self.arena_bytes)
+        if err in (3, 4):
+            raise ExchangeVoteError(err)
         if err:
             raise ExchangeError("peer exchange aborted (timeout or peer failure)")
         recv_total = plan[self.off_recv_total:self.off_recv_total + 8 * MAXP].view(np.int64)

@@ -43,6 +43,9 @@ struct XcCtrl {
   long long cnt[2][XC_MAXW][XC_MAXP];
   unsigned long long abort_flag;
   unsigned long long barrier_flag[XC_MAXW];
+  // device-side vote published with the counts row: [0] producer status (0 ok),
+  // [1] fingerprint of the invocations issued since the last exchange
+  unsigned long long vote[2][XC_MAXW][2];
 };
 
 struct XcPeers {
@@ -74,7 +77,8 @@ struct XcPlan {
   long long send_count[XC_MAXP];                 // this rank's rows per shard
   unsigned long long cursor[XC_MAXP];            // running slot reservation (scatter)
   unsigned int done_ctas;
-  int error;                                     // 1 overflow, 2 timeout/abort
+  int error;                                     // 1 overflow, 2 timeout/abort, 3 a rank reported
+                                                 // failed producers, 4 ranks issued different invocations
 };
 
 __device__ __forceinline__ int xc_dest(const XcSpec& sp, long long i) {
@@ -111,7 +115,9 @@ __global__ void __launch_bounds__(XC_THREADS) xchg_count_kernel(XcSpec sp, XcPla
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) xchg_plan_kernel(XcPeers pe, XcSpec sp, XcPlan* plan,
                                                         unsigned long long epoch,
-                                                        unsigned long long my_arena_base) {
+                                                        unsigned long long my_arena_base,
+                                                        unsigned long long my_status,
+                                                        unsigned long long my_fp) {
   const int W = pe.world, me = pe.rank, P = sp.nparts;
   const int par = (int)(epoch & 1);
   const int tid = threadIdx.x;
@@ -122,7 +128,11 @@ __global__ void __launch_bounds__(256) xchg_plan_kernel(XcPeers pe, XcSpec sp, X
     int p = x / P, d = x - p * P;
     pe.ctrl[p]->cnt[par][me][d] = plan->send_count[d];
   }
-  if (tid < W) pe.ctrl[tid]->arena_base[par][me] = my_arena_base;
+  if (tid < W) {
+    pe.ctrl[tid]->arena_base[par][me] = my_arena_base;
+    pe.ctrl[tid]->vote[par][me][0] = my_status;
+    pe.ctrl[tid]->vote[par][me][1] = my_fp;
+  }
   __threadfence_system();
   __syncthreads();
   // 2. release flag on every peer, then 3. acquire all peers' flags
@@ -147,9 +157,21 @@ __global__ void __launch_bounds__(256) xchg_plan_kernel(XcPeers pe, XcSpec sp, X
     }
     return;
   }
+  XcCtrl* mine = pe.ctrl[me];
+  // 3b. the vote that came with the counts: every rank sees every rank's status
+  //     and fingerprint, so all of them fail (or proceed) together — no host
+  //     collective before the exchange.
+  if (tid < W) {
+    if (mine->vote[par][tid][0] != 0) atomicMax(&bad, 3);
+    else if (mine->vote[par][tid][1] != my_fp) atomicMax(&bad, 4);
+  }
+  __syncthreads();
+  if (bad) {
+    if (tid == 0) plan->error = bad;
+    return;
+  }
   // 4. layout: shards of rank p are packed in increasing d, each (d, c) region
   //    256-byte aligned.  Every rank computes the same layout from the matrix.
-  XcCtrl* mine = pe.ctrl[me];
   if (tid < P) {
     long long total = 0, before = 0;
     for (int s = 0; s < W; ++s) {
@@ -798,6 +820,7 @@ BS_EXPORT int bs_stream_sync(cudaStream_t stream) { return (int)cudaStreamSynchr
 // exactly as XcPeers/XcSpec (built by the python side with ctypes).
 BS_EXPORT int bs_xc_exchange(const void* peers_h, const void* spec_h, void* plan_d,
                              unsigned long long epoch, unsigned long long arena_base,
+                             unsigned long long my_status, unsigned long long my_fp,
                              cudaStream_t stream) {
   XcPeers pe = *(const XcPeers*)peers_h;
   XcSpec sp = *(const XcSpec*)spec_h;
@@ -814,7 +837,7 @@ BS_EXPORT int bs_xc_exchange(const void* peers_h, const void* spec_h, void* plan
     xchg_count_kernel<<<blocks, XC_THREADS, 0, stream>>>(sp, plan);
     BS_LAUNCH_CHECK();
   }
-  xchg_plan_kernel<<<1, 256, 0, stream>>>(pe, sp, plan, epoch, arena_base);
+  xchg_plan_kernel<<<1, 256, 0, stream>>>(pe, sp, plan, epoch, arena_base, my_status, my_fp);
   BS_LAUNCH_CHECK();
   long long ntiles = (sp.n + XC_TILE - 1) / XC_TILE;
   int blocks = (int)(ntiles < (long long)sms * 2 ? ntiles : (long long)sms * 2);
@@ -836,7 +859,9 @@ BS_EXPORT int bs_xc_exchange_table(const void* peers_h, void* slots, long long t
                                    int nparts, void* plan_d, unsigned long long epoch,
                                    unsigned long long arena_base, int clear,
                                    unsigned long long clear_bits,
-                                   const unsigned long long* precounts, cudaStream_t stream) {
+                                   const unsigned long long* precounts,
+                                   unsigned long long my_status, unsigned long long my_fp,
+                                   cudaStream_t stream) {
   XcPeers pe = *(const XcPeers*)peers_h;
   if (pe.world > XC_MAXW || nparts > XC_MAXP || nparts < 1 || (vbytes != 4 && vbytes != 8)) return -1;
   XcSpec sp;
@@ -867,7 +892,7 @@ BS_EXPORT int bs_xc_exchange_table(const void* peers_h, void* slots, long long t
     xchg_table_count_kernel<<<blocks, 512, 0, stream>>>(tab, total, nparts, plan);
     BS_LAUNCH_CHECK();
   }
-  xchg_plan_kernel<<<1, 256, 0, stream>>>(pe, sp, plan, epoch, arena_base);
+  xchg_plan_kernel<<<1, 256, 0, stream>>>(pe, sp, plan, epoch, arena_base, my_status, my_fp);
   BS_LAUNCH_CHECK();
   if (nparts <= 8) {
     // few destinations: software write-combining in shared memory

@@ -13,11 +13,12 @@ dump() {  # $1 = mangled-name regex, $2 = output stem
     echo; echo "## mnemonic histogram (memory / sync / atomic classes)"
     grep -oE "\b(UBLKCP[.A-Z0-9_]*|UTMA[.A-Z0-9_]*|SYNCS[.A-Z0-9_]*|ATOMS[.A-Z0-9_]*|ATOMG[.A-Z0-9_]*|REDG[.A-Z0-9_]*|RED[.A-Z0-9_]*|LDG[.A-Z0-9_]*|STG[.A-Z0-9_]*|LDS[.A-Z0-9_]*|STS[.A-Z0-9_]*|MEMBAR[.A-Z0-9_]*|FENCE[.A-Z0-9_]*|MATCH[.A-Z0-9_]*|BAR[.A-Z0-9_]*|NANOSLEEP|CCTL[.A-Z0-9_]*|ERRBAR|UTC[A-Z0-9.]*MMA|HMMA[.A-Z0-9_]*)" /tmp/sass_$2.txt | sort | uniq -c | sort -rn
     echo; echo "## selected instruction lines"
-    grep -nE "UBLKCP|SYNCS|ATOMG|REDG|\.SYS|MEMBAR|MATCH|createpolicy|EVICT|LDG.*\.(EF|EL)|STG.*STRONG" /tmp/sass_$2.txt | head -60
+    grep -nE "UBLKCP|SYNCS|ATOMG|REDG|\.SYS|MEMBAR|MATCH|VOTE|createpolicy|EVICT|LDG.*\.(EF|EL)|STG.*STRONG" /tmp/sass_$2.txt | head -60
   } > profiles/sass/$2.txt
 }
 dump "hash_combine_tma_kernelIxLi0" hash_combine_tma_i64_add
 dump "xchg_scatter_kernel" xchg_scatter
+dump "xchg_table_scatter_buf_kernelILi8" xchg_table_scatter_buf
 dump "xchg_plan_kernel" xchg_plan
 dump "xchg_wait_kernel" xchg_wait
 dump "rs_scatter_kernel" radix_scatter

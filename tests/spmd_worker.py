@@ -142,6 +142,30 @@ def table_exchange_check(ex, world, rank):
     return ok
 
 
+def exchange_vote_check(ex, world, rank):
+    """The vote that travels with the counts: one rank reporting failure (or a
+    different fingerprint) makes the exchange raise on every rank, and the next
+    exchange works again."""
+    from bigslice_b200.ops import gpu
+    from bigslice_b200.parallel.peer import ExchangeVoteError
+    t = gpu.HashTable(4096, torch.int64, "add", "cuda")
+    k = torch.arange(1000, device="cuda")
+    kinds = []
+    for vote in ((1 if rank == world - 1 else 0, 5), (0, 100 + rank), (0, 9)):
+        t.combine(k, k)
+        try:
+            got = ex.peers.exchange_table(t, world, clear=True, vote=vote)
+            kinds.append(0)
+            n = sum(int(c[0].numel()) for c in got.values())
+        except ExchangeVoteError as e:
+            kinds.append(e.kind)
+            t.reset()
+            continue
+        t.reset_status()
+    want = [3, 4 if world > 1 else 0, 0]
+    return kinds == want
+
+
 def big_wordcount_check(sess, ex, world, rank):
     """A few steps of a 6M-row/rank Zipf wordcount through the table path (warm
     + main levels, in-place table exchange, combine on arrival): totals and the
@@ -232,6 +256,7 @@ def main():
     if device != "cpu" and ex.peers is not None:
         out["exchange_content_ok"] = exchange_content_check(ex, world, rank)
         out["table_exchange_ok"] = table_exchange_check(ex, world, rank)
+        out["exchange_vote_ok"] = exchange_vote_check(ex, world, rank)
         out["bigcount_ok"] = big_wordcount_check(sess, ex, world, rank)
     out["modes"] = sorted(set(e["mode"] for e in ex.exchange_log))
     try:

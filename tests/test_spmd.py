@@ -41,7 +41,7 @@ def check(outs, world):
                   "reshard_placement_ok"):
             assert o[k], (k, o)
     for o in outs:
-        for k in ("exchange_content_ok", "table_exchange_ok", "bigcount_ok"):
+        for k in ("exchange_content_ok", "table_exchange_ok", "exchange_vote_ok", "bigcount_ok"):
             if k in o:
                 assert o[k], (k, o["rank"])
     if world > 1:
