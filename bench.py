@@ -103,6 +103,73 @@ class ClockSampler:
                 "reasons": sorted(reasons)}
 
 
+class NvmlSampler:
+    """Polls SM clock and clock-event (throttle) reasons through NVML every few
+    milliseconds from a thread, so that even a timed region of a few tens of
+    milliseconds contains samples; only samples taken inside [t0, t1] count."""
+
+    REASONS = (("hw_slowdown", 0x8), ("sw_thermal_slowdown", 0x20), ("hw_thermal_slowdown", 0x40),
+               ("sw_power_cap", 0x4))
+
+    def __init__(self, index: int = 0, period_s: float = 0.004):
+        import pynvml
+        self.nv = pynvml
+        pynvml.nvmlInit()
+        try:
+            import torch
+            uuid = str(torch.cuda.get_device_properties(index).uuid)
+            self.h = pynvml.nvmlDeviceGetHandleByUUID(uuid if uuid.startswith("GPU-") else "GPU-" + uuid)
+        except Exception:
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        self.period = period_s
+        self.samples = []
+        self._stop = threading.Event()
+        self.t0 = self.t1 = None
+        self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+
+    def start(self):
+        threading.Thread(target=self._run, daemon=True).start()
+
+    def _run(self):
+        nv = self.nv
+        while not self._stop.is_set():
+            try:
+                mhz = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+                try:
+                    rs = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    rs = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                self.samples.append((time.perf_counter(), float(mhz), int(rs)))
+            except Exception:
+                pass
+            self._stop.wait(self.period)
+
+    def window(self, t0, t1):
+        self.t0, self.t1 = t0, t1
+
+    def stop(self):
+        self._stop.set()
+        inside = [s for s in self.samples if self.t0 is not None and self.t0 <= s[0] <= self.t1]
+        note = "timed region"
+        if not inside:  # cannot happen with a >4 ms region, but never report nothing
+            inside, note = self.samples[-3:], "nearest samples (region shorter than the sampling period)"
+        reasons = set()
+        for _, _, rs in inside:
+            for nm, bit in self.REASONS:
+                if rs & bit:
+                    reasons.add(nm)
+        sm = [s[1] for s in inside]
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": self.max_mhz,
+                "samples": len(sm), "reasons": sorted(reasons), "source": "nvml", "window": note}
+
+
+def make_sampler(index: int):
+    try:
+        return NvmlSampler(index)
+    except Exception:
+        return ClockSampler(index)
+
+
 def reference_arm(args):
     why = ("grailbio/bigslice is a pure-Go module: no setup.py/pyproject.toml for pip to install "
            "(pip: 'not installable'), no Go toolchain or module cache in this image, no network")
@@ -114,10 +181,23 @@ def main():
     if args.impl == "reference":
         reference_arm(args)
         return 0
+    # stdout carries exactly one JSON line: anything libraries print to fd 1
+    # (e.g. NCCL's version banner) is sent to stderr instead.
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+    try:
+        return run(args, os.fdopen(json_fd, "w"))
+    finally:
+        sys.stdout.flush()
+
+
+def run(args, json_out):
     import torch
     import torch.distributed as dist
     if not torch.cuda.is_available():
-        print(json.dumps({"error": "bench.py needs a CUDA device", "n_gpus": args.gpus}))
+        json_out.write(json.dumps({"error": "bench.py needs a CUDA device", "n_gpus": args.gpus}) + "\n")
+        json_out.flush()
         return 1
     import bigslice_b200 as bs
     from bigslice_b200.exec.spmd import init_process_group
@@ -191,12 +271,16 @@ def main():
     tot = torch.tensor([chk[1]], dtype=torch.int64, device=dev)
     dist.all_reduce(tot)
     assert int(tot[0]) == n * world, "wordcount lost rows: %d != %d" % (int(tot[0]), n * world)
-    sampler = ClockSampler(torch.cuda.current_device())
+    sampler = make_sampler(torch.cuda.current_device())
     if rank == 0:
         sampler.start()
+        time.sleep(0.02)
     from bigslice_b200.utils import spans
     m0 = spans.mark()
+    tw0 = time.perf_counter()
     ms, launches, _ = timed("rows_hbm", args.steps, False)
+    if hasattr(sampler, "window"):
+        sampler.window(tw0, time.perf_counter())
     if spans.enabled() and rank == 0:
         sys.stderr.write("host spans per step (rank 0):\n%s\n" % spans.format_summary(m0, args.steps))
         raw = spans.raw(m0)
@@ -252,9 +336,11 @@ def main():
             "e2e": e2e,
             "exchange_modes": sorted(set(e["mode"] for e in ex.exchange_log)),
         }
-        print(json.dumps(out))
+        json_out.write(json.dumps(out) + "\n")
+        json_out.flush()
     sess.shutdown()
     dist.barrier()
+    dist.destroy_process_group()
     return 0
 
 
