@@ -352,17 +352,6 @@ __global__ void __launch_bounds__(HC_THREADS, 1) hash_combine_tma_kernel(
         if (lane == leader) bs_mbar_arrive(&empty[s]);
       }
 #endif
-#ifdef HC_DBG_SUMKEYS
-      {
-        unsigned long long ks = 0, nr = 0;
-#pragma unroll
-        for (int j = 0; j < HC_ROWS; ++j)
-          if (tid + j * HC_CONSUMERS < rows) { ks += (unsigned long long)k[j]; nr += 1; }
-        atomicAdd(&st->special_val, ks);
-        atomicAdd(&st->out_count, nr);
-        continue;
-      }
-#endif
       // --- phase A: shared-memory hot table ---
       uint32_t h[HC_ROWS];
       unsigned miss = 0;
@@ -376,10 +365,6 @@ __global__ void __launch_bounds__(HC_THREADS, 1) hash_combine_tma_kernel(
         }
         h[j] = bs_mix_u64((uint64_t)k[j]);
         uint32_t sl = (h[j] >> 20) & (HC_SLOTS - 1);  // high bits: independent of the HBM slot bits
-#ifdef HC_DBG_NO_SMEM
-        miss |= 1u << j;
-        continue;
-#endif
         long long k0 = *(volatile long long*)&skeys[sl];
         if (k0 != k[j]) {
           if (k0 != BS_EMPTY_KEY) {

@@ -394,3 +394,93 @@ def test_pragmas_compose():
     assert m.procs() == 2 and not m.exclusive() and m2.exclusive()
     assert bs.Pragmas([m, m2]).procs() == 2 and bs.Pragmas([m, m2]).exclusive()
     assert bs.Map(s, lambda x: x, bs.ExperimentalMaterialize, out=[bs.int64]).materialize()
+
+
+# ---- the custom-Slice protocol (exec/compile_test.go:432-458) ----
+class _Doubling(bs.Slice):
+    """User-defined slice: wraps another slice (one pipelined dependency) and
+    overrides ``reader``."""
+
+    calls = 0
+
+    def __init__(self, inner: bs.Slice):
+        super().__init__(bs.make_name("doubling"), inner.typ, inner.num_shard(),
+                         deps=[bs.Dep(inner)])
+
+    def reader(self, shard, deps):
+        from bigslice_b200.frame import Frame
+        from bigslice_b200.sliceio import FuncReader
+        src = deps[0]
+        typ = self.typ
+
+        def read(n):
+            f = src.read(n)
+            if f is None:
+                return None
+            _Doubling.calls += 1
+            return Frame([f.col(0), f.col(1) * 2], typ)
+        return FuncReader(read)
+
+
+class _MemoryShardCache:
+    """A user-provided shard cache (any object with the ShardCache methods)."""
+
+    def __init__(self):
+        self.frames = {}
+
+    def is_cached(self, shard):
+        return shard in self.frames
+
+    def writethrough_reader(self, shard, reader):
+        from bigslice_b200.sliceio import FuncReader
+        got = []
+
+        def read(n):
+            f = reader.read(n)
+            if f is None:
+                self.frames[shard] = got
+                return None
+            got.append(f)
+            return f
+        return FuncReader(read)
+
+    def cache_reader(self, shard):
+        from bigslice_b200.sliceio import FrameReader, MultiReader
+        return MultiReader([FrameReader(f) for f in self.frames[shard]])
+
+
+from bigslice_b200.internal import slicecache as _slicecache  # noqa: E402
+
+
+class _CachedDoubling(_Doubling, _slicecache.Cacheable):
+    """Cacheable is discovered by isinstance on the (unwrapped) user slice."""
+
+    store = _MemoryShardCache()
+
+    def cache(self):
+        return type(self).store
+
+
+@bs.Func
+def _custom_pipeline(n: int, cached: bool):
+    base = bs.Const(3, torch.arange(n), torch.arange(n) * 10)
+    mid = (_CachedDoubling if cached else _Doubling)(base)
+    return bs.Reduce(bs.Map(mid, lambda k, v: (k % 4, v)), bs.ops.add)
+
+
+def test_user_defined_slice_and_cacheable_protocol():
+    n = 100
+    want = {}
+    for i in range(n):
+        want[i % 4] = want.get(i % 4, 0) + i * 20
+    with bs.start(bs.Local, bs.Parallelism(2)) as sess:
+        _Doubling.calls = 0
+        assert dict(sess.run(_custom_pipeline, n, False).rows()) == want
+        assert _Doubling.calls == 3  # pipelined with Const and Map: one tile per shard
+        # the same user slice, now also Cacheable
+        _CachedDoubling.store.frames.clear()
+        _Doubling.calls = 0
+        assert dict(sess.run(_custom_pipeline, n, True).rows()) == want
+        assert sorted(_CachedDoubling.store.frames) == [0, 1, 2] and _Doubling.calls == 3
+        res = sess.run(_custom_pipeline, n, True)  # served from the user's cache
+        assert dict(res.rows()) == want and _Doubling.calls == 3
