@@ -136,6 +136,11 @@ def wordcount_top(source: str, n: int):
 
     def top(k, v):
         kk = min(n, v.numel())
+        if v.is_cuda:
+            from ..ops import gpu
+            if gpu.available():
+                idx = gpu.topk(v, kk)[1]  # radix select (csrc/misc.cu)
+                return k[idx], v[idx]
         idx = torch.topk(v, kk).indices
         return k[idx], v[idx]
     from ..slices import Flatmap

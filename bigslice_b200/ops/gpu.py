@@ -487,6 +487,51 @@ def expand_indices(offsets: torch.Tensor) -> torch.Tensor:
     return src
 
 
+def _orderable_i64(v: torch.Tensor) -> torch.Tensor:
+    """int64 tensor whose signed order equals the order of ``v`` (ints: widened;
+    floats: the usual sign-magnitude -> two's-complement bit trick; NaNs are the largest)."""
+    if v.dtype in (torch.int64,):
+        return v.contiguous()
+    if v.dtype in (torch.int8, torch.int16, torch.int32, torch.uint8, torch.bool):
+        return v.to(torch.int64)
+    if v.dtype in (torch.float16, torch.bfloat16):
+        v = v.to(torch.float32)
+    if v.dtype.is_floating_point:
+        v = v + 0.0  # -0.0 -> +0.0: the two zeros are one value
+    if v.dtype == torch.float32:
+        b = v.contiguous().view(torch.int32).to(torch.int64)
+        return torch.where(b < 0, b ^ 0x7FFFFFFF, b)
+    if v.dtype == torch.float64:
+        b = v.contiguous().view(torch.int64)
+        return torch.where(b < 0, b ^ 0x7FFFFFFFFFFFFFFF, b)
+    raise TypeError("topk: unsupported dtype %s" % v.dtype)
+
+
+def topk(values: torch.Tensor, k: int) -> Tuple[torch.Tensor, torch.Tensor]:
+    """(values, indices) of the ``k`` largest elements, descending; equal values
+    are listed in index order, and when ties straddle the cut it is unspecified
+    which of them are kept (as with ``torch.topk``).  Radix select on the device
+    (``csrc/misc.cu: bs_topk_i64``)."""
+    lib = require()
+    n = values.numel()
+    k = min(int(k), n)
+    if k <= 0:
+        e = torch.empty(0, dtype=torch.int64, device=values.device)
+        return values[:0], e
+    keys = _orderable_i64(values.reshape(-1))
+    idx = torch.empty(k, dtype=torch.int64, device=values.device)
+    scratch = torch.empty(1040 // 8 + 1, dtype=torch.int64, device=values.device)
+    rc = lib.bs_topk_i64(_ptr(keys), c_ll(n), c_ll(k), _ptr(idx), _ptr(scratch), _stream())
+    if rc != 0:
+        raise RuntimeError("bigslice_b200 kernel topk failed: cuda error %d" % -rc)
+    # k is small: order the winners (value descending, then index ascending)
+    kv = keys[idx]
+    order = torch.argsort(idx, stable=True)
+    order = order[torch.argsort(kv[order], descending=True, stable=True)]
+    idx = idx[order]
+    return values.reshape(-1)[idx], idx
+
+
 def crc32(t: torch.Tensor) -> int:
     """CRC32-IEEE of a device tensor's bytes (device per-block CRCs + host
     GF(2) combine)."""

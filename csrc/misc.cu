@@ -313,3 +313,109 @@ BS_EXPORT int bs_crc32_blocks(const void* data, long long n, unsigned int* out, 
   BS_LAUNCH_CHECK();
   return 0;
 }
+
+// ---------------------------------------------------------------------------
+// K15: top-k by radix select (cmd/urls top-N, exec/topn.go).  Eight 8-bit passes
+// from the most significant digit narrow down the k-th largest value: each pass
+// histograms the digit of the values that still match the prefix found so far
+// (shared-memory histogram, one global flush per CTA); the host walks the 256
+// counts (one 1 KB D2H per pass).  A final pass writes the indices of all values
+// above the threshold and as many ties as are needed.  Values are int64 in an
+// order-preserving encoding chosen by the caller.
+#define TK_THREADS 512
+__device__ __forceinline__ unsigned long long tk_key(long long v) {
+  return (unsigned long long)v ^ 0x8000000000000000ULL;
+}
+
+__global__ void __launch_bounds__(TK_THREADS) topk_hist_kernel(const long long* __restrict__ vals,
+                                                               long long n, unsigned long long prefix,
+                                                               unsigned long long mask, int shift,
+                                                               unsigned int* __restrict__ hist) {
+  __shared__ unsigned int h[256];
+  if (threadIdx.x < 256) h[threadIdx.x] = 0;
+  __syncthreads();
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) {
+    const unsigned long long k = tk_key(vals[i]);
+    if ((k & mask) == prefix) atomicAdd(&h[(unsigned)(k >> shift) & 0xffu], 1u);
+  }
+  __syncthreads();
+  if (threadIdx.x < 256 && h[threadIdx.x]) atomicAdd(&hist[threadIdx.x], h[threadIdx.x]);
+}
+
+// out_idx[0 .. n_gt) = indices of values above the threshold (any order),
+// out_idx[n_gt .. n_gt + n_eq) = indices of the first ties that win the race.
+__global__ void __launch_bounds__(TK_THREADS) topk_select_kernel(const long long* __restrict__ vals,
+                                                                 long long n, unsigned long long thresh,
+                                                                 long long n_gt, long long n_eq,
+                                                                 long long* __restrict__ out_idx,
+                                                                 unsigned long long* __restrict__ cursors) {
+  const unsigned lane = threadIdx.x & 31u;
+  const long long limit = ((n + 31) / 32) * 32;
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (; i < limit; i += stride) {
+    const bool ok = i < n;
+    const unsigned long long k = ok ? tk_key(vals[i]) : 0ULL;
+    const bool gt = ok && k > thresh, eq = ok && k == thresh;
+    const unsigned bg = __ballot_sync(0xffffffffu, gt), be = __ballot_sync(0xffffffffu, eq);
+    unsigned long long baseg = 0, basee = 0;
+    if (lane == 0) {
+      if (bg) baseg = atomicAdd(&cursors[0], (unsigned long long)__popc(bg));
+      if (be) basee = atomicAdd(&cursors[1], (unsigned long long)__popc(be));
+    }
+    baseg = __shfl_sync(0xffffffffu, baseg, 0);
+    basee = __shfl_sync(0xffffffffu, basee, 0);
+    const unsigned lt = (1u << lane) - 1u;
+    if (gt) {
+      const unsigned long long p = baseg + __popc(bg & lt);
+      if (p < (unsigned long long)n_gt) out_idx[p] = i;
+    }
+    if (eq) {
+      const unsigned long long p = basee + __popc(be & lt);
+      if (p < (unsigned long long)n_eq) out_idx[n_gt + p] = i;
+    }
+  }
+}
+
+// scratch: 256 uint32 histogram + 2 uint64 cursors (caller-provided, >= 1040 bytes).
+// Writes min(k, n) indices to out_idx; returns <0 on error.
+BS_EXPORT int bs_topk_i64(const long long* vals, long long n, long long k, long long* out_idx,
+                          void* scratch, cudaStream_t stream) {
+  if (n <= 0 || k <= 0) return 0;
+  if (k > n) k = n;
+  unsigned int* hist = (unsigned int*)scratch;
+  unsigned long long* cursors = (unsigned long long*)((unsigned char*)scratch + 1024);
+  const int sms = bs_num_sms();
+  long long want = (n + TK_THREADS - 1) / TK_THREADS;
+  const int blocks = (int)(want < (long long)sms * 4 ? want : (long long)sms * 4);
+  unsigned long long prefix = 0, mask = 0;
+  long long remaining = k;  // how many of the values matching the prefix are still wanted
+  unsigned int h[256];
+  for (int shift = 56; shift >= 0; shift -= 8) {
+    cudaError_t e = cudaMemsetAsync(hist, 0, 1024, stream);
+    if (e != cudaSuccess) return -(int)e;
+    topk_hist_kernel<<<blocks, TK_THREADS, 0, stream>>>(vals, n, prefix, mask, shift, hist);
+    BS_COUNT_LAUNCH();
+    e = cudaMemcpyAsync(h, hist, sizeof(h), cudaMemcpyDeviceToHost, stream);
+    if (e != cudaSuccess) return -(int)e;
+    e = cudaStreamSynchronize(stream);
+    if (e != cudaSuccess) return -(int)e;
+    int d = 255;
+    for (; d > 0; --d) {
+      if ((long long)h[d] >= remaining) break;
+      remaining -= h[d];
+    }
+    prefix |= (unsigned long long)d << shift;
+    mask |= 0xffULL << shift;
+  }
+  // prefix is now the k-th largest key; `remaining` ties are needed
+  const long long n_gt = k - remaining;
+  cudaError_t e = cudaMemsetAsync(cursors, 0, 16, stream);
+  if (e != cudaSuccess) return -(int)e;
+  topk_select_kernel<<<blocks, TK_THREADS, 0, stream>>>(vals, n, prefix, n_gt, remaining, out_idx, cursors);
+  BS_COUNT_LAUNCH();
+  e = cudaGetLastError();
+  return e == cudaSuccess ? 0 : -(int)e;
+}

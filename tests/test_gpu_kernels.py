@@ -301,3 +301,29 @@ def test_scan_and_clear_compaction_and_table_pool(gpu):
     assert pool.hits > h0
     oa, ob = torch.argsort(a[0]), torch.argsort(b[0])
     assert torch.equal(a[0][oa], b[0][ob]) and torch.equal(a[1][oa], b[1][ob])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dtype", [torch.int64, torch.int32, torch.float32, torch.float64])
+def test_topk_radix_select_matches_torch(gpu, dtype):
+    g = torch.Generator(device="cuda").manual_seed(9)
+    for n, k, span in ((1, 1, 10), (1000, 7, 5), (100000, 100, 50), (3000000, 1000, 1 << 40),
+                       (65537, 65537, 3), (5000, 9000, 100)):
+        if dtype.is_floating_point:
+            v = (torch.randn(n, device="cuda", generator=g) * span).to(dtype)
+            v[::7] = 0.0  # ties, and both zeros
+            v[1::97] = -0.0
+        else:
+            hi = min(span, 1 << 30) if dtype == torch.int32 else span
+            v = torch.randint(-hi, hi, (n,), device="cuda", generator=g).to(dtype)
+        vals, idx = gpu.topk(v, k)
+        kk = min(k, n)
+        want = torch.sort(v, descending=True, stable=True)
+        assert vals.shape[0] == kk and torch.equal(vals, want.values[:kk])
+        assert torch.equal(v[idx], vals) and len(set(idx.tolist())) == kk
+        # equal values are reported in index order (which ties make the cut is unspecified)
+        same = vals[1:] == vals[:-1]
+        assert bool((idx[1:][same] > idx[:-1][same]).all())
+    from bigslice_b200.exec.topn import top_n
+    v = torch.tensor([3, 9, 9, 1, 7], device="cuda")
+    assert top_n(v, 3) == [1, 2, 4]
