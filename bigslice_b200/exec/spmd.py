@@ -175,8 +175,9 @@ class SpmdExecutor(LocalExecutor):
         # Every rank must issue the same invocation (the reference's workers compile
         # exactly the driver's invocation, bigmachine.go:546-640): the fingerprint
         # rides on the next control-plane vote instead of costing a collective here.
-        self._pending_fp.append((einv.index, einv.location, einv.inv.func,
-                                 int(fingerprint(einv.inv)[:15], 16)))
+        with self._glock:
+            self._pending_fp.append((einv.index, einv.location, einv.inv.func,
+                                     int(fingerprint(einv.inv)[:15], 16)))
         if not einv.uses_cache():
             return do_compile(einv)  # nothing in a CompileEnv to agree on
         if self.rank == 0:
@@ -191,10 +192,10 @@ class SpmdExecutor(LocalExecutor):
         einv.env = pickle.loads(box[0])
         return do_compile(einv)
 
-    def _vote(self, bad: int) -> int:
+    def _vote(self, bad: int, upto: Optional[int] = None) -> int:
         """Control-plane agreement before an exchange: did every rank's producers
         succeed, and did every rank issue the same invocations since the last vote."""
-        acc, fps = self._take_fingerprint()
+        acc, fps = self._take_fingerprint(upto)
         flag = torch.tensor([bad, acc, -acc], dtype=torch.int64)
         with span("xchg/status_vote"):
             dist.all_reduce(flag, op=dist.ReduceOp.MAX, group=self.ctrl_group)
@@ -304,7 +305,7 @@ class SpmdExecutor(LocalExecutor):
             with span("xchg/table_total"):
                 return self._exchange_table(gid, head, table, nparts, bad)
         if self.world > 1:
-            bad = self._vote(bad)
+            bad = self._vote(bad, head.name.inv_index)
         if bad:
             raise errors.fatal("spmd: a producer of %s failed on some rank" % group[0].name)
         frames: List[Frame] = []
@@ -368,8 +369,14 @@ class SpmdExecutor(LocalExecutor):
                 self.group_tables[gid] = t
             return t
 
-    def _take_fingerprint(self) -> Tuple[int, List]:
-        fps, self._pending_fp = self._pending_fp, []
+    def _take_fingerprint(self, upto: Optional[int] = None) -> Tuple[int, List]:
+        """Fingerprints of the invocations not yet agreed on, up to and including
+        invocation ``upto`` — the one whose exchange carries the vote.  (The main
+        thread may already have compiled later invocations, e.g. after this one
+        failed locally; those belong to later votes on every rank.)"""
+        with self._glock:
+            fps = [f for f in self._pending_fp if upto is None or f[0] <= upto]
+            self._pending_fp = [f for f in self._pending_fp if not (upto is None or f[0] <= upto)]
         acc = 0
         for _, _, _, fp in fps:
             acc = (acc * 1000003 + fp) & ((1 << 61) - 1)
@@ -395,7 +402,7 @@ class SpmdExecutor(LocalExecutor):
         else:
             # the producer status and the invocation fingerprint travel with the
             # counts: all ranks agree on device, without a host collective
-            acc, fps = self._take_fingerprint()
+            acc, fps = self._take_fingerprint(head.name.inv_index)
             try:
                 with span("xchg/exchange_table"):
                     got = self.peers.exchange_table(table, nparts, clear=gpu.RECYCLE == "clear",

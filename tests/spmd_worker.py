@@ -57,6 +57,39 @@ def chain(prev: bs.Slice):
     return bs.Reduce(bs.Map(prev, lambda k, v: (k % 5, v)), bs.ops.add)
 
 
+@bs.Func
+def failing(nshard: int):
+    """Shard 1 fails fatally in its Map; the others produce rows."""
+    per = 8
+    keys = torch.arange(per * nshard)
+    keys[per] = -7777  # lands in shard 1 (Const splits rows evenly, in order)
+
+    def check(k, v):
+        if bool((k == -7777).any()):
+            raise bs.errors.fatal("disk on fire")
+        return k % 5, v
+    return bs.Reduce(bs.Map(bs.Const(nshard, keys, torch.ones(per * nshard, dtype=torch.int64)), check),
+                     bs.ops.add)
+
+
+def failure_check(sess, ex, world, rank):
+    """A fatal producer error on one rank fails the invocation on every rank
+    (status vote: gloo on CPU, carried by the exchange on GPUs) and the session
+    keeps working afterwards."""
+    from bigslice_b200 import errors
+    try:
+        sess.run(failing, world + 1)
+        return False
+    except errors.Error as e:
+        if not errors.is_fatal(e):
+            return False
+    rows = ex.gather(sess.run(wordcount, world))
+    want = {}
+    for k in KEYS.tolist():
+        want[k] = want.get(k, 0) + 1
+    return dict(rows) == want
+
+
 def exchange_content_check(ex, world, rank):
     """Rows pushed through the fused exchange must arrive exactly once, intact,
     at the owner of hash(key) % nparts — checked column by column."""
@@ -258,6 +291,7 @@ def main():
         out["table_exchange_ok"] = table_exchange_check(ex, world, rank)
         out["exchange_vote_ok"] = exchange_vote_check(ex, world, rank)
         out["bigcount_ok"] = big_wordcount_check(sess, ex, world, rank)
+    out["failure_ok"] = failure_check(sess, ex, world, rank)
     out["modes"] = sorted(set(e["mode"] for e in ex.exchange_log))
     try:
         from bigslice_b200.ops import gpu

@@ -38,7 +38,7 @@ def check(outs, world):
     for o in outs:
         assert o["world"] == world
         for k in ("wordcount_ok", "chain_ok", "strcount_ok", "join_ok", "reshard_ok",
-                  "reshard_placement_ok"):
+                  "reshard_placement_ok", "failure_ok"):
             assert o[k], (k, o)
     for o in outs:
         for k in ("exchange_content_ok", "table_exchange_ok", "exchange_vote_ok", "bigcount_ok"):
