@@ -46,7 +46,41 @@ def combine_frame(f: Frame, func, ctx=None) -> Frame:
     if _gpu_combinable(f, func):
         from ..ops import gpu
         return gpu.hash_combine_frame(f, func.builtin)
+    g = _host_hash_combine(f, func)
+    if g is not None:
+        return g
     return combine_sorted(f.sorted(), func, ctx)
+
+
+_HOST_VTYPE = {torch.int32: 0, torch.int64: 1, torch.float32: 2, torch.float64: 3}
+_HOST_OP = {"add": 0, "min": 1, "max": 2}
+
+
+def _host_hash_combine(f: Frame, func) -> Optional[Frame]:
+    """CPU frames of <int64 key, numeric value> with a builtin functor: C++
+    open-addressing aggregation with the GIL released (``csrc/native.cpp:
+    host_hash_combine``), then a sort of the *distinct* keys only — instead of
+    sorting every row.  Returns None when it does not apply."""
+    op = getattr(func, "builtin", None)
+    if op not in _HOST_OP or f.num_out() != 2 or f.prefix() != 1 or len(f) < 2048:
+        return None
+    k, v = f.col(0), f.col(1)
+    if not (isinstance(k, torch.Tensor) and isinstance(v, torch.Tensor) and k.device.type == "cpu"
+            and k.dtype == torch.int64 and k.dim() == 1 and v.dim() == 1 and v.dtype in _HOST_VTYPE):
+        return None
+    from .. import _native
+    nat = _native.lib()
+    if nat is None or not hasattr(nat, "host_hash_combine"):
+        return None
+    k, v = k.contiguous(), v.contiguous()
+    ok, ov = torch.empty_like(k), torch.empty_like(v)
+    m = nat.host_hash_combine(k.data_ptr(), v.data_ptr(), k.numel(), _HOST_VTYPE[v.dtype], _HOST_OP[op],
+                              ok.data_ptr(), ov.data_ptr())
+    if m < 0:
+        return None
+    ok, ov = ok[:m], ov[:m]
+    order = torch.sort(ok, stable=True)[1]
+    return Frame([ok[order], ov[order]], f.typ)
 
 
 class CombiningFrame:

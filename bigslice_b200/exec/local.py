@@ -114,8 +114,22 @@ def split_by_partition(f: Frame, ids: torch.Tensor, npart: int) -> List[Frame]:
         if gpu.available():
             return gpu.partition_frame(f, ids, npart)
     ids = ids.to(torch.int64).cpu() if ids.device.type != "cpu" else ids.to(torch.int64)
-    order = torch.sort(ids, stable=True)[1]
-    counts = torch.bincount(ids, minlength=npart).tolist()
+    order = counts = None
+    if ids.numel() >= 2048:
+        # C++ stable counting sort, GIL released (csrc/native.cpp: host_partition_perm)
+        from .. import _native
+        nat = _native.lib()
+        if nat is not None and hasattr(nat, "host_partition_perm"):
+            ids = ids.contiguous()
+            perm = torch.empty_like(ids)
+            cnt = torch.empty(npart, dtype=torch.int64)
+            if nat.host_partition_perm(ids.data_ptr(), ids.numel(), npart, perm.data_ptr(),
+                                       cnt.data_ptr()) < 0:
+                raise errors.fatal("partitioner returned a shard outside [0, %d)" % npart)
+            order, counts = perm, cnt.tolist()
+    if order is None:
+        order = torch.sort(ids, stable=True)[1]
+        counts = torch.bincount(ids, minlength=npart).tolist()
     g = f.take(order)
     out, off = [], 0
     for c in counts:

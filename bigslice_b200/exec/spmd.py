@@ -337,8 +337,8 @@ class SpmdExecutor(LocalExecutor):
             return False
         if task.partitioner is not default_partitioner:
             return False
-        if self.world > 1 and self.peers is None:
-            return False
+        if self.peers is None and not (self.world == 1 and task.num_partition == 1):
+            return False  # the table is shuffled by the peer-memory kernels only
         from ..ops import gpu
         typ = task.type.typ
         if task.combiner.builtin not in gpu.OPS or typ.num_out() != 2 or typ.prefix() != 1:

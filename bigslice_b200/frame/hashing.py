@@ -13,6 +13,8 @@ Three implementations share these semantics: this vectorised torch version
 from __future__ import annotations
 
 import numpy as np
+from typing import Optional
+
 import torch
 
 _M = 0xFFFFFFFF
@@ -44,8 +46,29 @@ def _fmix(h: torch.Tensor) -> torch.Tensor:
     return h ^ (h >> 16)
 
 
+_NATIVE_MIN = 2048  # below this the torch ops are as fast as the call overhead
+
+
+def _native_hash(v: torch.Tensor, seed: int, width: int) -> Optional[torch.Tensor]:
+    """C++ host path (``csrc/native.cpp: host_hash_i64``, GIL released) for CPU
+    int64 tensors; None when it does not apply."""
+    if v.device.type != "cpu" or v.dtype != torch.int64 or v.dim() != 1 or v.numel() < _NATIVE_MIN:
+        return None
+    from .. import _native
+    nat = _native.lib()
+    if nat is None or not hasattr(nat, "host_hash_i64"):
+        return None
+    v = v.contiguous()
+    out = torch.empty_like(v)
+    nat.host_hash_i64(v.data_ptr(), out.data_ptr(), v.numel(), width, seed & _M, False)
+    return out
+
+
 def hash32(v: torch.Tensor, seed: int) -> torch.Tensor:
     """murmur3 of 4 LE bytes; ``v`` holds uint32 values in int64."""
+    out = _native_hash(v, seed, 4)
+    if out is not None:
+        return out
     h = torch.full_like(v, seed & _M)
     h = _mix_h(h, v & _M)
     return _fmix(h ^ 4)
@@ -53,6 +76,9 @@ def hash32(v: torch.Tensor, seed: int) -> torch.Tensor:
 
 def hash64(v: torch.Tensor, seed: int) -> torch.Tensor:
     """murmur3 of 8 LE bytes; ``v`` is int64 (bit pattern)."""
+    out = _native_hash(v, seed, 8)
+    if out is not None:
+        return out
     lo = v & _M
     hi = (v >> 32) & _M
     h = torch.full_like(v, seed & _M)

@@ -15,6 +15,7 @@
 #include <cstdint>
 #include <cstring>
 #include <string>
+#include <type_traits>
 #include <unordered_map>
 #include <unordered_set>
 #include <vector>
@@ -224,6 +225,168 @@ static uint32_t py_murmur3_bytes(py::bytes b, uint32_t seed) {
   return murmur3_32(reinterpret_cast<const uint8_t*>(p), (size_t)n, seed);
 }
 
+// ---------------------------------------------------------------------------
+// Host data-path kernels for the CPU executors (called with the GIL released, so
+// the evaluator's thread pool scales across cores): murmur3 of fixed-width keys,
+// stable partition permutation, hash aggregation of <int64 key, numeric value>.
+// Tensors are passed as raw addresses (torch `data_ptr()`); the Python side
+// guarantees contiguity, dtype and lifetime.
+static inline uint32_t fmix32(uint32_t h) {
+  h ^= h >> 16;
+  h *= 0x85ebca6bu;
+  h ^= h >> 13;
+  h *= 0xc2b2ae35u;
+  h ^= h >> 16;
+  return h;
+}
+static inline uint32_t mm_round(uint32_t h, uint32_t k) {
+  k *= 0xcc9e2d51u;
+  k = rotl32(k, 15);
+  k *= 0x1b873593u;
+  h ^= k;
+  h = rotl32(h, 13);
+  return h * 5 + 0xe6546b64u;
+}
+static inline uint32_t murmur3_u64(uint64_t v, uint32_t seed) {
+  uint32_t h = mm_round(seed, (uint32_t)v);
+  h = mm_round(h, (uint32_t)(v >> 32));
+  return fmix32(h ^ 8u);
+}
+static inline uint32_t murmur3_u32(uint32_t v, uint32_t seed) { return fmix32(mm_round(seed, v) ^ 4u); }
+
+// out[i] = murmur3 of the 8-byte (width 8) or low 4-byte (width 4) value in[i]; in/out int64.
+static void host_hash_i64(uintptr_t in_, uintptr_t out_, int64_t n, int width, uint32_t seed, bool xor_into) {
+  const int64_t* in = reinterpret_cast<const int64_t*>(in_);
+  int64_t* out = reinterpret_cast<int64_t*>(out_);
+  if (width == 8) {
+    for (int64_t i = 0; i < n; ++i) {
+      uint32_t h = murmur3_u64((uint64_t)in[i], seed);
+      out[i] = xor_into ? (out[i] ^ (int64_t)h) : (int64_t)h;
+    }
+  } else {
+    for (int64_t i = 0; i < n; ++i) {
+      uint32_t h = murmur3_u32((uint32_t)in[i], seed);
+      out[i] = xor_into ? (out[i] ^ (int64_t)h) : (int64_t)h;
+    }
+  }
+}
+
+// Stable counting sort of row indices by destination id: perm groups the rows of
+// partition 0, then 1, ...; counts[p] = rows of partition p.  Returns -1 on an
+// id outside [0, npart).
+static int64_t host_partition_perm(uintptr_t ids_, int64_t n, int64_t npart, uintptr_t perm_, uintptr_t counts_) {
+  const int64_t* ids = reinterpret_cast<const int64_t*>(ids_);
+  int64_t* perm = reinterpret_cast<int64_t*>(perm_);
+  int64_t* counts = reinterpret_cast<int64_t*>(counts_);
+  for (int64_t p = 0; p < npart; ++p) counts[p] = 0;
+  for (int64_t i = 0; i < n; ++i) {
+    int64_t d = ids[i];
+    if (d < 0 || d >= npart) return -1;
+    ++counts[d];
+  }
+  std::vector<int64_t> cur((size_t)npart);
+  int64_t run = 0;
+  for (int64_t p = 0; p < npart; ++p) {
+    cur[(size_t)p] = run;
+    run += counts[p];
+  }
+  for (int64_t i = 0; i < n; ++i) perm[cur[(size_t)ids[i]]++] = i;
+  return n;
+}
+
+template <typename V>
+struct HostCombine {
+  static inline V add(V a, V b) {
+    if constexpr (std::is_integral<V>::value) {  // wraps like the device atomics (no signed-overflow UB)
+      using U = typename std::make_unsigned<V>::type;
+      return (V)((U)a + (U)b);
+    } else {
+      return a + b;
+    }
+  }
+  static inline V apply(int op, V a, V b) { return op == 0 ? add(a, b) : (op == 1 ? (b < a ? b : a) : (b > a ? b : a)); }
+};
+
+// Open-addressing aggregation; writes the distinct keys and combined values
+// (unordered) to out_keys/out_vals (capacity n) and returns their number.
+template <typename V>
+static int64_t host_combine_t(const int64_t* keys, const V* vals, int64_t n, int op, int64_t* out_keys, V* out_vals) {
+  if (n <= 0) return 0;
+  size_t cap = 1024;
+  while (cap < (size_t)n / 4) cap <<= 1;  // grows on demand: most inputs have far fewer keys than rows
+  std::vector<int64_t> tk(cap);
+  std::vector<V> tv(cap);
+  std::vector<uint8_t> used(cap, 0);
+  size_t count = 0;
+  auto mix = [](uint64_t x) -> uint64_t {
+    x ^= x >> 33;
+    x *= 0xff51afd7ed558ccdULL;
+    x ^= x >> 33;
+    x *= 0xc4ceb9fe1a85ec53ULL;
+    x ^= x >> 33;
+    return x;
+  };
+  auto grow = [&]() {
+    size_t ncap = cap * 2;
+    std::vector<int64_t> nk(ncap);
+    std::vector<V> nv(ncap);
+    std::vector<uint8_t> nu(ncap, 0);
+    for (size_t i = 0; i < cap; ++i) {
+      if (!used[i]) continue;
+      size_t s = (size_t)mix((uint64_t)tk[i]) & (ncap - 1);
+      while (nu[s]) s = (s + 1) & (ncap - 1);
+      nu[s] = 1;
+      nk[s] = tk[i];
+      nv[s] = tv[i];
+    }
+    tk.swap(nk);
+    tv.swap(nv);
+    used.swap(nu);
+    cap = ncap;
+  };
+  for (int64_t i = 0; i < n; ++i) {
+    const int64_t k = keys[i];
+    size_t s = (size_t)mix((uint64_t)k) & (cap - 1);
+    while (true) {
+      if (!used[s]) {
+        used[s] = 1;
+        tk[s] = k;
+        tv[s] = vals[i];
+        if (++count * 2 > cap) grow();
+        break;
+      }
+      if (tk[s] == k) {
+        tv[s] = HostCombine<V>::apply(op, tv[s], vals[i]);
+        break;
+      }
+      s = (s + 1) & (cap - 1);
+    }
+  }
+  int64_t m = 0;
+  for (size_t i = 0; i < cap; ++i) {
+    if (used[i]) {
+      out_keys[m] = tk[i];
+      out_vals[m] = tv[i];
+      ++m;
+    }
+  }
+  return m;
+}
+
+// vtype: 0 int32, 1 int64, 2 float32, 3 float64; op: 0 add, 1 min, 2 max.
+static int64_t host_hash_combine(uintptr_t keys, uintptr_t vals, int64_t n, int vtype, int op,
+                                 uintptr_t out_keys, uintptr_t out_vals) {
+  const int64_t* k = reinterpret_cast<const int64_t*>(keys);
+  int64_t* ok = reinterpret_cast<int64_t*>(out_keys);
+  switch (vtype) {
+    case 0: return host_combine_t<int32_t>(k, reinterpret_cast<const int32_t*>(vals), n, op, ok, reinterpret_cast<int32_t*>(out_vals));
+    case 1: return host_combine_t<int64_t>(k, reinterpret_cast<const int64_t*>(vals), n, op, ok, reinterpret_cast<int64_t*>(out_vals));
+    case 2: return host_combine_t<float>(k, reinterpret_cast<const float*>(vals), n, op, ok, reinterpret_cast<float*>(out_vals));
+    case 3: return host_combine_t<double>(k, reinterpret_cast<const double*>(vals), n, op, ok, reinterpret_cast<double*>(out_vals));
+  }
+  return -1;
+}
+
 PYBIND11_MODULE(_bsnative, m) {
   m.doc() = "bigslice_b200 host runtime: evaluator core, crc32, murmur3";
   py::class_<EvalCore>(m, "EvalCore")
@@ -242,4 +405,7 @@ PYBIND11_MODULE(_bsnative, m) {
   m.def("murmur3_strings", &py_murmur3_strings);
   m.def("murmur3_fixed", &py_murmur3_fixed);
   m.def("murmur3_bytes", &py_murmur3_bytes);
+  m.def("host_hash_i64", &host_hash_i64, py::call_guard<py::gil_scoped_release>());
+  m.def("host_partition_perm", &host_partition_perm, py::call_guard<py::gil_scoped_release>());
+  m.def("host_hash_combine", &host_hash_combine, py::call_guard<py::gil_scoped_release>());
 }

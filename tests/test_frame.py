@@ -173,3 +173,55 @@ def test_vec_column():
     assert f.typ.out(1).name == "[4]float32"
     s = f.sorted()
     assert s.col(1)[0].tolist() == [4.0, 5.0, 6.0, 7.0]
+
+
+# ---- native host data-path kernels (csrc/native.cpp) vs the torch reference ----
+def _without_native(fn):
+    import os
+    from bigslice_b200 import _native
+    os.environ["BIGSLICE_NO_NATIVE"] = "1"
+    _native.reset_for_tests()
+    try:
+        return fn()
+    finally:
+        del os.environ["BIGSLICE_NO_NATIVE"]
+        _native.reset_for_tests()
+
+
+def test_native_host_hash_partition_combine_match_reference():
+    from bigslice_b200 import _native, slicefunc
+    from bigslice_b200.exec.combiner import combine_frame
+    from bigslice_b200.exec.local import split_by_partition
+    from bigslice_b200.frame import hashing
+    if _native.lib() is None:
+        pytest.skip("native runtime not built")
+    g = torch.Generator().manual_seed(4)
+    n = 50000
+    for dt in (torch.int64, torch.int32, torch.float64, torch.float32, torch.int16, torch.uint8):
+        col = (torch.randint(-(1 << 40), 1 << 40, (n,), generator=g) % 251 - 100).to(dt) \
+            if dt != torch.int64 else torch.randint(-(1 << 62), 1 << 62, (n,), generator=g)
+        for seed in (0, 0x9ACB0442):
+            want = _without_native(lambda: hashing.hash_tensor(col, seed))
+            assert torch.equal(hashing.hash_tensor(col, seed), want), (dt, seed)
+    keys = torch.randint(0, 3000, (n,), generator=g)
+    typ = slicetype.Type([torch.int64, torch.int64], 1)
+    f = Frame([keys, torch.arange(n)], typ)
+    ids = keys % 7
+    parts = split_by_partition(f, ids, 7)
+    ref = _without_native(lambda: split_by_partition(f, ids, 7))
+    for a, b in zip(parts, ref):  # stable: identical row order inside every partition
+        assert torch.equal(a.col(0), b.col(0)) and torch.equal(a.col(1), b.col(1))
+    with pytest.raises(bs.errors.Error):
+        split_by_partition(f, ids + 1, 7)  # shard 7 is out of range
+    for vdt in (torch.int64, torch.int32, torch.float32, torch.float64):
+        for op in (bs.ops.add, bs.ops.min, bs.ops.max):
+            vals = torch.randint(-50, 50, (n,), generator=g).to(vdt)
+            fr = Frame([keys, vals], slicetype.Type([torch.int64, vdt], 1))
+            fn = slicefunc.of(op)
+            got = combine_frame(fr, fn)
+            want = _without_native(lambda: combine_frame(fr, fn))
+            assert torch.equal(got.col(0), want.col(0)) and torch.equal(got.col(1), want.col(1)), (vdt, op)
+    # integer adds wrap like the device atomics
+    big = Frame([torch.zeros(4096, dtype=torch.int64), torch.full((4096,), (1 << 62) + 5)], typ)
+    out = combine_frame(big, slicefunc.of(bs.ops.add))
+    assert out.col(1).tolist() == [int(torch.full((4096,), (1 << 62) + 5).sum())]  # torch wraps too
