@@ -57,19 +57,29 @@ _NP = {"int8": np.int8, "int16": np.int16, "int32": np.int32, "int64": np.int64,
 def crc32(data, value: int = 0) -> int:
     """CRC32-IEEE; native slice-by-8 when built, zlib otherwise."""
     nat = _native.lib()
-    if nat is not None:
-        return nat.crc32(data, value)
-    return zlib.crc32(data, value) & 0xFFFFFFFF
+    # zlib's CRC32 (hardware folding in current builds, releases the GIL) is faster
+    # than the slice-by-8 in csrc/native.cpp; the native module stays the fallback
+    # and provides crc32_combine for stitching device-computed checksums.
+    try:
+        return zlib.crc32(data, value) & 0xFFFFFFFF
+    except (TypeError, ValueError, BufferError):
+        if nat is not None:
+            return nat.crc32(bytes(data), value)
+        raise
 
 
-def _tensor_bytes(t: torch.Tensor) -> bytes:
+def _tensor_bytes(t: torch.Tensor):
+    """The tensor's bytes as a flat memoryview over its (host, contiguous)
+    storage — no copy for CPU tensors; the view keeps the tensor alive."""
     t = t.detach()
     if t.is_cuda:
         t = t.cpu()
     t = t.contiguous()
     if t.dtype == torch.bfloat16:
-        return t.view(torch.int16).numpy().tobytes()
-    return t.numpy().tobytes()
+        t = t.view(torch.int16)
+    if t.numel() == 0:
+        return b""
+    return memoryview(t.numpy()).cast("B")
 
 
 def _base(dt: DType) -> DType:
@@ -77,6 +87,12 @@ def _base(dt: DType) -> DType:
 
 
 def _encode_varlen(vals, is_str: bool) -> bytes:
+    nat = _native.lib()
+    if nat is not None and hasattr(nat, "codec_encode_varlen"):
+        try:
+            return nat.codec_encode_varlen(vals if isinstance(vals, (list, tuple)) else list(vals), is_str)
+        except TypeError:
+            pass  # unusual element types: the generic loop below reports them
     enc = []
     for v in vals:
         if v is None:
@@ -101,7 +117,7 @@ def _encode_column(col, dt: DType, session: Session) -> bytes:
                         0, len(payload)) + payload
     if dt.is_tensor:
         payload = _tensor_bytes(col)
-        return hdr.pack(0, _DT_INDEX[_base(dt).name], dt.width, len(payload)) + payload
+        return hdr.pack(0, _DT_INDEX[_base(dt).name], dt.width, len(payload)) + bytes(payload)
     if dt.kind == "str":
         payload = _encode_varlen(col, True)
         return hdr.pack(1, _DT_INDEX["string"], 0, len(payload)) + payload
@@ -133,16 +149,17 @@ def _encode_column(col, dt: DType, session: Session) -> bytes:
 DEVICE_CRC_MIN_BYTES = 1 << 20
 
 
-def encode_frame(f: Frame, session: Optional[Session] = None) -> bytes:
-    """Encode one frame as one checksummed batch."""
-    session = session or Session()
+def _frame_pieces(f: Frame, session: Session):
+    """The batch body as a list of bytes-like pieces (tensor payloads are
+    zero-copy views) plus the device-computed CRCs of some of them."""
     pieces = [struct.pack("<QI", len(f), f.num_out())]
     dev_crcs = {}  # piece index -> (crc, nbytes) computed on the device
     hdr = struct.Struct("<BBIQ")
     for col, dt in zip(f.cols(), f.typ.cols):
-        if dt.is_tensor and isinstance(col, torch.Tensor) and col.is_cuda \
-                and col.numel() * col.element_size() >= DEVICE_CRC_MIN_BYTES:
-            crc = _device_crc(col)
+        if dt.is_tensor and isinstance(col, torch.Tensor):
+            crc = None
+            if col.is_cuda and col.numel() * col.element_size() >= DEVICE_CRC_MIN_BYTES:
+                crc = _device_crc(col)
             payload = _tensor_bytes(col)
             pieces.append(hdr.pack(0, _DT_INDEX[_base(dt).name], dt.width, len(payload)))
             if crc is not None:
@@ -150,20 +167,42 @@ def encode_frame(f: Frame, session: Optional[Session] = None) -> bytes:
             pieces.append(payload)
         else:
             pieces.append(_encode_column(col, dt, session))
-    b = b"".join(pieces)
-    head = struct.pack("<IQ", MAGIC, len(b))
-    if not dev_crcs:
-        crc = crc32(b, crc32(head))
-    else:
-        nat = _native.lib()
-        crc = crc32(head)
-        for i, p in enumerate(pieces):
-            if i in dev_crcs:
-                c2, n2 = dev_crcs[i]
-                crc = nat.crc32_combine(crc, c2, n2)
-            else:
-                crc = crc32(p, crc)
-    return head + b + struct.pack("<I", crc)
+    return pieces, dev_crcs
+
+
+def _pieces_crc(head: bytes, pieces, dev_crcs) -> int:
+    crc = crc32(head)
+    nat = _native.lib() if dev_crcs else None
+    for i, p in enumerate(pieces):
+        if i in dev_crcs and nat is not None:
+            c2, n2 = dev_crcs[i]
+            crc = nat.crc32_combine(crc, c2, n2)
+        elif len(p):
+            crc = crc32(p, crc)
+    return crc
+
+
+def encode_frame(f: Frame, session: Optional[Session] = None) -> bytes:
+    """Encode one frame as one checksummed batch."""
+    pieces, dev_crcs = _frame_pieces(f, session or Session())
+    head = struct.pack("<IQ", MAGIC, sum(len(p) for p in pieces))
+    crc = _pieces_crc(head, pieces, dev_crcs)
+    return b"".join([head] + pieces + [struct.pack("<I", crc)])
+
+
+def write_frame(w: BinaryIO, f: Frame, session: Optional[Session] = None) -> int:
+    """Stream one checksummed batch to ``w`` without assembling it in memory
+    (tensor payloads go from their storage straight to the writer)."""
+    pieces, dev_crcs = _frame_pieces(f, session or Session())
+    blen = sum(len(p) for p in pieces)
+    head = struct.pack("<IQ", MAGIC, blen)
+    crc = _pieces_crc(head, pieces, dev_crcs)
+    w.write(head)
+    for p in pieces:
+        if len(p):
+            w.write(p)
+    w.write(struct.pack("<I", crc))
+    return 16 + blen
 
 
 def _device_crc(col: torch.Tensor) -> Optional[int]:
@@ -185,10 +224,9 @@ class Encoder:
         self.bytes_written = 0
 
     def write(self, f: Frame) -> int:
-        b = encode_frame(f, self.session)
-        self.w.write(b)
-        self.bytes_written += len(b)
-        return len(b)
+        n = write_frame(self.w, f, self.session)
+        self.bytes_written += n
+        return n
 
     encode = write
 
@@ -208,6 +246,17 @@ def _decode_varlen(payload: memoryview, n: int, is_str: bool) -> np.ndarray:
     ob = (n + 1) * 8
     if len(payload) < ob:
         raise errors.IntegrityError("sliceio: short string column")
+    nat = _native.lib()
+    if nat is not None and hasattr(nat, "codec_decode_varlen"):
+        try:
+            vals = nat.codec_decode_varlen(payload, n, is_str)
+        except ValueError as e:
+            raise errors.IntegrityError("sliceio: %s" % e)
+        except UnicodeDecodeError as e:
+            raise errors.IntegrityError("sliceio: corrupt string column", e)
+        out = np.empty(n, dtype=object)
+        out[:] = vals
+        return out
     offs = np.frombuffer(payload[:ob], dtype="<i8")
     data = bytes(payload[ob:])
     out = np.empty(n, dtype=object)

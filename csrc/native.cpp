@@ -387,6 +387,81 @@ static int64_t host_hash_combine(uintptr_t keys, uintptr_t vals, int64_t n, int 
   return -1;
 }
 
+// ---------------------------------------------------------------------------
+// Variable-length columns of the frame codec: [n+1 little-endian int64 offsets]
+// [concatenated bytes].  str elements are UTF-8, bytes elements raw, None = empty.
+static py::bytes codec_encode_varlen(py::sequence items, bool is_str) {
+  const py::ssize_t n = py::len(items);
+  std::vector<const char*> ptr((size_t)n);
+  std::vector<py::ssize_t> len((size_t)n);
+  std::vector<py::object> keep;  // temporaries (bytes(v) conversions) alive until copied
+  size_t total = 0;
+  for (py::ssize_t i = 0; i < n; ++i) {
+    py::object it = items[i];
+    PyObject* o = it.ptr();
+    const char* p = "";
+    py::ssize_t l = 0;
+    if (o == Py_None) {
+    } else if (is_str) {
+      if (!PyUnicode_Check(o)) throw py::type_error("codec: string column holds a non-str value");
+      p = PyUnicode_AsUTF8AndSize(o, &l);
+      if (p == nullptr) throw py::error_already_set();
+    } else {
+      if (!PyBytes_Check(o)) {
+        it = py::bytes(py::reinterpret_steal<py::object>(PyObject_Bytes(o)));
+        if (!it) throw py::error_already_set();
+        o = it.ptr();
+      }
+      char* q;
+      if (PyBytes_AsStringAndSize(o, &q, &l) != 0) throw py::error_already_set();
+      p = q;
+    }
+    keep.push_back(it);
+    ptr[(size_t)i] = p;
+    len[(size_t)i] = l;
+    total += (size_t)l;
+  }
+  std::string out;
+  out.resize((size_t)(n + 1) * 8 + total);
+  int64_t off = 0;
+  char* base = &out[0];
+  char* data = base + (size_t)(n + 1) * 8;
+  memcpy(base, &off, 8);
+  for (py::ssize_t i = 0; i < n; ++i) {
+    memcpy(data + off, ptr[(size_t)i], (size_t)len[(size_t)i]);
+    off += len[(size_t)i];
+    memcpy(base + (size_t)(i + 1) * 8, &off, 8);
+  }
+  return py::bytes(out);
+}
+
+// Returns a list of str / bytes; raises ValueError on inconsistent offsets.
+static py::list codec_decode_varlen(py::buffer payload, int64_t n, bool is_str) {
+  py::buffer_info info = payload.request();
+  const size_t nbytes = (size_t)info.size * (size_t)info.itemsize;
+  const char* base = static_cast<const char*>(info.ptr);
+  const size_t ob = (size_t)(n + 1) * 8;
+  if (n < 0 || nbytes < ob) throw py::value_error("short string column");
+  const char* data = base + ob;
+  const int64_t dlen = (int64_t)(nbytes - ob);
+  py::list out((size_t)n);
+  int64_t prev;
+  memcpy(&prev, base, 8);
+  if (n > 0 && prev != 0) throw py::value_error("corrupt string offsets");
+  for (int64_t i = 0; i < n; ++i) {
+    int64_t next;
+    memcpy(&next, base + (size_t)(i + 1) * 8, 8);
+    if (next < prev || next > dlen) throw py::value_error("corrupt string offsets");
+    PyObject* o = is_str ? PyUnicode_DecodeUTF8(data + prev, (Py_ssize_t)(next - prev), nullptr)
+                         : PyBytes_FromStringAndSize(data + prev, (Py_ssize_t)(next - prev));
+    if (o == nullptr) throw py::error_already_set();
+    PyList_SET_ITEM(out.ptr(), (Py_ssize_t)i, o);
+    prev = next;
+  }
+  if (n > 0 && prev != dlen) throw py::value_error("corrupt string offsets");
+  return out;
+}
+
 PYBIND11_MODULE(_bsnative, m) {
   m.doc() = "bigslice_b200 host runtime: evaluator core, crc32, murmur3";
   py::class_<EvalCore>(m, "EvalCore")
@@ -405,6 +480,8 @@ PYBIND11_MODULE(_bsnative, m) {
   m.def("murmur3_strings", &py_murmur3_strings);
   m.def("murmur3_fixed", &py_murmur3_fixed);
   m.def("murmur3_bytes", &py_murmur3_bytes);
+  m.def("codec_encode_varlen", &codec_encode_varlen);
+  m.def("codec_decode_varlen", &codec_decode_varlen);
   m.def("host_hash_i64", &host_hash_i64, py::call_guard<py::gil_scoped_release>());
   m.def("host_partition_perm", &host_partition_perm, py::call_guard<py::gil_scoped_release>());
   m.def("host_hash_combine", &host_hash_combine, py::call_guard<py::gil_scoped_release>());
