@@ -16,6 +16,7 @@ from __future__ import annotations
 
 from typing import List, Optional
 
+import numpy as np
 import torch
 
 from .. import stats
@@ -52,6 +53,33 @@ def combine_frame(f: Frame, func, ctx=None) -> Frame:
     return combine_sorted(f.sorted(), func, ctx)
 
 
+def _host_group_combine(f: Frame, k, v, op: str) -> Optional[Frame]:
+    """str / bytes keys: C++ grouping (``host_group_objects``: one hash-map pass
+    over UTF-8 views, no Python loop), a torch scatter for the values, and a sort
+    of the distinct keys only."""
+    if not (isinstance(v, torch.Tensor) and v.device.type == "cpu" and v.dim() == 1
+            and v.dtype in _HOST_VTYPE):
+        return None
+    from .. import _native
+    nat = _native.lib()
+    if nat is None or not hasattr(nat, "host_group_objects"):
+        return None
+    try:
+        firsts, group = nat.host_group_objects(k.tolist())
+    except TypeError:
+        return None  # mixed / exotic key objects: the generic sorted path handles them
+    gid = torch.from_numpy(group)
+    m = len(firsts)
+    if op == "add":
+        out = torch.zeros(m, dtype=v.dtype).index_add_(0, gid, v)
+    else:
+        out = torch.empty(m, dtype=v.dtype).scatter_reduce_(0, gid, v, "amin" if op == "min" else "amax",
+                                                            include_self=False)
+    keys = k[firsts]
+    g = Frame([keys, out], f.typ)
+    return g.sorted()
+
+
 _HOST_VTYPE = {torch.int32: 0, torch.int64: 1, torch.float32: 2, torch.float64: 3}
 _HOST_OP = {"add": 0, "min": 1, "max": 2}
 
@@ -65,6 +93,8 @@ def _host_hash_combine(f: Frame, func) -> Optional[Frame]:
     if op not in _HOST_OP or f.num_out() != 2 or f.prefix() != 1 or len(f) < 2048:
         return None
     k, v = f.col(0), f.col(1)
+    if isinstance(k, np.ndarray) and k.dtype == object:
+        return _host_group_combine(f, k, v, op)
     if not (isinstance(k, torch.Tensor) and isinstance(v, torch.Tensor) and k.device.type == "cpu"
             and k.dtype == torch.int64 and k.dim() == 1 and v.dim() == 1 and v.dtype in _HOST_VTYPE):
         return None

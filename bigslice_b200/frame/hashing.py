@@ -154,6 +154,13 @@ def hash_tensor(col: torch.Tensor, seed: int = 0) -> torch.Tensor:
 def hash_objects(col: np.ndarray, seed: int = 0) -> torch.Tensor:
     """Per-element hash of a host object column (str/bytes)."""
     from .. import _native
+    nat = _native.lib()
+    if nat is not None and hasattr(nat, "murmur3_objects") and len(col):
+        try:  # no Python-level loop: UTF-8 views of the str objects are hashed in C++
+            return torch.from_numpy(nat.murmur3_objects(col if isinstance(col, list) else col.tolist(),
+                                                        seed & _M))
+        except TypeError:
+            pass  # an unusual element: the loop below names its type
     enc = []
     for v in col:
         if isinstance(v, str):

@@ -15,6 +15,7 @@
 #include <cstdint>
 #include <cstring>
 #include <string>
+#include <string_view>
 #include <type_traits>
 #include <unordered_map>
 #include <unordered_set>
@@ -388,6 +389,80 @@ static int64_t host_hash_combine(uintptr_t keys, uintptr_t vals, int64_t n, int 
 }
 
 // ---------------------------------------------------------------------------
+// Object (str / bytes) key columns on the host: hashing and aggregation without
+// a Python-level loop.  A str's UTF-8 form is cached inside the object, so views
+// of it stay valid while the sequence is alive.
+static inline bool object_bytes(PyObject* o, const char** p, Py_ssize_t* l) {
+  if (o == Py_None) {
+    *p = "";
+    *l = 0;
+    return true;
+  }
+  if (PyUnicode_Check(o)) {
+    *p = PyUnicode_AsUTF8AndSize(o, l);
+    if (*p == nullptr) throw py::error_already_set();
+    return true;
+  }
+  if (PyBytes_Check(o)) {
+    char* q;
+    if (PyBytes_AsStringAndSize(o, &q, l) != 0) throw py::error_already_set();
+    *p = q;
+    return true;
+  }
+  if (PyByteArray_Check(o)) {
+    *p = PyByteArray_AS_STRING(o);
+    *l = PyByteArray_GET_SIZE(o);
+    return true;
+  }
+  return false;
+}
+
+static py::array_t<int64_t> py_murmur3_objects(py::sequence items, uint32_t seed) {
+  const py::ssize_t n = py::len(items);
+  py::array_t<int64_t> out(n);
+  auto w = out.mutable_unchecked<1>();
+  for (py::ssize_t i = 0; i < n; ++i) {
+    py::object it = items[i];
+    const char* p;
+    Py_ssize_t l;
+    if (!object_bytes(it.ptr(), &p, &l))
+      throw py::type_error("unhashable object column element");
+    w(i) = (int64_t)murmur3_32(reinterpret_cast<const uint8_t*>(p), (size_t)l, seed);
+  }
+  return out;
+}
+
+struct SvHash {
+  size_t operator()(const std::string_view& v) const noexcept { return std::hash<std::string_view>()(v); }
+};
+
+// Group equal keys (str compared by UTF-8 bytes, bytes raw; a column holds one
+// kind): returns (first-occurrence row index per group, group id per row).
+static py::tuple host_group_objects(py::sequence items) {
+  const py::ssize_t n = py::len(items);
+  std::unordered_map<std::string_view, int64_t, SvHash> ids;
+  ids.reserve((size_t)n / 4 + 16);
+  std::vector<py::object> keep;
+  keep.reserve((size_t)n);
+  std::vector<int64_t> first;
+  py::array_t<int64_t> group(n);
+  auto g = group.mutable_unchecked<1>();
+  for (py::ssize_t i = 0; i < n; ++i) {
+    py::object it = items[i];
+    const char* p;
+    Py_ssize_t l;
+    if (!object_bytes(it.ptr(), &p, &l)) throw py::type_error("ungroupable object column element");
+    keep.push_back(it);
+    auto ins = ids.emplace(std::string_view(p, (size_t)l), (int64_t)first.size());
+    if (ins.second) first.push_back((int64_t)i);
+    g(i) = ins.first->second;
+  }
+  py::array_t<int64_t> firsts((py::ssize_t)first.size());
+  if (!first.empty()) memcpy(firsts.mutable_data(), first.data(), first.size() * sizeof(int64_t));
+  return py::make_tuple(firsts, group);
+}
+
+// ---------------------------------------------------------------------------
 // Variable-length columns of the frame codec: [n+1 little-endian int64 offsets]
 // [concatenated bytes].  str elements are UTF-8, bytes elements raw, None = empty.
 static py::bytes codec_encode_varlen(py::sequence items, bool is_str) {
@@ -480,6 +555,8 @@ PYBIND11_MODULE(_bsnative, m) {
   m.def("murmur3_strings", &py_murmur3_strings);
   m.def("murmur3_fixed", &py_murmur3_fixed);
   m.def("murmur3_bytes", &py_murmur3_bytes);
+  m.def("murmur3_objects", &py_murmur3_objects);
+  m.def("host_group_objects", &host_group_objects);
   m.def("codec_encode_varlen", &codec_encode_varlen);
   m.def("codec_decode_varlen", &codec_decode_varlen);
   m.def("host_hash_i64", &host_hash_i64, py::call_guard<py::gil_scoped_release>());

@@ -225,3 +225,28 @@ def test_native_host_hash_partition_combine_match_reference():
     big = Frame([torch.zeros(4096, dtype=torch.int64), torch.full((4096,), (1 << 62) + 5)], typ)
     out = combine_frame(big, slicefunc.of(bs.ops.add))
     assert out.col(1).tolist() == [int(torch.full((4096,), (1 << 62) + 5).sum())]  # torch wraps too
+
+
+def test_native_object_hash_and_group_match_reference():
+    from bigslice_b200 import _native, slicefunc
+    from bigslice_b200.exec.combiner import combine_frame
+    if _native.lib() is None:
+        pytest.skip("native runtime not built")
+    rng = np.random.default_rng(2)
+    words = np.array(["w%d" % i for i in rng.integers(0, 3000, 20000)] + ["", "héllo", None], dtype=object)
+    for seed in (0, 77):
+        want = _without_native(lambda: hashing.hash_objects(words, seed))
+        assert torch.equal(hashing.hash_objects(words, seed), want)
+    raw = np.array([b"ab", bytearray(b"cd"), b""], dtype=object)
+    assert hashing.hash_objects(raw, 1).tolist() == [hashing.murmur3_bytes(b, 1) for b in (b"ab", b"cd", b"")]
+    with pytest.raises(TypeError):
+        hashing.hash_objects(np.array([1.5, "a"], dtype=object), 0)
+    keys = words[:20000]
+    for vdt in (torch.int64, torch.float32):
+        vals = torch.from_numpy(rng.integers(-9, 9, 20000)).to(vdt)
+        f = Frame([keys, vals], slicetype.Type([slicetype.string, vdt], 1))
+        for op in (bs.ops.add, bs.ops.min, bs.ops.max):
+            fn = slicefunc.of(op)
+            got = combine_frame(f, fn)
+            want = _without_native(lambda: combine_frame(f, fn))
+            assert list(got.col(0)) == list(want.col(0)) and torch.equal(got.col(1), want.col(1))
