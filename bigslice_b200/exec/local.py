@@ -132,7 +132,13 @@ def split_by_partition(f: Frame, ids: torch.Tensor, npart: int) -> List[Frame]:
         counts = torch.bincount(ids, minlength=npart).tolist()
     g = f.take(order)
     out, off = [], 0
+    empty = None
     for c in counts:
+        if c == 0:  # one shared empty frame: with many shards most partitions of a tile are empty
+            if empty is None:
+                empty = g.slice(0, 0)
+            out.append(empty)
+            continue
         out.append(g.slice(off, off + c))
         off += c
     return out
@@ -293,9 +299,30 @@ class LocalExecutor(Executor):
         """Readers for every dependency (expanded deps contribute one reader
         per producer task), failing with TaskLost if any output is gone."""
         ins: List[Reader] = []
+        plain = type(self).reader is LocalExecutor.reader  # not overridden by a subclass
         for dep in task.deps:
             readers = []
-            for dt in dep.tasks():
+            dts = dep.tasks()
+            if plain and len(dts) > 8:
+                # wide shuffle: one lock acquisition for all producers, and only the
+                # producers that have rows for this partition contribute a reader
+                for dt in dts:
+                    if dt.state() != TaskState.OK:
+                        raise errors.TaskLostError("dependency %s is not available" % dt.name)
+                with self.lock:
+                    bufs = [self.buffers.get(id(dt)) for dt in dts]
+                for dt, b in zip(dts, bufs):
+                    if b is None:
+                        raise errors.TaskLostError("output of %s is not available" % dt.name)
+                    if isinstance(b, TaskBuffer) and not b.parts[dep.partition]:
+                        continue
+                    readers.append(b.reader(dep.partition))
+                if dep.expand:
+                    ins.extend(readers)
+                else:
+                    ins.append(MultiReader(readers) if readers else EmptyReader())
+                continue
+            for dt in dts:
                 if dt.state() != TaskState.OK:
                     raise errors.TaskLostError("dependency %s is not available" % dt.name)
                 readers.append(self.reader(dt, dep.partition))
@@ -310,13 +337,26 @@ class LocalExecutor(Executor):
         its output (``bufferOutput`` + inline combine)."""
         npart = task.num_partition
         buf = TaskBuffer(npart)
-        combiners: Optional[List[Combiner]] = None
+        # Map-side combining happens *before* partitioning: one (spilling) combiner
+        # per task instead of one per partition, and only the combined rows are
+        # split.  The combiner's output is sorted by key and the split is stable, so
+        # every partition still receives its rows combined and in key order — the
+        # contract of the reference's per-partition combiners (worker.runCombine).
+        combiner: Optional[Combiner] = None
         if task.combiner is not None:
-            combiners = [Combiner(task.type.typ if hasattr(task.type, "typ") else task.type,
-                                  task.combiner, "%s-p%d" % (task.name.op, p), ctx=ctx)
-                         for p in range(npart)]
+            combiner = Combiner(task.type.typ if hasattr(task.type, "typ") else task.type,
+                                task.combiner, task.name.op, ctx=ctx)
         t_read = t_write = 0.0
         nrec = 0
+
+        def emit(f: Frame) -> None:
+            if npart > 1:
+                parts = split_by_partition(f, task.partitioner(f, npart), npart)
+                for p, g in enumerate(parts):
+                    if len(g):
+                        buf.append(p, g)
+            else:
+                buf.append(0, f)
         try:
             while True:
                 t0 = time.perf_counter()
@@ -328,32 +368,22 @@ class LocalExecutor(Executor):
                 if len(f) == 0:
                     continue
                 nrec += len(f)
-                if npart > 1:
-                    ids = task.partitioner(f, npart)
-                    parts = split_by_partition(f, ids, npart)
+                if combiner is not None:
+                    combiner.combine(f)
                 else:
-                    parts = [f]
-                for p, g in enumerate(parts):
-                    if len(g) == 0:
-                        continue
-                    if combiners is not None:
-                        combiners[p].combine(g)
-                    else:
-                        buf.append(p, g)
+                    emit(f)
                 t_write += time.perf_counter() - t1
-            if combiners is not None:
+            if combiner is not None:
                 t1 = time.perf_counter()
-                for p, c in enumerate(combiners):
-                    r = c.reader(self.device)
-                    for g in r:
-                        buf.append(p, g)
-                    r.close()
+                r = combiner.reader(self.device)
+                for g in r:
+                    emit(g)
+                r.close()
                 t_write += time.perf_counter() - t1
         finally:
             out.close()
-            if combiners is not None:
-                for c in combiners:
-                    c.discard()
+            if combiner is not None:
+                combiner.discard()
         task.stats = {"inrecords": nrec, "readDuration": int(t_read * 1e6),
                       "writeDuration": int(t_write * 1e6), "write": buf.nrows}
         return buf

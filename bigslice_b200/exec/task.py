@@ -134,8 +134,9 @@ class Task:
 
     # -- state ---------------------------------------------------------------
     def state(self) -> TaskState:
-        with self._cond:
-            return self._state
+        # a single attribute read is atomic; taking the condition's lock here made
+        # wide shuffles (consumers x producers state checks) contend on it
+        return self._state
 
     def err(self) -> Optional[BaseException]:
         with self._cond:

@@ -110,6 +110,7 @@ class MergeReader(Reader):
         self.nkeys = typ.prefix()
         self.bufs: List[FrameBuffer] = [FrameBuffer(r, i, tile) for i, r in enumerate(readers)]
         self._err: Optional[BaseException] = None
+        self._first = True
 
     def read(self, n=None):
         if self._err is not None:
@@ -120,7 +121,46 @@ class MergeReader(Reader):
             self._err = e
             raise
 
+    #: Streams are drained eagerly up to this many rows in total: a consumer of a
+    #: wide shuffle merges hundreds of streams of a few rows each, and one sort of
+    #: everything beats hundreds of incremental merge steps.
+    EAGER_ROWS = 1 << 22
+
+    def _drain_small(self) -> Optional[Frame]:
+        """If all streams together hold at most EAGER_ROWS rows, read them
+        completely and return their sorted union (the streams are then exhausted);
+        otherwise leave what was read buffered and return None."""
+        total, complete = 0, True
+        for b in self.bufs:
+            frames = [b.frame] if b.frame is not None and len(b.frame) else []
+            total += sum(len(f) for f in frames)
+            while not b.eof and total <= self.EAGER_ROWS:
+                f = b.reader.read(b.tile)
+                if f is None:
+                    b.eof = True
+                    b.reader.close()
+                    break
+                if len(f):
+                    frames.append(f)
+                    total += len(f)
+            b.frame = (frames[0] if len(frames) == 1 else concat(frames, self.typ)) if frames else None
+            complete = complete and b.eof
+        if not complete:
+            return None
+        parts = [b.frame for b in self.bufs if b.frame is not None]
+        self.bufs = []
+        if not parts:
+            return Frame.empty(self.typ)
+        out = parts[0] if len(parts) == 1 else concat(parts, self.typ)
+        return out.sorted() if len(parts) > 1 else out
+
     def _step(self) -> Optional[Frame]:
+        if self._first:
+            self._first = False
+            if len(self.bufs) > 2:
+                out = self._drain_small()
+                if out is not None:
+                    return out if len(out) else None
         live = [b for b in self.bufs if b.fill()]
         self.bufs = live
         if not live:
