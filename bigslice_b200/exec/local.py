@@ -352,9 +352,12 @@ class LocalExecutor(Executor):
         def emit(f: Frame) -> None:
             if npart > 1:
                 parts = split_by_partition(f, task.partitioner(f, npart), npart)
+                # the device partition kernel does not keep the row order inside a
+                # partition; combined output must stay sorted by key for the consumers
+                resort = combiner is not None and f.device.type == "cuda"
                 for p, g in enumerate(parts):
                     if len(g):
-                        buf.append(p, g)
+                        buf.append(p, g.sorted() if resort else g)
             else:
                 buf.append(0, f)
         try:
