@@ -41,7 +41,7 @@ from .. import context as _context
 from .. import errors, func as _func, slicefunc
 from ..frame import Frame, concat
 from ..frame import columns as C
-from ..sliceio import EmptyReader, FrameReader, MultiReader, Reader, decode_batch, encode_frame
+from ..sliceio import EmptyReader, FrameReader, MultiReader, Reader, encode_frame
 from ..slices import default_partitioner
 from .combiner import combine_frame
 from .invocation import InvocationGraph, fingerprint

@@ -131,7 +131,6 @@ def wordcount(source: str):
 def wordcount_top(source: str, n: int):
     """Reduce then keep the ``n`` most frequent keys of every shard (the
     cmd/urls top-N shape)."""
-    from ..slices import Map
     red = Reduce(_SOURCES[source], functors.add)
 
     def top(k, v):
