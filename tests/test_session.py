@@ -338,3 +338,26 @@ def test_inv_disk_cache(tmp_path):
     assert not os.path.exists(d)
     with pytest.raises(RuntimeError):
         c.get_or_create(1, create)
+
+
+@bs.Func
+def _wide_shuffle(nshard: int, phases: int):
+    s = bs.Const(nshard, torch.arange(nshard * 4), torch.ones(nshard * 4, dtype=torch.int64))
+    for _ in range(phases):
+        s = bs.Reduce(bs.Map(s, lambda k, v: (k + 1, v)), bs.ops.add)
+    return s
+
+
+def test_wide_shuffles_stay_cheap():
+    """Hundreds of shards x several shuffle phases (the reference's
+    TestMultiPhaseEval shape, with real data): per-(task, partition) overheads must
+    stay small — this took minutes before combiners ran ahead of the partitioner,
+    empty partitions stopped costing objects and tiny tasks stopped trading the GIL."""
+    import time
+    with bs.start(bs.Local, bs.Parallelism(4)) as sess:
+        t0 = time.time()
+        res = sess.run(_wide_shuffle, 200, 3)
+        rows = dict(res.rows())
+        dt = time.time() - t0
+    assert rows == {k + 3: 1 for k in range(800)}
+    assert dt < 30, "200 shards x 3 phases took %.1fs" % dt
