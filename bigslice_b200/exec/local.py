@@ -314,6 +314,7 @@ class LocalExecutor(Executor):
             and not os.environ.get("BIGSLICE_NO_START_GATE") else None)
         self.lock = threading.Lock()
         self.buffers: Dict[int, TaskBuffer] = {}
+        self._pindex: Dict[int, tuple] = {}
         self.session = None
         self.tracer = None
 
@@ -452,9 +453,16 @@ class LocalExecutor(Executor):
                 for dt, b in zip(dts, bufs):
                     if b is None:
                         raise errors.TaskLostError("output of %s is not available" % dt.name)
-                    if isinstance(b, TaskBuffer) and not b.parts[dep.partition]:
-                        continue
-                    readers.append(b.reader(dep.partition))
+                idx = self._partition_index(dts, bufs)
+                if idx is not None:
+                    # producers x consumers pairs are mostly empty: the group's output is
+                    # indexed once (partition -> producers with rows), not scanned per consumer
+                    readers = [b.reader(dep.partition) for b in idx.get(dep.partition, ())]
+                else:
+                    for b in bufs:
+                        if isinstance(b, TaskBuffer) and not b.parts[dep.partition]:
+                            continue
+                        readers.append(b.reader(dep.partition))
                 if dep.expand:
                     ins.extend(readers)
                 else:
@@ -469,6 +477,28 @@ class LocalExecutor(Executor):
             else:
                 ins.append(MultiReader(readers))
         return ins
+
+    def _partition_index(self, dts, bufs):
+        """partition -> [buffers that hold rows for it], for a wide group whose
+        outputs are all in memory; cached per group until any of its buffers is
+        replaced (a recomputed task gets a new buffer object)."""
+        if not all(isinstance(b, TaskBuffer) for b in bufs):
+            return None
+        key = id(dts[0])
+        stamp = hash(tuple(map(id, bufs)))
+        with self.lock:
+            hit = self._pindex.get(key)
+            if hit is not None and hit[0] == stamp and hit[1] == len(bufs):
+                return hit[2]
+        idx: Dict[int, List[TaskBuffer]] = {}
+        for b in bufs:  # producer order is kept inside every partition
+            for p in b.parts.d:
+                idx.setdefault(p, []).append(b)
+        with self.lock:
+            if len(self._pindex) > 64:
+                self._pindex.clear()
+            self._pindex[key] = (stamp, len(bufs), idx)
+        return idx
 
     def buffer_output(self, task: Task, out: Reader, ctx) -> TaskBuffer:
         """Drain the task's pipeline, partitioning (and map-side combining)
