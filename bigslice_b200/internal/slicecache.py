@@ -14,6 +14,7 @@ available in this image); the format is this framework's own codec.
 from __future__ import annotations
 
 import gzip
+import itertools
 import os
 from typing import List, Optional
 
@@ -54,11 +55,16 @@ def shard_path(prefix: str, shard: int, nshard: int) -> str:
     return "%s-%04d-of-%04d" % (prefix, shard, nshard)
 
 
+_tmp_seq = itertools.count()
+
+
 class _WritethroughReader(Reader):
     def __init__(self, reader: Reader, path: str):
         self.reader = reader
         self.path = path
-        self.tmp = "%s.tmp.%d" % (path, os.getpid())
+        # unique per writer: a task of an abandoned (failed) evaluation may still be
+        # writing this shard while its recomputation has already started
+        self.tmp = "%s.tmp.%d.%d" % (path, os.getpid(), next(_tmp_seq))
         self.fh = None
         self.enc: Optional[Encoder] = None
         self.done = False
