@@ -27,6 +27,14 @@ def lib():
         _lib = importlib.import_module("bigslice_b200._bsnative")
     except Exception:
         _lib = None
+        if not os.environ.get("BIGSLICE_NO_AUTOBUILD"):
+            try:  # a fresh checkout (the .so is not tracked): build in-tree once
+                from . import build
+                build.build_native()
+                importlib.invalidate_caches()
+                _lib = importlib.import_module("bigslice_b200._bsnative")
+            except Exception:
+                _lib = None
     return _lib
 
 

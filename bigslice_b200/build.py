@@ -33,6 +33,27 @@ def _newer(target: str, sources) -> bool:
     return any(os.path.getmtime(s) > t for s in sources)
 
 
+class _BuildLock:
+    """Serialises in-tree builds across processes (several ranks may import a
+    fresh checkout at once); the winner builds, the others find the result."""
+
+    def __init__(self, name: str):
+        self.path = os.path.join(PKG, ".build-%s.lock" % name)
+        self.fh = None
+
+    def __enter__(self):
+        import fcntl
+        self.fh = open(self.path, "w")
+        fcntl.flock(self.fh, fcntl.LOCK_EX)
+        return self
+
+    def __exit__(self, *a):
+        import fcntl
+        fcntl.flock(self.fh, fcntl.LOCK_UN)
+        self.fh.close()
+        return False
+
+
 def cuda_lib_path() -> str:
     return os.path.join(PKG, "_bscuda.so")
 
@@ -44,16 +65,21 @@ def build_cuda(force: bool = False, verbose: bool = False) -> str:
     deps = srcs + glob.glob(os.path.join(CSRC, "*.cuh"))
     if not force and not _newer(out, deps):
         return out
-    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
-    cmd = [nvcc] + NVCC_FLAGS + ["-shared", "-o", out] + srcs
-    if verbose:
-        cmd.insert(1, "-Xptxas")
-        cmd.insert(2, "-v")
-    r = subprocess.run(cmd, capture_output=True, text=True)
-    if r.returncode != 0:
-        raise RuntimeError("nvcc failed:\n%s\n%s" % (" ".join(cmd), r.stderr[-4000:]))
-    if verbose:
-        sys.stderr.write(r.stderr)
+    with _BuildLock("cuda"):
+        if not force and not _newer(out, deps):
+            return out  # another process built it while we waited
+        nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+        tmp = out + ".tmp.%d" % os.getpid()
+        cmd = [nvcc] + NVCC_FLAGS + ["-shared", "-o", tmp] + srcs
+        if verbose:
+            cmd.insert(1, "-Xptxas")
+            cmd.insert(2, "-v")
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError("nvcc failed:\n%s\n%s" % (" ".join(cmd), r.stderr[-4000:]))
+        os.replace(tmp, out)  # readers never see a half-written library
+        if verbose:
+            sys.stderr.write(r.stderr)
     return out
 
 
@@ -69,13 +95,18 @@ def build_native(force: bool = False) -> str:
     src = os.path.join(CSRC, "native.cpp")
     if not force and not _newer(out, [src]):
         return out
-    cxx = shutil.which("g++") or "g++"
-    inc = [pybind11.get_include(), sysconfig.get_paths()["include"]]
-    cmd = [cxx, "-O3", "-std=c++17", "-shared", "-fPIC", "-fvisibility=hidden"] + \
-          ["-I" + i for i in inc] + [src, "-o", out]
-    r = subprocess.run(cmd, capture_output=True, text=True)
-    if r.returncode != 0:
-        raise RuntimeError("g++ failed:\n%s\n%s" % (" ".join(cmd), r.stderr[-4000:]))
+    with _BuildLock("native"):
+        if not force and not _newer(out, [src]):
+            return out
+        cxx = shutil.which("g++") or "g++"
+        inc = [pybind11.get_include(), sysconfig.get_paths()["include"]]
+        tmp = out + ".tmp.%d" % os.getpid()
+        cmd = [cxx, "-O3", "-std=c++17", "-shared", "-fPIC", "-fvisibility=hidden"] + \
+              ["-I" + i for i in inc] + [src, "-o", tmp]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError("g++ failed:\n%s\n%s" % (" ".join(cmd), r.stderr[-4000:]))
+        os.replace(tmp, out)
     return out
 
 

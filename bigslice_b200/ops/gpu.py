@@ -42,6 +42,14 @@ def _load():
         if _lib is not None or _load_error is not None:
             return _lib
         path = lib_path()
+        if not os.path.exists(path) and not os.environ.get("BIGSLICE_CUDA_LIB"):
+            # a fresh checkout (the .so is not tracked): build in-tree once
+            try:
+                from .. import build
+                build.build_cuda()
+            except Exception as e:  # noqa: BLE001 - reported through _load_error
+                _load_error = "%s not built and the in-tree build failed: %s" % (path, e)
+                return None
         if not os.path.exists(path):
             _load_error = "%s not built (run python -m bigslice_b200.build)" % path
             return None
