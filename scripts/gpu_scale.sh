@@ -17,5 +17,7 @@ echo "bench rc=$?" >> gpurun_out/bench_n$N.err
 timeout 900 bash -c "$(declare -f run); N=$N run 29572 benchmarks/reshard_bw.py --max-mb 1024 --out gpurun_out/reshard_bw_n$N.jsonl" > gpurun_out/reshard_bw_n$N.log 2>&1
 timeout 900 bash -c "$(declare -f run); N=$N run 29573 benchmarks/cogroup_join.py --large 67108864 --small 4194304 --out gpurun_out/cogroup_n$N.json" > gpurun_out/cogroup_n$N.log 2>&1
 timeout 900 bash -c "$(declare -f run); N=$N run 29574 bench.py --gpus $N --steps 5 --warmup 3 --shuffle nccl --no-e2e" > gpurun_out/bench_n${N}_nccl.json 2> gpurun_out/bench_n${N}_nccl.err
+timeout 900 bash -c "$(declare -f run); N=$N run 29575 benchmarks/urls_topn.py --rows 134217728 --out gpurun_out/urls_topn_n$N.json" > gpurun_out/urls_topn_n$N.log 2>&1
+tail -1 gpurun_out/urls_topn_n$N.log
 tail -3 gpurun_out/bench_n$N.err; cat gpurun_out/bench_n$N.json; cat gpurun_out/bench_n${N}_nccl.json
 tail -8 gpurun_out/reshard_bw_n$N.log; tail -2 gpurun_out/cogroup_n$N.log
