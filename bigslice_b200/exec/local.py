@@ -143,6 +143,7 @@ class _StartGate:
 
     def __init__(self):
         self.expired_run = 0
+        self.waiters = 0
         self.lock = threading.Lock()      # the gate itself (released by holder or watchdog)
         self.meta = threading.Lock()      # guards holder/since
         self.holder: Optional[object] = None
@@ -154,17 +155,24 @@ class _StartGate:
     def enter(self) -> Optional[object]:
         if self.expired_run >= self.HEAVY_RUN:
             return None  # heavy phase: tasks overlap from the start (see observe())
-        if self.thread is None:
+        if not self.lock.acquire(blocking=False):
+            # contended: only now is the watchdog needed (it opens the gate once the
+            # current holder has had its slice)
+            if self.thread is None:
+                with self.meta:
+                    if self.thread is None:
+                        self.thread = threading.Thread(target=self._watch, daemon=True,
+                                                       name="bigslice-start-gate")
+                        self.thread.start()
             with self.meta:
-                if self.thread is None:
-                    self.thread = threading.Thread(target=self._watch, daemon=True,
-                                                   name="bigslice-start-gate")
-                    self.thread.start()
-        self.lock.acquire()
+                self.waiters += 1
+            self.wake.set()
+            self.lock.acquire()
+            with self.meta:
+                self.waiters -= 1
         tok = object()
         with self.meta:
             self.holder, self.since = tok, time.perf_counter()
-        self.wake.set()
         return tok
 
     def leave(self, tok: object) -> None:
@@ -184,15 +192,19 @@ class _StartGate:
             self.wake.wait()
             if self.closed:
                 return
-            time.sleep(self.SLICE_S / 2)
             with self.meta:
-                if self.holder is None:
+                if self.waiters == 0:
                     self.wake.clear()
-                elif time.perf_counter() - self.since >= self.SLICE_S:
+                    continue
+                age = time.perf_counter() - self.since if self.holder is not None else None
+                if age is not None and age >= self.SLICE_S:
                     self.holder = None        # the holder keeps running, ungated
                     self.expired_run += 1
-                    self.wake.clear()
                     self.lock.release()
+                    age = None
+            # a holder inside its slice: look again when the slice ends; otherwise the
+            # gate is changing hands, check back shortly
+            time.sleep(max(self.SLICE_S - age, 0.0002) if age is not None else 0.0005)
 
     def close(self) -> None:
         self.closed = True

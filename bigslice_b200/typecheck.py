@@ -58,17 +58,25 @@ class TypecheckError(TypeError):
 Error = TypecheckError
 
 
+_inside_cache: dict = {}
+
+
 def caller_location(skip_helpers: int = 0) -> Tuple[str, int]:
     """File and line of the innermost frame outside this package."""
     f = sys._getframe(1)
     skipped = 0
     while f is not None:
-        fn = os.path.abspath(f.f_code.co_filename)
-        inside = fn.startswith(_PKG_DIR + os.sep) and \
-            not fn.startswith(os.path.join(_PKG_DIR, "example") + os.sep) and \
-            not fn.startswith(os.path.join(_PKG_DIR, "cmd") + os.sep) and \
-            not fn.startswith(os.path.join(_PKG_DIR, "models") + os.sep)
-        helper = f.f_code in _helper_codes
+        code = f.f_code
+        inside = _inside_cache.get(code)
+        if inside is None:  # classified once per code object: this runs on every Session.run
+            fn = os.path.abspath(code.co_filename)
+            inside = fn.startswith(_PKG_DIR + os.sep) and \
+                not fn.startswith(os.path.join(_PKG_DIR, "example") + os.sep) and \
+                not fn.startswith(os.path.join(_PKG_DIR, "cmd") + os.sep) and \
+                not fn.startswith(os.path.join(_PKG_DIR, "models") + os.sep)
+            if len(_inside_cache) < 4096:
+                _inside_cache[code] = inside
+        helper = code in _helper_codes
         if not inside and not helper:
             if skipped >= skip_helpers + TestCalldepth:
                 return f.f_code.co_filename, f.f_lineno
