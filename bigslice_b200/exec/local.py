@@ -430,8 +430,10 @@ class LocalExecutor(Executor):
             except BaseException as e:  # storage trouble is not an application error
                 task.set(TaskState.LOST)
                 return
-        with self.lock:
-            self.buffers[id(task)] = buf
+        # Single dict operations are atomic under the GIL; this map is hit by every
+        # task and a Python-level lock around it turns into a convoy (a holder that
+        # loses the GIL keeps every other task waiting for a whole switch interval).
+        self.buffers[id(task)] = buf
         task.set(TaskState.OK)
 
     last_device_error: Optional[BaseException] = None
@@ -460,8 +462,8 @@ class LocalExecutor(Executor):
                 for dt in dts:
                     if dt.state() != TaskState.OK:
                         raise errors.TaskLostError("dependency %s is not available" % dt.name)
-                with self.lock:
-                    bufs = [self.buffers.get(id(dt)) for dt in dts]
+                get = self.buffers.get
+                bufs = [get(id(dt)) for dt in dts]
                 for dt, b in zip(dts, bufs):
                     if b is None:
                         raise errors.TaskLostError("output of %s is not available" % dt.name)
@@ -498,18 +500,16 @@ class LocalExecutor(Executor):
             return None
         key = id(dts[0])
         stamp = hash(tuple(map(id, bufs)))
-        with self.lock:
-            hit = self._pindex.get(key)
-            if hit is not None and hit[0] == stamp and hit[1] == len(bufs):
-                return hit[2]
+        hit = self._pindex.get(key)
+        if hit is not None and hit[0] == stamp and hit[1] == len(bufs):
+            return hit[2]
         idx: Dict[int, List[TaskBuffer]] = {}
         for b in bufs:  # producer order is kept inside every partition
             for p in b.parts.d:
                 idx.setdefault(p, []).append(b)
-        with self.lock:
-            if len(self._pindex) > 64:
-                self._pindex.clear()
-            self._pindex[key] = (stamp, len(bufs), idx)
+        if len(self._pindex) > 64:
+            self._pindex.clear()
+        self._pindex[key] = (stamp, len(bufs), idx)  # racing builders store equal indexes
         return idx
 
     def buffer_output(self, task: Task, out: Reader, ctx) -> TaskBuffer:
@@ -573,8 +573,7 @@ class LocalExecutor(Executor):
 
     # -- output access ---------------------------------------------------------
     def reader(self, task: Task, partition: int) -> Reader:
-        with self.lock:
-            buf = self.buffers.get(id(task))
+        buf = self.buffers.get(id(task))
         if buf is None:
             raise errors.TaskLostError("output of %s is not available" % task.name)
         return buf.reader(partition)
@@ -582,16 +581,14 @@ class LocalExecutor(Executor):
     def discard(self, task: Task) -> None:
         if task.combine_key:
             return  # shared-combiner tasks are not individually discardable
-        with self.lock:
-            buf = self.buffers.pop(id(task), None)
+        buf = self.buffers.pop(id(task), None)
         if isinstance(buf, _StoredBuffer):
             buf.discard()
         if task.state() == TaskState.OK:
             task.set(TaskState.LOST)
 
     def stored_bytes(self) -> int:
-        with self.lock:
-            bufs = list(self.buffers.values())
+        bufs = list(self.buffers.values())
         return sum(f.nbytes() for b in bufs for part in b.parts for f in part)
 
     Run, Reader, Discard = run, reader, discard
