@@ -327,7 +327,8 @@ def run(args, json_out):
             "data": "synthetic: Zipf(s=%.2f) keys over %d-word vocabulary, counts=1, random seed per rank"
                     % (args.zipf, args.vocab),
             "config": {"model": "Reduce-by-key wordcount (int64,int64) rows, Zipf keys",
-                       "global_rows": total_rows, "rows_per_gpu": n, "row_bytes": 16,
+                       "global_rows": total_rows, "global_batch": total_rows, "rows_per_gpu": n,
+                       "row_bytes": 16,
                        "parallelism": "dp%d (%d shard%s per GPU)" % (world, S, "" if S == 1 else "s"),
                        "shuffle": args.shuffle,
                        "l2_policy": "inputs (%.1f GB/GPU) larger than the 126 MB L2" % (n * 16 / 1e9)},
