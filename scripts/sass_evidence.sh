@@ -23,4 +23,16 @@ dump "xchg_plan_kernel" xchg_plan
 dump "xchg_wait_kernel" xchg_wait
 dump "rs_scatter_kernel" radix_scatter
 dump "table_compact_kernelIxE" table_compact_i64
+dump "hash_column_kernel" hash_column
+dump "partition_scatter_kernel" partition_scatter
+dump "gather_rows_kernel" gather_rows
+dump "xchg_table_scatter_kernelILi8" xchg_table_scatter_tiles
+dump "xchg_table_count_kernel" xchg_table_count
+dump "segreduce_kernelIxLi0" segreduce_i64_add
+dump "topk_hist_kernel" topk_hist
+dump "topk_select_kernel" topk_select
+dump "compact_" compact_indices
+dump "expand_indices_kernel" expand_indices
+dump "crc32_blocks_kernel" crc32_blocks
+dump "rs_global_hist_kernel" radix_global_hist
 ls -la profiles/sass
