@@ -361,3 +361,32 @@ def test_wide_shuffles_stay_cheap():
         dt = time.time() - t0
     assert rows == {k + 3: 1 for k in range(800)}
     assert dt < 30, "200 shards x 3 phases took %.1fs" % dt
+
+
+def test_start_gate_never_blocks_dependent_work():
+    """A task that waits for another *running* task must not be starved by the
+    start gate (tiny tasks run serialised, but only for a few milliseconds)."""
+    import time
+    started = threading.Event()
+    release = threading.Event()
+
+    def first(x):
+        started.set()
+        assert release.wait(10), "the second task never got through the gate"
+        return x
+
+    def second(x):
+        assert started.wait(10)
+        release.set()
+        return x
+
+    @bs.Func
+    def two():
+        a = bs.Map(bs.Const(1, torch.arange(4)), first, out=[bs.int64])
+        b = bs.Map(bs.Const(1, torch.arange(4)), second, out=[bs.int64])
+        return bs.Cogroup(a, b)
+
+    t0 = time.time()
+    with bs.start(bs.Local, bs.Parallelism(2)) as sess:
+        rows = sess.run(two).rows()
+    assert len(rows) == 4 and time.time() - t0 < 10
