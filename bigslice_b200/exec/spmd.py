@@ -135,7 +135,10 @@ class SpmdExecutor(LocalExecutor):
                                    % (r, "\n".join(d for d in diff if d)))
         self.registry_size = len(locs)
         if self.shuffle == "auto":
-            self.shuffle = "fused" if (self.device is not None and self.device.type == "cuda") else "object"
+            # GPUs: fused peer-memory kernels.  CPU ranks: the library all-to-all over
+            # gloo for tensor frames (every row crosses the wire once), codec-encoded
+            # frames over the control plane for anything else.
+            self.shuffle = "fused" if (self.device is not None and self.device.type == "cuda") else "gloo"
         if self.shuffle == "fused":
             from ..parallel.peer import PeerGroup
             self.peers = PeerGroup(self.ctrl_group, self.arena_bytes, self.device)
@@ -525,6 +528,9 @@ class SpmdExecutor(LocalExecutor):
         if self.shuffle in ("nccl", "fused") and tensor_only and f.device.type == "cuda" \
                 and nparts <= self.world * 64:
             return "nccl", self._shuffle_collective(f, ids, nparts)
+        if self.shuffle == "gloo" and tensor_only and f.device.type == "cpu" and self.world > 1 \
+                and dist.get_backend() == "gloo":
+            return "gloo", self._shuffle_collective(f, ids, nparts)
         return "object", self._shuffle_objects(f, ids, nparts)
 
     def _shuffle_collective(self, f: Frame, ids: torch.Tensor, nparts: int):

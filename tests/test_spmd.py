@@ -54,7 +54,8 @@ def test_spmd_cpu_gloo(world, tmp_path):
     outs = launch(world, tmp_path)
     check(outs, world)
     if world > 1:
-        assert outs[0]["modes"] == ["object"]
+        # tensor frames ride the gloo all-to-all, string/list frames the object path
+        assert set(outs[0]["modes"]) == {"gloo", "object"}
 
 
 @pytest.mark.gpu
