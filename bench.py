@@ -43,7 +43,10 @@ def parse():
     ap.add_argument("--vocab", type=int, default=1 << 24)
     ap.add_argument("--zipf", type=float, default=1.0)
     ap.add_argument("--e2e-steps", type=int, default=0, help="0 = min(steps, 5)")
-    ap.add_argument("--shuffle", default="fused")
+    ap.add_argument("--shuffle", default="fused",
+                    help="fused (peer-memory kernels) | nccl-table (same combine kernels, rows through "
+                         "the library all-to-all: the like-for-like baseline) | nccl (generic frames "
+                         "through the library path)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--seed", type=int, default=1234)
     ap.add_argument("--shards-per-gpu", type=int, default=1,

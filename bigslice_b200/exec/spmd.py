@@ -340,8 +340,10 @@ class SpmdExecutor(LocalExecutor):
             return False
         if task.partitioner is not default_partitioner:
             return False
-        if self.peers is None and not (self.world == 1 and task.num_partition == 1):
-            return False  # the table is shuffled by the peer-memory kernels only
+        if self.peers is None and not (self.world == 1 and task.num_partition == 1) \
+                and self.shuffle != "nccl-table":
+            return False  # the table is shuffled by the peer-memory kernels (or, as the
+            #               like-for-like baseline, by the library all-to-all: "nccl-table")
         from ..ops import gpu
         typ = task.type.typ
         if task.combiner.builtin not in gpu.OPS or typ.num_out() != 2 or typ.prefix() != 1:
@@ -394,6 +396,8 @@ class SpmdExecutor(LocalExecutor):
         out: Dict[int, List[Frame]] = {}
         if self.world == 1 and bad:
             raise errors.fatal("spmd: a producer of %s failed" % head.name)
+        if self.shuffle == "nccl-table" and not (self.world == 1 and nparts == 1):
+            return self._exchange_table_library(gid, head, table, nparts, bad, t0, ev0)
         if self.world == 1 and nparts == 1:
             # the local table is already the answer
             clear = gpu.RECYCLE == "clear"
@@ -447,6 +451,42 @@ class SpmdExecutor(LocalExecutor):
             for p in range(self.rank, nparts, self.world):
                 self.exchanged[(gid, p)] = [x for x in out.get(p, []) if len(x)]
         self._log_exchange(head, mode, t0, ev0)
+
+    def _exchange_table_library(self, gid: int, head: Task, table, nparts: int, bad: int, t0, ev0) -> None:
+        """Like-for-like baseline of the Reduce shuffle (``shuffle="nccl-table"``):
+        the same combine kernels on both sides, but the table is compacted and its
+        rows travel through ``all_to_all_single`` (NCCL) instead of the peer-memory
+        scatter.  Everything the fused path fuses shows up here as separate passes:
+        compaction, hashing, local partition, three library collectives."""
+        from ..ops import gpu
+        from ..parallel.peer import collective_exchange_tensors
+        typ = head.type.typ
+        if self.world > 1:
+            bad = self._vote(bad, head.name.inv_index)
+        if bad:
+            raise errors.fatal("spmd: a producer of %s failed on some rank" % head.name)
+        k, v = table.compact()
+        st = table.status.tolist()
+        gpu.table_pool().put(table, clean=False)
+        dest = gpu.hash_column(k) % nparts
+        if self.world > 1:
+            k, v, dest = collective_exchange_tensors([k, v, dest], dest % self.world, None)
+        out: Dict[int, List[Frame]] = {}
+        for p in range(self.rank, nparts, self.world):
+            sel = dest == p if nparts > self.world else None
+            pk, pv = (k[sel], v[sel]) if sel is not None else (k, v)
+            if pk.numel() == 0:
+                out[p] = []
+                continue
+            fk, fv = gpu.hash_combine(pk, pv, head.combiner.builtin, distinct_hint=pk.numel())
+            out[p] = [Frame([fk, fv], typ)]
+        if st[1]:
+            self._route_special(head, st[2], nparts, out, typ)
+        self.card_hints[self._hint_key(head)] = max(int(k.numel() * 1.15), 1 << 12)
+        with self._glock:
+            for p in range(self.rank, nparts, self.world):
+                self.exchanged[(gid, p)] = [x for x in out.get(p, []) if len(x)]
+        self._log_exchange(head, "nccl-table", t0, ev0)
 
     def _route_special(self, head: Task, bits: int, nparts: int, out, typ) -> None:
         """A row with the reserved sentinel key: all ranks contribute their
