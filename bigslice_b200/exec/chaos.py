@@ -7,6 +7,11 @@ output of tasks that already completed (spontaneous post-success loss), and can
 ``testsystem.Kill`` / ``rpc.InjectFailures`` / ``stressExecutor`` seams
 (SURVEY §4.2).  The evaluator must still drive every computation to the right
 answer by recomputing lost lineage.
+
+Reference seams: ``exec/evalstress_test.go:22-185`` (stressExecutor: random
+delays, LOST with rate <= 20 %, spontaneous post-success loss),
+``exec/chaosmonkey_test.go:22-235`` (machine kills during a Reduce),
+``exec/bigmachine_test.go:625-676`` (testsystem helpers).
 """
 from __future__ import annotations
 

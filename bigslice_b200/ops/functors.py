@@ -7,6 +7,10 @@ combine+exchange path) instead of generic segmented tree reductions.
 
 Each functor is also an ordinary vectorised python function so the same graph
 runs on the CPU executor.
+
+The reference calls the user's combiner reflectively per row
+(``exec/combiner.go:149-174``, ``sortio/reader.go:97-105``); naming the common
+associative operations is what lets the engine pick a kernel instead.
 """
 from __future__ import annotations
 

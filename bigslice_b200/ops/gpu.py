@@ -4,6 +4,13 @@ Every wrapper launches on the current torch CUDA stream and takes/returns
 torch tensors; nothing here falls back to PyTorch silently — on a machine with
 a GPU the library must load (``require()`` raises otherwise), so a passing GPU
 test always exercised the hand-written kernels.
+
+What the kernels replace in the reference: ``frame/frame.go:389-401``
++ ``frame/ops_builtin.go:143-164`` (hashing), ``exec/local.go:217-230`` (row-wise
+partition copies), ``exec/combiner.go:62-357`` + ``exec/bigmachine.go:1144-1209``
+(combining frame / map-side combine), ``sortio/sort.go:52`` (in-memory sort),
+``slice.go:700-720`` (filter compaction), ``sortio/reader.go:88-127`` (merge-reduce),
+``exec/topn.go:39-57`` (top-n).
 """
 from __future__ import annotations
 

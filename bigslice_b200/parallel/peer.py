@@ -12,6 +12,12 @@ plan to learn the received row counts.
 NCCL (or gloo on CPU) all-to-all of the same data is available as
 :func:`collective_exchange` — the measured baseline, and the path for columns
 the kernel does not handle (strings, lists, objects).
+
+Takes the place of the reference's pull-based shuffle transport: ``Worker.Read``
+streams dialled per producer machine (``exec/bigmachine.go:857-1005``,
+``:1306-1319``) with retry/reopen semantics (``:1351-1393``); here rows are pushed
+once, from inside the partition kernel, and failures surface as an error on every
+rank (bounded spins, abort flags, the vote carried with the counts).
 """
 from __future__ import annotations
 

@@ -6,6 +6,10 @@ socket allocates its pinned staging buffers there (first touch) and every
 host->device copy crosses the socket interconnect — at 8 ranks that halves the
 aggregate H2D rate.  ``bind_to_gpu`` pins the calling process to the CPUs NVML
 reports as local to the GPU *before* any pinned memory is allocated.
+
+(The reference's resource model is machines x procs, ``exec/slicemachine.go:
+26-817``; inside one box the analogous placement decision is which socket a
+rank's host threads and staging buffers live on.)
 """
 from __future__ import annotations
 
