@@ -48,6 +48,9 @@ def parse():
                          "the library all-to-all: the like-for-like baseline) | nccl (generic frames "
                          "through the library path)")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-baseline", action="store_true", help="skip the library (NCCL / torch) arm")
+    ap.add_argument("--no-proxy", action="store_true", help="skip the CPU Local-executor proxy")
+    ap.add_argument("--baseline-steps", type=int, default=3)
     ap.add_argument("--seed", type=int, default=1234)
     ap.add_argument("--shards-per-gpu", type=int, default=1,
                     help="split every GPU's rows into this many shards (tasks); >1 also exercises "
@@ -173,6 +176,109 @@ def make_sampler(index: int):
         return ClockSampler(index)
 
 
+def perkey_check(res, keys, world, rank, S, dev):
+    """Exact per-key comparison of one step's result with a reference made of
+    library pieces only (see the call site)."""
+    import torch
+    import torch.distributed as dist
+    from bigslice_b200.frame import hashing
+    nparts = S * world
+    uk, cnt = torch.unique(keys, return_counts=True)
+    dest = (hashing.hash_tensor(uk, 0) % nparts) % world          # pure-torch murmur3
+    order = torch.sort(dest, stable=True)[1]
+    uk, cnt, dest = uk[order], cnt[order], dest[order]
+    send = torch.bincount(dest, minlength=world)
+    recv = torch.empty_like(send)
+    if world > 1:
+        dist.all_to_all_single(recv, send)
+    else:
+        recv = send.clone()
+    rk = torch.empty(int(recv.sum()), dtype=uk.dtype, device=dev)
+    rc = torch.empty(int(recv.sum()), dtype=cnt.dtype, device=dev)
+    if world > 1:
+        dist.all_to_all_single(rk, uk, recv.tolist(), send.tolist())
+        dist.all_to_all_single(rc, cnt, recv.tolist(), send.tolist())
+    else:
+        rk, rc = uk, cnt
+    wk, inv = torch.unique(rk, return_inverse=True)
+    wc_ = torch.zeros(wk.numel(), dtype=torch.int64, device=dev).index_add_(0, inv, rc)
+    f = res.to_frame()
+    gk, gc = f.col(0), f.col(1)
+    o = torch.sort(gk)[1]
+    ok = gk.numel() == wk.numel() and torch.equal(gk[o], wk) and torch.equal(gc[o], wc_)
+    res.discard()
+    t = torch.tensor([1 if ok else 0], device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MIN)
+    return bool(int(t[0]))
+
+
+def library_baseline(args, keys, vals, world, rank, dev, dist):
+    """The same Reduce step built from library calls only, device-timed the same
+    way.  N>1: the framework's own combine kernels with the rows shuffled by NCCL
+    ``all_to_all_single`` (what `--shuffle nccl-table` runs: compaction, hashing,
+    local partition, three collectives, combine on arrival).  N=1 (no shuffle):
+    ``torch.unique(return_inverse) + index_add_`` (CUB radix sort underneath)."""
+    import torch
+    from bigslice_b200.ops import gpu
+    from bigslice_b200.parallel.peer import collective_exchange_tensors
+    n = keys.numel()
+
+    def one():
+        if world == 1:
+            uk, inv = torch.unique(keys, return_inverse=True)
+            return uk, torch.zeros(uk.numel(), dtype=vals.dtype, device=dev).index_add_(0, inv, vals)
+        k, v = gpu.hash_combine(keys, vals, "add", distinct_hint=1 << 24)
+        dest = gpu.hash_column(k) % world
+        k, v, _ = collective_exchange_tensors([k, v, dest], dest, None)
+        return gpu.hash_combine(k, v, "add", distinct_hint=k.numel())
+    for _ in range(2):
+        one()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    dist.barrier()
+    torch.cuda.synchronize()
+    ev0.record()
+    for _ in range(args.baseline_steps):
+        one()
+    ev1.record()
+    torch.cuda.synchronize()
+    dist.barrier()
+    ms = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=dev)
+    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms = float(ms[0]) / args.baseline_steps
+    what = ("torch.unique(return_inverse)+index_add_ (CUB sort) on one GPU" if world == 1 else
+            "hash_combine kernels + NCCL all_to_all_single shuffle of the combined rows (nccl-table)")
+    return {"value": n * world / (ms / 1e3), "unit": "rows/s", "ms_per_step": ms,
+            "steps": args.baseline_steps, "what": what}
+
+
+def cpu_proxy(args, rows=1 << 21):
+    """NOT the reference: the repo's own CPU `Local` executor (C++ host combiner,
+    8 shards) on a 2^21-row sample of the same distribution — a labelled CPU
+    anchor, as BASELINE.md section 2 permits when the Go reference cannot run."""
+    import time as _t
+    import torch
+    import bigslice_b200 as bs
+    from bigslice_b200.models import wordcount as wc
+    try:
+        k = wc.zipf_keys(rows, args.vocab, args.zipf, seed=99)
+        v = torch.ones(rows, dtype=torch.int64)
+        nsh = 8
+
+        @bs.Func
+        def job():
+            return bs.Reduce(bs.Const(nsh, k, v), bs.ops.add)
+        with bs.start(bs.Local, bs.Parallelism(8)) as sess:
+            sess.run(job).discard()
+            t0 = _t.perf_counter()
+            sess.run(job).discard()
+            dt = _t.perf_counter() - t0
+        return {"rows": rows, "rows_per_s": rows / dt, "seconds": dt,
+                "what": "bigslice_b200 Local executor on CPU (8 shards, 8 procs), labelled proxy - not the Go reference"}
+    except Exception as e:  # the proxy must never break the benchmark
+        return {"error": str(e)[:200]}
+
+
 def reference_arm(args):
     why = ("grailbio/bigslice is a pure-Go module: no setup.py/pyproject.toml for pip to install "
            "(pip: 'not installable'), no Go toolchain or module cache in this image, no network")
@@ -236,12 +342,33 @@ def run(args, json_out):
         return res
 
     def summarize(res):
-        """Device->host read of the step's result: distinct keys, total count."""
+        """Distinct keys and total count of the step's result (device-side sums,
+        two scalars read back): used by the warm-up checks."""
         d, t = 0, 0
         for f in res.frames():
             d += len(f)
             t += int(f.col(1).sum().item())
         return d, t
+
+    host_out = {}
+
+    def fetch(res):
+        """End-to-end read of the step's result: every result frame is copied
+        device->host into pinned buffers (the call a user makes to consume the
+        counts).  Returns (distinct keys, total count, bytes copied)."""
+        d, t, nbytes = 0, 0, 0
+        for i, f in enumerate(res.frames()):
+            n = len(f)
+            for c, col in enumerate(f.cols()):
+                key = (i, c)
+                hb = host_out.get(key)
+                if hb is None or hb.numel() < n:
+                    hb = host_out[key] = torch.empty(max(n, 1) * 5 // 4, dtype=col.dtype).pin_memory()
+                hb[:n].copy_(col, non_blocking=True)
+                nbytes += n * col.element_size()
+            d += n
+        torch.cuda.current_stream().synchronize()  # the rows are on the host now
+        return d, t, nbytes
 
     def barrier():
         torch.cuda.synchronize()
@@ -257,7 +384,7 @@ def run(args, json_out):
         for _ in range(steps):
             res = step(source)
             if with_d2h:
-                last = summarize(res)
+                last = fetch(res)
             res.discard()
         ev1.record()
         barrier()
@@ -274,6 +401,12 @@ def run(args, json_out):
     tot = torch.tensor([chk[1]], dtype=torch.int64, device=dev)
     dist.all_reduce(tot)
     assert int(tot[0]) == n * world, "wordcount lost rows: %d != %d" % (int(tot[0]), n * world)
+    # Per-key correctness at every N: the result must equal, key by key, an
+    # independent reference built from library pieces only — torch.unique of the
+    # rank-local rows, the framework-independent murmur3 placement (pure torch),
+    # an NCCL all_to_all of the per-rank partials and a second torch.unique.
+    perkey_ok = perkey_check(step("rows_hbm"), keys, world, rank, S, dev)
+    assert perkey_ok, "per-key check failed on rank %d" % rank
     sampler = make_sampler(torch.cuda.current_device())
     if rank == 0:
         sampler.start()
@@ -317,15 +450,29 @@ def run(args, json_out):
         src.h2d_bytes = 0
         ms2, _, last = timed("rows_pinned", ksteps, True)
         e2e = {"value": total_rows * ksteps / (ms2 / 1e3), "unit": "rows/s",
-               "h2d_bytes_per_step": src.h2d_bytes // ksteps, "d2h_bytes_per_step": 8 * 2,
+               "h2d_bytes_per_step": src.h2d_bytes // ksteps, "d2h_bytes_per_step": last[2],
+               "d2h": "every result frame (keys + counts) copied to pinned host memory each step",
                "steps": ksteps, "ms_per_step": ms2 / ksteps, "distinct_keys_rank0": last[0]}
+
+    # ---- library baseline: same job, shuffle through NCCL (--shuffle nccl-table) ----
+    lib_base = None
+    if args.shuffle == "fused" and not args.no_baseline:
+        lib_base = library_baseline(args, keys, vals, world, rank, dev, dist)
+    proxy = cpu_proxy(args) if (rank == 0 and not args.no_proxy) else None
 
     if rank == 0:
         out = {
             "metric": "rows/sec (whole box, device-timed, max over ranks) for Reduce-by-key wordcount",
             "value": value, "unit": "rows/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": (value / lib_base["value"]) if lib_base else None,
+            "baseline_def": ("BASELINE.md publishes no number and the Go reference cannot be built here; "
+                             "vs_baseline = value / the library arm below (same rows, same step, measured in "
+                             "this process): " + (lib_base["what"] if lib_base else "n/a")),
+            "library_baseline": lib_base,
+            "proxy_cpu_local": proxy,
+            "perkey_check": "passed (torch.unique + NCCL all_to_all reference, every key and count)",
             "dtype": "int64 keys/values (non-neural workload; no reduced precision)",
             "data": "synthetic: Zipf(s=%.2f) keys over %d-word vocabulary, counts=1, random seed per rank"
                     % (args.zipf, args.vocab),
@@ -339,6 +486,7 @@ def run(args, json_out):
             "clocks": clocks,
             "e2e": e2e,
             "exchange_modes": sorted(set(e["mode"] for e in ex.exchange_log)),
+            "graphs": dict(ex.rx.stats) if getattr(ex, "rx", None) is not None else None,
         }
         json_out.write(json.dumps(out) + "\n")
         json_out.flush()

@@ -255,10 +255,15 @@ class Session:
         if begin is not None:
             with span("run/begin_invocation"):
                 begin(tasks)
+        failed = True
         try:
             with span("run/evaluate"):
                 evaluate(self.executor, tasks, group, pool=self._eval_pool())
+            failed = False
         finally:
+            end = getattr(self.executor, "end_invocation", None)
+            if end is not None:
+                end(tasks, failed)
             log.debug("invocation %d (%s) evaluated in %.3fs", inv.index, location, time.time() - t0)
             if group is not None:
                 for st in status_tasks:

@@ -20,10 +20,21 @@ in a canonical order (producer groups sorted by graph depth, then name), which
 is identical on all ranks; tasks themselves still run under the normal
 evaluator with ``parallelism`` local procs.
 
+The Reduce fast path is *asynchronous*: producers hash-aggregate into an HBM
+table, the collective thread enqueues one CUDA graph (table scatter over NVLink,
+combine on arrival, compaction; ``parallel/rx.py``) on the exchange stream and
+hands the consumers :class:`~bigslice_b200.frame.deferred.DeferredFrame`s whose
+row counts are read from pinned memory only when somebody needs them.  The
+per-exchange agreement between ranks (producer status, invocation fingerprint)
+is a shared-memory status board (``utils/shmboard.py``), not a collective.
+
 This executor takes the place of the reference's cluster executor
 (``exec/bigmachine.go``, ``exec/slicemachine.go``): the "machines" are the GPUs
-of one NVSwitch box.  Like the reference's machine-combiner mode it does not
-recover lost tasks: a failure on any rank aborts the invocation everywhere.
+of one NVSwitch box.  Failure model: a *fatal* producer error on any rank fails
+the invocation on every rank; anything else — a producer that failed
+transiently, a table or landing-region overflow, a peer that timed out — marks
+the exchange *lost*: its producers are re-run and the exchange is repeated
+(``exec/bigmachine.go:441-454``), up to the evaluator's consecutive-loss limit.
 """
 from __future__ import annotations
 
@@ -76,14 +87,20 @@ def init_process_group(device: Optional[str] = None) -> None:
         # threads + pinned staging buffers stay on the GPU's NUMA node
         from ..utils import topology
         topology.bind_to_gpu(torch.cuda.current_device())
-        dist.init_process_group("nccl", device_id=torch.device("cuda", torch.cuda.current_device()))
+        if os.environ.get("BIGSLICE_DIST_BACKEND") == "gloo":
+            # several ranks may share one device (tests on a single-GPU box): NCCL
+            # refuses duplicate devices, the bootstrap needs nothing but gloo
+            dist.init_process_group("gloo")
+        else:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", torch.cuda.current_device()))
     else:
         dist.init_process_group("gloo")
 
 
 class SpmdExecutor(LocalExecutor):
     def __init__(self, parallelism: int = 1, device: Optional[str] = "auto",
-                 shuffle: str = "auto", arena_bytes: int = 1 << 30, zero_copy: bool = False):
+                 shuffle: str = "auto", arena_bytes: int = 1 << 30, zero_copy: bool = False,
+                 exchange_timeout: float = 30.0):
         if device == "auto":
             device = "cuda" if torch.cuda.is_available() else None
         if device == "cuda":
@@ -107,7 +124,17 @@ class SpmdExecutor(LocalExecutor):
         self._glock = threading.Lock()
         self.exchange_log: List[dict] = []
         self.group_tables: Dict[int, Any] = {}       # gid -> streaming HashTable
-        self.card_hints: Dict[str, int] = {}         # slice name -> distinct keys seen
+        self.card_hints: Dict[tuple, int] = {}       # stable slice key -> cardinality seen last time
+        self.rx = None                               # ReduceExchange (lazily created, collective)
+        self.board = None                            # shared-memory status board (world > 1)
+        self.xseq = 0                                # exchanges posted on the board
+        self.exchange_timeout = float(os.environ.get('BIGSLICE_EXCHANGE_TIMEOUT', exchange_timeout))
+        self._want_arena = 0                         # landing overflow seen: grow before the next exchange
+        self._rx_reset = False                       # a peer timed out: re-establish epochs first
+        self._lost_groups: set = set()
+        self._cancels: Dict[int, threading.Event] = {}
+        self.group_cancel: Dict[int, threading.Event] = {}
+        self.fault_hook = None                       # tests: called as hook(stage, group_name)
 
     def name(self) -> str:
         return "spmd"
@@ -142,14 +169,29 @@ class SpmdExecutor(LocalExecutor):
         if self.shuffle == "fused":
             from ..parallel.peer import PeerGroup
             self.peers = PeerGroup(self.ctrl_group, self.arena_bytes, self.device)
+        if self.world > 1:
+            from ..utils.shmboard import Board
+            name = "bigslice-board-%s-%d" % (os.environ.get("MASTER_PORT", "0"), session.index)
+            if self.rank == 0:
+                self.board = Board(name, self.world, 0, create=True)
+            dist.barrier(group=self.ctrl_group)
+            if self.rank != 0:
+                self.board = Board(name, self.world, self.rank, create=False)
+            dist.barrier(group=self.ctrl_group)
 
         def shutdown():
             if self._coll_thread is not None:
                 self._coll_q.put(None)
                 self._coll_thread.join(timeout=5)
                 self._coll_thread = None
+            if self.rx is not None:
+                self.rx.close()
+                self.rx = None
             if self.peers is not None:
                 self.peers.close()
+            if self.board is not None:
+                self.board.close(unlink=self.rank == 0)
+                self.board = None
         return shutdown
 
     def check_registry(self) -> None:
@@ -209,9 +251,7 @@ class SpmdExecutor(LocalExecutor):
                                % (where, self.rank))
         return int(flag[0])
 
-    def begin_invocation(self, roots: Sequence[Task]) -> None:
-        """Start the collective thread that performs this invocation's group
-        exchanges in canonical order."""
+    def _group_depths(self, roots: Sequence[Task]):
         groups: Dict[int, List[Task]] = {}
         depth: Dict[int, int] = {}
 
@@ -236,15 +276,35 @@ class SpmdExecutor(LocalExecutor):
                 if gid not in groups:
                     groups[gid] = t.group
                     depth[gid] = max(task_depth(x, memo) for x in t.group)
+        return groups, depth
+
+    def begin_invocation(self, roots: Sequence[Task]) -> None:
+        """Queue this invocation's group exchanges, in canonical order, for the
+        collective thread."""
+        groups, depth = self._group_depths(roots)
+        cancel = threading.Event()
         todo = []
         with self._glock:
+            self._cancels[id(roots[0]) if roots else 0] = cancel
             for gid, g in groups.items():
                 if gid not in self.group_done:
                     self.group_done[gid] = threading.Event()
+                    self.group_cancel[gid] = cancel
                     todo.append((depth[gid], str(g[0].name), gid, g))
         todo.sort(key=lambda x: (x[0], x[1]))
-        if not todo:
-            return
+        if todo:
+            self._submit(todo)
+
+    def end_invocation(self, roots: Sequence[Task], failed: bool) -> None:
+        """Called by the session when ``evaluate`` returns or raises: a failed
+        evaluation releases the collective thread from producers that will never
+        be submitted (it still takes part in the vote, with a bad status)."""
+        with self._glock:
+            cancel = self._cancels.pop(id(roots[0]) if roots else 0, None)
+        if failed and cancel is not None:
+            cancel.set()
+
+    def _submit(self, todo) -> None:
         # One long-lived collective thread serves every invocation, in submission
         # order: exchanges of different invocations never interleave differently
         # on different ranks, and no thread is created per run.
@@ -255,6 +315,20 @@ class SpmdExecutor(LocalExecutor):
                                                      name="bigslice-spmd-collective")
                 self._coll_thread.start()
         self._coll_q.put(todo)
+
+    def _ensure_group(self, task: Task) -> None:
+        """A producer of a group whose exchange is not (or no longer) scheduled is
+        being run: the group was lost and is re-evaluated.  Every rank runs every
+        task of the graph (tasks of other ranks as no-ops), so all ranks queue the
+        repeated exchange at the same point of their sequence."""
+        gid = id(task.group[0])
+        with self._glock:
+            if gid in self.group_done:
+                return
+            self.group_done[gid] = threading.Event()
+            self.group_err.pop(gid, None)
+            self.group_cancel[gid] = threading.Event()
+        self._submit([(0, str(task.group[0].name), gid, task.group)])
 
     # -- the collective thread ---------------------------------------------------
     def _collective_main(self) -> None:
@@ -267,44 +341,49 @@ class SpmdExecutor(LocalExecutor):
             self._collective_loop(todo)
 
     def _collective_loop(self, todo) -> None:
-        failed: Optional[BaseException] = None
         for _, _, gid, group in todo:
-            ev = self.group_done[gid]
-            if failed is None:
-                try:
-                    self._exchange_group(gid, group)
-                except BaseException as e:  # noqa: BLE001
-                    failed = e
-            if failed is not None:
-                self.group_err[gid] = failed
-            ev.set()
+            ev = self.group_done.get(gid)
+            try:
+                self._exchange_group(gid, group)
+            except BaseException as e:  # noqa: BLE001
+                # every rank still takes part in the later exchanges of this
+                # invocation (with whatever status its producers reach): skipping
+                # them here would leave the peers waiting
+                self.group_err[gid] = e
+            if ev is not None:
+                ev.set()
 
-    def _local_status(self, group: List[Task]) -> int:
-        """Wait for this rank's producers; 0 ok, 1 failed."""
+    def _local_status(self, gid: int, group: List[Task]) -> int:
+        """Wait for this rank's producers: 0 all OK; 1 one failed for good (ERR)
+        or the evaluation was abandoned.  LOST producers are being retried by the
+        evaluator — keep waiting for them."""
+        cancel = self.group_cancel.get(gid)
         for t in group:
             if not self.owns(t):
                 continue
-            st = t.wait_state(TaskState.OK)
-            if st != TaskState.OK:
-                return 1
+            while True:
+                st = t.wait_state(TaskState.OK, timeout=0.05)
+                if st == TaskState.OK:
+                    break
+                if st == TaskState.ERR:
+                    return 1
+                if cancel is not None and cancel.is_set():
+                    return 1
         return 0
 
     def _exchange_group(self, gid: int, group: List[Task]) -> None:
         with span("xchg/wait_producers"):
-            bad = self._local_status(group)
+            bad = self._local_status(gid, group)
         head = group[0]
         nparts = head.num_partition
         typ = head.type.typ
+        if self.fault_hook is not None:
+            self.fault_hook("before_exchange", str(head.name))
         with self._glock:
             table = self.group_tables.pop(gid, None)
         # The table path is a static property of the task (same answer on every
         # rank, also on ranks whose shards were empty or whose producers failed).
-        if self._table_path_ok(head) and (table is not None or self.world > 1):
-            if table is None:
-                from ..ops import gpu
-                table = gpu.table_pool().get(1024, head.type.typ.out(1).torch_dtype,
-                                             head.combiner.builtin, self.device)
-                table.track(nparts)
+        if self._table_path_ok(head):
             with span("xchg/table_total"):
                 return self._exchange_table(gid, head, table, nparts, bad)
         if self.world > 1:
@@ -340,37 +419,50 @@ class SpmdExecutor(LocalExecutor):
             return False
         if task.partitioner is not default_partitioner:
             return False
-        if self.peers is None and not (self.world == 1 and task.num_partition == 1) \
-                and self.shuffle != "nccl-table":
-            return False  # the table is shuffled by the peer-memory kernels (or, as the
-            #               like-for-like baseline, by the library all-to-all: "nccl-table")
+        if self.shuffle not in ("fused", "nccl-table"):
+            return False
         from ..ops import gpu
+        from ..parallel import rx
         typ = task.type.typ
         if task.combiner.builtin not in gpu.OPS or typ.num_out() != 2 or typ.prefix() != 1:
             return False
         return (typ.out(0).torch_dtype == torch.int64 and typ.out(0).kind == "int"
                 and typ.out(1).torch_dtype in gpu.VTYPE and typ.out(1).kind != "vec"
-                and task.num_partition <= 256)
+                and task.num_partition <= rx.MAXP)
 
-    def _hint_key(self, task: Task) -> str:
-        return "%s/%s" % (task.type.name(), task.combiner.builtin)
+    def _hint_key(self, task: Task, what: str = "local") -> tuple:
+        """Cardinality hints are keyed on the slice's *creation site* — not on its
+        name, whose per-site index changes with every ``Session.run`` (each run
+        re-executes the Func body) — plus the combiner and the shard count."""
+        nm = task.type.name()
+        return (getattr(nm, "op", str(nm)), getattr(nm, "file", ""), getattr(nm, "line", 0),
+                task.combiner.builtin, task.num_partition, what)
 
     def _group_table(self, task: Task, rows_hint: int):
-        """The (per rank, per producer group) HBM table all local producer
-        tasks aggregate into; sized from the cardinality seen last time."""
+        """The (per rank, per producer group) HBM table all local producer tasks
+        aggregate into: sized from the cardinality seen last time, else for the
+        worst case (every row of every local producer a distinct key)."""
         from ..ops import gpu
         gid = id(task.group[0])
         with self._glock:
             t = self.group_tables.get(gid)
             if t is None:
                 hint = self.card_hints.get(self._hint_key(task))
-                cap = gpu.table_capacity(hint) if hint is not None else 2 * max(rows_hint, 1 << 16)
+                if hint is not None:
+                    cap = gpu.table_capacity(int(hint * 1.15) + 1024)
+                else:
+                    rows = 0
+                    for g in task.group:
+                        if not self.owns(g):
+                            continue
+                        src = g.slices[-1] if getattr(g, "slices", None) else None
+                        rh = getattr(src, "rows_hint", None)
+                        rows += int(rh(g.name.shard)) if rh is not None else max(rows_hint, 1)
+                    cap = gpu.table_capacity(max(rows, rows_hint, 1 << 15))
                 # pooled: a table emptied by its last reader (clearing exchange or
                 # compaction) is reused without an init pass
                 t = gpu.table_pool().get(cap, task.type.typ.out(1).torch_dtype, task.combiner.builtin,
                                          self.device)
-                if not (self.world == 1 and task.num_partition == 1):
-                    t.track(task.num_partition)  # destinations counted while combining
                 self.group_tables[gid] = t
             return t
 
@@ -387,70 +479,209 @@ class SpmdExecutor(LocalExecutor):
             acc = (acc * 1000003 + fp) & ((1 << 61) - 1)
         return acc, fps
 
+    def _rx(self):
+        """The Reduce exchange state (created collectively on first use: every
+        rank takes the table path for the same groups)."""
+        if self.rx is None:
+            from ..parallel.rx import ReduceExchange
+            self.rx = ReduceExchange(self.ctrl_group if self.world > 1 else None,
+                                     self.arena_bytes if self.world > 1 else 1 << 20, self.device,
+                                     timeout_s=self.exchange_timeout)
+        return self.rx
+
+    def _board_vote(self, bad: int, acc: int, fps, head: Task) -> None:
+        """Host-side agreement for one exchange: post my status + fingerprint and
+        read everyone else's from shared memory (no collective, no GPU)."""
+        if self.board is None:
+            if bad:
+                raise errors.fatal("spmd: a producer of %s failed" % head.name)
+            return
+        self.xseq += 1
+        self.board.post(self.xseq, int(bad), acc)
+        with span("xchg/board_vote"):
+            votes = self.board.wait_all(self.xseq, self.exchange_timeout)
+        if votes is None:
+            self._rx_reset = True
+            raise errors.TaskLostError("spmd: rank(s) %s did not reach the exchange of %s within %.0f s"
+                                       % (self.board.missing(self.xseq), head.name, self.exchange_timeout))
+        if any(v[0] for v in votes):
+            raise errors.fatal("spmd: a producer of %s failed on some rank" % head.name)
+        if any(v[1] != acc for v in votes):
+            where = ", ".join("inv%d at %s (func #%d)" % f[:3] for f in fps) or "an earlier invocation"
+            raise errors.fatal("ranks issued different invocations (%s, rank %d); SPMD programs must "
+                               "run identical Session.run sequences" % (where, self.rank))
+
     def _exchange_table(self, gid: int, head: Task, table, nparts: int, bad: int = 0) -> None:
+        from ..frame.deferred import DeferredFrame
         from ..ops import gpu
-        from ..parallel.peer import ExchangeVoteError
         typ = head.type.typ
+        vdtype, op = typ.out(1).torch_dtype, head.combiner.builtin
         t0 = time.perf_counter()
         ev0 = self._cuda_event()
-        out: Dict[int, List[Frame]] = {}
-        if self.world == 1 and bad:
-            raise errors.fatal("spmd: a producer of %s failed" % head.name)
         if self.shuffle == "nccl-table" and not (self.world == 1 and nparts == 1):
+            if table is None:
+                table = gpu.table_pool().get(1024, vdtype, op, self.device)
             return self._exchange_table_library(gid, head, table, nparts, bad, t0, ev0)
+        rx = self._rx()
+        rx.harvest()
+        lkey = self._hint_key(head)
+        out: Dict[int, List[Frame]] = {}
         if self.world == 1 and nparts == 1:
-            # the local table is already the answer
-            clear = gpu.RECYCLE == "clear"
-            k, v = table.compact(clear=clear)
-            gpu.table_pool().put(table, clean=clear)
-            out[0] = [Frame([k, v], typ)]
-            sent = len(k)
+            # the local table is already the answer: asynchronous compaction, the row
+            # count goes to pinned memory (no host synchronisation)
+            if bad:
+                raise errors.fatal("spmd: a producer of %s failed" % head.name)
+            if table is None:
+                out[0] = []
+            else:
+                hint = self.card_hints.get(lkey)
+                cap = min(table.total + 1, int(hint * 1.25) + 4096) if hint is not None else table.total + 1
+                ok = torch.empty(cap, dtype=torch.int64, device=self.device)
+                ov = torch.empty(cap, dtype=vdtype, device=self.device)
+                table.compact_into(ok, ov, clear=True)
+
+                def learned(rep, key=lkey):
+                    if rep.error == 0:
+                        self.card_hints[key] = max(int(rep.out_rows[0]), 1 << 10)
+                    else:
+                        self.card_hints[key] = 4 * max(self.card_hints.get(key, 0), int(rep.out_rows[0]), 1 << 14)
+                pend = rx.publish(table.status, cap, on_report=learned)
+                gpu.table_pool().put(table, clean=True)
+                out[0] = [DeferredFrame([ok, ov], typ, self._resolver(pend, gid, head, 0))]
             mode = "table-local"
         else:
-            # the producer status and the invocation fingerprint travel with the
-            # counts: all ranks agree on device, without a host collective
+            if self._rx_reset or self._want_arena:
+                # a lost exchange left epochs or the arena in doubt: start over (collective)
+                with span("xchg/reset"):
+                    rx.reset(max(self._want_arena, rx.arena_bytes))
+                self._rx_reset, self._want_arena = False, 0
+            if self.world == 1 and rx.arena_bytes < self.arena_bytes:
+                rx.reset(self.arena_bytes)  # single rank: the arena is allocated on first use
+            if table is None:  # this rank had no rows: an empty table still takes part
+                table = gpu.table_pool().get(1024, vdtype, op, self.device)
             acc, fps = self._take_fingerprint(head.name.inv_index)
-            try:
-                with span("xchg/exchange_table"):
-                    got = self.peers.exchange_table(table, nparts, clear=gpu.RECYCLE == "clear",
-                                                    vote=(1 if bad else 0, acc))
-            except ExchangeVoteError as e:
-                if e.kind == 3:
-                    raise errors.fatal("spmd: a producer of %s failed on some rank" % head.name) from e
-                where = ", ".join("inv%d at %s (func #%d)" % f[:3] for f in fps) or "an earlier invocation"
-                raise errors.fatal("ranks issued different invocations (%s, rank %d); SPMD programs must "
-                                   "run identical Session.run sequences" % (where, self.rank)) from e
-            with span("xchg/status_sync"):
-                st = table.status.tolist()
-            if st[0]:
-                self.card_hints[self._hint_key(head)] = 4 * max(self.card_hints.get(self._hint_key(head), 0), 1 << 16)
-                raise errors.fatal("spmd: combine table overflow (%d rows): the number of distinct keys "
-                                   "more than doubled since the last run of this slice; the estimate has "
-                                   "been raised, re-run the invocation" % st[0])
-            gpu.table_pool().put(table, clean=gpu.RECYCLE == "clear")
-            sent = 0
-            for p, (rk, rv) in got.items():
-                sent += rk.numel()
-                if rk.numel() == 0:
-                    out[p] = []
-                    continue
-                # rows from different ranks may share keys: combine on arrival
-                dkey = self._hint_key(head) + "/dest%d" % p
-                dh = self.card_hints.get(dkey)
-                with span("xchg/dest_combine"):
-                    fk, fv = gpu.hash_combine(rk, rv, head.combiner.builtin,
-                                              distinct_hint=min(rk.numel(), dh) if dh else rk.numel())
-                self.card_hints[dkey] = max(int(fk.numel() * 1.15), 1 << 12)
-                out[p] = [Frame([fk, fv], typ)]
-            if st[1]:  # the reserved EMPTY key was present: route it on the host (rare)
-                self._route_special(head, st[2], nparts, out, typ)
+            # order the exchange stream after the producers' combine kernels
+            after = torch.cuda.Event()
+            after.record(torch.cuda.default_stream(self.device))
+            rx.stream.wait_event(after)
+            pl, region_rows = rx.geometry(nparts)
+            locals_ = [j for j in range(pl) if self.rank + j * self.world < nparts]
+            dkeys = [self._hint_key(head, "dest%d" % (self.rank + j * self.world)) for j in locals_]
+            hints = [self.card_hints.get(k) for k in dkeys]
+            pend = None
+            first_err = None
+            with torch.cuda.stream(rx.stream):
+                if all(h is not None for h in hints):
+                    dests = []
+                    for j, h in zip(locals_, hints):
+                        dt = gpu.table_pool().get(gpu.table_capacity(int(h * 1.15) + 1024), vdtype, op,
+                                                  self.device, warm=0)
+                        cap = int(h * 1.25) + 4096
+                        dests.append((j, dt, torch.empty(cap, dtype=torch.int64, device=self.device),
+                                      torch.empty(cap, dtype=vdtype, device=self.device), cap))
+                    with span("xchg/enqueue"):
+                        pend = rx.exchange(table, nparts, dests, vote=(1 if bad else 0, acc),
+                                           on_report=self._learner(head, lkey, dkeys, nparts))
+                else:
+                    # first run of this slice: one synchronisation to learn how much
+                    # arrives, then everything is sized exactly
+                    with span("xchg/first_run_sync"):
+                        probe = rx.exchange_probe(table, nparts, vote=(1 if bad else 0, acc))
+                        rep = probe.resolve()
+                    dests = []
+                    if rep.error == 0:
+                        for j in locals_:
+                            rows = int(rep.recv_rows[j])
+                            dt = gpu.table_pool().get(gpu.table_capacity(rows + 1024), vdtype, op,
+                                                      self.device, warm=0)
+                            cap = rows + 16
+                            dests.append((j, dt, torch.empty(cap, dtype=torch.int64, device=self.device),
+                                          torch.empty(cap, dtype=vdtype, device=self.device), cap))
+                    else:
+                        from ..parallel.rx import ExchangeFailed
+                        first_err = ExchangeFailed(rep.error, rep.need_rows)
+                        self._learner(head, lkey, dkeys, nparts)(rep)
+                    pend = rx.exchange_finish(table, nparts, dests,
+                                              on_report=None if first_err else
+                                              self._learner(head, lkey, dkeys, nparts))
+                done = pend.event
+            table.ready = done  # the next user's stream waits for the scatter on the device
+            gpu.table_pool().put(table, clean=True)
+            for j, dt, ok, ov, cap in dests:
+                gpu.table_pool().put(dt, clean=True)
+            if self.fault_hook is not None:
+                self.fault_hook("after_enqueue", str(head.name))
+            # host-side agreement (shared memory): a fatal producer failure on any
+            # rank fails the invocation everywhere, now, without draining the GPU
+            self._board_vote(bad, acc, fps, head)
+            if first_err is not None:
+                if first_err.retriable:
+                    raise errors.TaskLostError("spmd: exchange of %s was lost (%s)" % (head.name, first_err))
+                raise errors.fatal("spmd: exchange of %s failed: %s" % (head.name, first_err))
+            for j, dt, ok, ov, cap in dests:
+                out[self.rank + j * self.world] = [
+                    DeferredFrame([ok, ov], typ, self._resolver(pend, gid, head, j), ready_event=done)]
             mode = "fused-table"
-        self.card_hints[self._hint_key(head)] = max(int(sent * 1.15), 1 << 12) if self.world == 1 \
-            else max(int(self.peers.last_sent * 1.15), 1 << 12)
         with self._glock:
             for p in range(self.rank, nparts, self.world):
-                self.exchanged[(gid, p)] = [x for x in out.get(p, []) if len(x)]
-        self._log_exchange(head, mode, t0, ev0)
+                self.exchanged[(gid, p)] = list(out.get(p, []))
+        self._log_exchange(head, mode, t0, ev0, sync=False)
+
+    def _learner(self, head: Task, lkey, dkeys, nparts: int):
+        """Report callback: cardinalities for the next run's table/buffer sizes;
+        what a failed exchange needs to succeed next time."""
+        from ..parallel import rx as _rx
+
+        def learned(rep):
+            if rep.error == 0:
+                self.card_hints[lkey] = max(int(rep.sent_rows), 1 << 10)
+                for i, k in enumerate(dkeys):
+                    self.card_hints[k] = max(int(rep.out_rows[i]), 1 << 10)
+                return
+            if rep.error == _rx.LANDING_OVERFLOW and self.rx is not None:
+                self._want_arena = max(self._want_arena,
+                                       self.rx.bytes_for(nparts, int(rep.need_rows * 1.5) + 4096))
+            elif rep.error == _rx.TABLE_OVERFLOW:
+                self.card_hints[lkey] = 4 * max(self.card_hints.get(lkey, 0), 1 << 16)
+            elif rep.error == _rx.DEST_OVERFLOW:
+                for k in dkeys:  # next attempt takes the exactly-sized first-run path
+                    self.card_hints.pop(k, None)
+            elif rep.error == _rx.TIMEOUT:
+                self._rx_reset = True
+        return learned
+
+    def _resolver(self, pend, gid: int, head: Task, j: int):
+        """Length of a deferred result frame; a failed exchange is *lost* (its
+        producers are re-run by the evaluator) unless the verdict is fatal."""
+        from ..parallel.rx import ExchangeFailed
+
+        def resolve() -> int:
+            try:
+                return pend.rows(j)
+            except ExchangeFailed as e:
+                if e.retriable:
+                    self._mark_group_lost(gid, head)
+                    raise errors.TaskLostError("spmd: exchange of %s was lost (%s); recomputing"
+                                               % (head.name, e)) from e
+                raise errors.fatal("spmd: exchange of %s failed: %s" % (head.name, e)) from e
+        return resolve
+
+    def _mark_group_lost(self, gid: int, head: Task) -> None:
+        """The group's exchange did not deliver: forget it and mark the producers
+        LOST so that the evaluator re-runs them (and, through ``_ensure_group``,
+        the exchange)."""
+        with self._glock:
+            if gid not in self.group_done:
+                return  # already handled by another consumer
+            self.group_done.pop(gid, None)
+            self.group_err.pop(gid, None)
+            for k in [k for k in self.exchanged if k[0] == gid]:
+                del self.exchanged[k]
+        for t in head.group or [head]:
+            with self.lock:
+                self.buffers.pop(id(t), None)
+            if t.state() == TaskState.OK:
+                t.set(TaskState.LOST)
 
     def _exchange_table_library(self, gid: int, head: Task, table, nparts: int, bad: int, t0, ev0) -> None:
         """Like-for-like baseline of the Reduce shuffle (``shuffle="nccl-table"``):
@@ -480,34 +711,13 @@ class SpmdExecutor(LocalExecutor):
                 continue
             fk, fv = gpu.hash_combine(pk, pv, head.combiner.builtin, distinct_hint=pk.numel())
             out[p] = [Frame([fk, fv], typ)]
-        if st[1]:
-            self._route_special(head, st[2], nparts, out, typ)
-        self.card_hints[self._hint_key(head)] = max(int(k.numel() * 1.15), 1 << 12)
+        # (a row with the reserved EMPTY key is part of the compacted output and
+        # travels like any other row)
+        self.card_hints[self._hint_key(head)] = max(int(k.numel()), 1 << 10)
         with self._glock:
             for p in range(self.rank, nparts, self.world):
                 self.exchanged[(gid, p)] = [x for x in out.get(p, []) if len(x)]
         self._log_exchange(head, "nccl-table", t0, ev0)
-
-    def _route_special(self, head: Task, bits: int, nparts: int, out, typ) -> None:
-        """A row with the reserved sentinel key: all ranks contribute their
-        partial over the control plane and its owner adds the row."""
-        import struct
-        from ..frame import hashing
-        key = -(1 << 63)
-        vt = typ.out(1).torch_dtype
-        raw = struct.pack("<q", bits if bits < (1 << 63) else bits - (1 << 64))
-        val = torch.frombuffer(bytearray(raw), dtype=vt)[0].item()
-        vals = [None] * self.world
-        dist.all_gather_object(vals, val, group=self.ctrl_group)
-        d = int(hashing.hash64(torch.tensor([key]), 0)[0]) % nparts
-        if self.owner(d) != self.rank:
-            return
-        op = head.combiner.builtin
-        tot = vals[0]
-        for x in vals[1:]:
-            tot = tot + x if op == "add" else (min(tot, x) if op == "min" else max(tot, x))
-        out.setdefault(d, []).append(Frame([torch.tensor([key], device=self.device),
-                                            torch.tensor([tot], dtype=vt, device=self.device)], typ))
 
     def _cuda_event(self):
         if self.device is not None and self.device.type == "cuda":
@@ -516,12 +726,15 @@ class SpmdExecutor(LocalExecutor):
             return ev
         return None
 
-    def _log_exchange(self, head: Task, mode: str, t0: float, ev0, **kw) -> None:
+    def _log_exchange(self, head: Task, mode: str, t0: float, ev0, sync: bool = True, **kw) -> None:
         """Record the exchange in the log and, device-timed with CUDA events,
-        in the session trace (pid = rank, category "exchange")."""
+        in the session trace (pid = rank, category "exchange").  ``sync=False``
+        (asynchronous exchanges): host time only, nothing waits for the device."""
         rec = {"group": str(head.name), "mode": mode, "seconds": time.perf_counter() - t0}
         rec.update(kw)
-        if ev0 is not None:
+        if len(self.exchange_log) > 4096:
+            del self.exchange_log[:2048]
+        if ev0 is not None and sync:
             ev1 = torch.cuda.Event(enable_timing=True)
             ev1.record()
             ev1.synchronize()
@@ -612,14 +825,17 @@ class SpmdExecutor(LocalExecutor):
 
     # -- task execution ---------------------------------------------------------
     def run(self, task: Task) -> None:
+        if task.group is not None:
+            self._ensure_group(task)
         if not self.owns(task):
             task.set(TaskState.RUNNING)
             task.set(TaskState.OK)  # executed by its owner rank
             return
+        if self.fault_hook is not None:
+            self.fault_hook("run", str(task.name))
+        # LOST stays LOST: the evaluator re-runs the task (a transient producer
+        # failure is retried locally, before the group's exchange happens)
         super().run(task)
-        if task.state() == TaskState.LOST:
-            # no lineage recovery across ranks: surface as a fatal error
-            task.error(errors.fatal("spmd: task %s lost (no recovery in SPMD mode)" % task.name))
 
     def dep_readers(self, task: Task) -> List[Reader]:
         ins: List[Reader] = []
@@ -631,17 +847,28 @@ class SpmdExecutor(LocalExecutor):
                 ins.append(self.reader(dt, dep.partition))
                 continue
             gid = id(dep.head.group[0])
+            for dt in dep.head.group:
+                if dt.state() != TaskState.OK:
+                    raise errors.TaskLostError("dependency %s is not available" % dt.name)
             ev = self.group_done.get(gid)
             if ev is None:
-                raise errors.fatal("spmd: no exchange scheduled for %s" % dep.head.name)
+                raise errors.TaskLostError("spmd: the exchange of %s is not available" % dep.head.name)
             ev.wait()
-            if gid in self.group_err:
-                raise errors.fatal("spmd: exchange for %s failed" % dep.head.name, self.group_err[gid])
+            err = self.group_err.get(gid)
+            if err is not None:
+                if isinstance(err, errors.TaskLostError) or not errors.is_fatal(err):
+                    self._mark_group_lost(gid, dep.head)
+                    raise errors.TaskLostError("spmd: exchange for %s was lost: %s" % (dep.head.name, err))
+                raise errors.fatal("spmd: exchange for %s failed" % dep.head.name, err)
             with self._glock:
-                frames = self.exchanged.get((gid, dep.partition), [])
+                frames = self.exchanged.get((gid, dep.partition))
+            if frames is None:
+                raise errors.TaskLostError("spmd: the exchange of %s is not available" % dep.head.name)
             typ = dep.head.type.typ
             r: Reader
-            if frames:
+            if frames and all(isinstance(f, _deferred()) for f in frames):
+                r = _DeferredReader(frames)  # hands the frames over without touching their length
+            elif frames:
                 r = _TaggedReader(concat(frames, typ, self.device))
             else:
                 r = EmptyReader()
@@ -652,6 +879,8 @@ class SpmdExecutor(LocalExecutor):
 
     def buffer_output(self, task: Task, out: Reader, ctx) -> TaskBuffer:
         if task.group is None:
+            if task.num_partition <= 1 and task.combiner is None:
+                return self._buffer_passthrough(task, out)
             return super().buffer_output(task, out, ctx)
         # Shuffle producer: keep whole tiles; the group exchange partitions (and
         # combines) them in one fused pass.
@@ -668,13 +897,8 @@ class SpmdExecutor(LocalExecutor):
                 nrec += len(f)
                 if fast and len(f):
                     if table is None:
-                        hint_rows = 0
-                        src = task.slices[-1] if task.slices else None
-                        rh = getattr(src, "rows_hint", None)
-                        if rh is not None:
-                            hint_rows = int(rh(task.name.shard))
                         with span("task/group_table"):
-                            table = self._group_table(task, max(hint_rows, len(f)))
+                            table = self._group_table(task, len(f))
                     with span("task/combine_launch"):
                         table.combine(f.col(0), f.col(1))  # async: overlaps the next read
                 else:
@@ -682,6 +906,30 @@ class SpmdExecutor(LocalExecutor):
         finally:
             out.close()
         task.stats = {"inrecords": nrec, "write": nrec}
+        return buf
+
+    def _buffer_passthrough(self, task: Task, out: Reader) -> TaskBuffer:
+        """Unpartitioned output: frames are kept as they come.  Deferred frames
+        (results of an asynchronous exchange) are stored *without* asking for their
+        length, so a Reduce step runs end to end with no host synchronisation."""
+        DF = _deferred()
+        buf = TaskBuffer(1)
+        nrec, lazy = 0, False
+        try:
+            while True:
+                f = out.read(None)
+                if f is None:
+                    break
+                if isinstance(f, DF) and not f.resolved():
+                    buf.parts.add(0, f)
+                    lazy = True
+                    continue
+                if len(f):
+                    nrec += len(f)
+                    buf.append(0, f)
+        finally:
+            out.close()
+        task.stats = {"write": buf.nrows} if lazy else {"inrecords": nrec, "write": buf.nrows}
         return buf
 
     def reader(self, task: Task, partition: int) -> Reader:
@@ -702,8 +950,11 @@ class SpmdExecutor(LocalExecutor):
 
     # -- results -------------------------------------------------------------------
     def result_reader(self, result) -> Reader:
-        """Rows of the shards this rank owns, in shard order (SPMD view)."""
-        return MultiReader([self.reader(t, 0) for t in result.tasks if self.owns(t)])
+        """Rows of the shards this rank owns, in shard order (SPMD view).  A
+        result whose output (or whose exchange) was lost since the run is
+        re-evaluated when it is read, as in the reference's fault-tolerant scans
+        (``exec/bigmachine.go:1500-1513``); every rank must then read it too."""
+        return MultiReader([_ReevalReader(self, t) for t in result.tasks if self.owns(t)])
 
     def gather(self, result) -> List[tuple]:
         """All rows of ``result`` on every rank, in shard order."""
@@ -726,6 +977,80 @@ class SpmdExecutor(LocalExecutor):
         for s in sorted(merged):
             out.extend(merged[s])
         return out
+
+
+def _deferred():
+    from ..frame.deferred import DeferredFrame
+    return DeferredFrame
+
+
+class _DeferredReader(Reader):
+    """Hands deferred frames to the consumer as they are; the consumer's stream
+    waits for the producing stream on the device."""
+    combined_unique = False
+
+    def __init__(self, frames: List[Frame]):
+        self.frames = list(frames)
+        self.cur: Optional[FrameReader] = None
+
+    def read(self, n=None):
+        while True:
+            if self.cur is not None:
+                f = self.cur.read(n)
+                if f is not None:
+                    return f
+                self.cur = None
+            if not self.frames:
+                return None
+            f = self.frames.pop(0)
+            f.wait_ready()
+            if n is None:
+                return f
+            self.cur = FrameReader(f)
+
+
+class _ReevalReader(Reader):
+    """Reads a task's output; if it (or the exchange behind it) turns out to be
+    lost, the task is re-evaluated and the read starts over."""
+
+    def __init__(self, ex: "SpmdExecutor", task: Task):
+        self.ex, self.task = ex, task
+        self.frames: Optional[List[Frame]] = None
+        self.tries = 0
+
+    def _load(self) -> List[Frame]:
+        from .eval import evaluate
+        while True:
+            try:
+                if self.task.state() != TaskState.OK:
+                    evaluate(self.ex, [self.task])
+                r = self.ex.reader(self.task, 0)
+                out = []
+                for f in r:
+                    len(f)  # resolve deferred frames here, where a loss can be handled
+                    out.append(f)
+                r.close()
+                return out
+            except errors.TaskLostError:
+                self.tries += 1
+                if self.tries > 5:
+                    raise
+                if self.task.state() == TaskState.OK:
+                    self.task.set(TaskState.LOST)
+
+    def read(self, n=None):
+        if self.frames is None:
+            self.frames = self._load()
+            self.cur = None
+        while True:
+            if self.cur is not None:
+                f = self.cur.read(n)
+                if f is not None:
+                    return f
+                self.cur = None
+            if not self.frames:
+                return None
+            self.cur = FrameReader(self.frames.pop(0))
 
 
 def _decode_one(b: bytes, typ, device) -> Frame:

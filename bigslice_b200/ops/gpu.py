@@ -283,12 +283,21 @@ class HashTable:
         _chk(_lib.bs_table_compact(_ptr(self.slots), c_ll(self.total), c_int(VTYPE[self.vdtype]),
                                    _ptr(ok), _ptr(ov), _ptr(self.status), c_int(1 if clear else 0),
                                    ctypes.c_ulonglong(self.identity_bits() if clear else 0),
-                                   _stream()), "table_compact")
+                                   c_ll(cap_out), _stream()), "table_compact")
         st = self.status.tolist()
         if st[0]:
             raise TableFull(st[0])
         n = st[3]
         return ok[:n], ov[:n]
+
+    def compact_into(self, out_keys: torch.Tensor, out_vals: torch.Tensor, clear: bool = True) -> None:
+        """Asynchronous compaction into caller-provided buffers (rows beyond their
+        capacity are dropped; ``status.out_count`` still reports the rows needed).
+        No host synchronisation: pair with ``ReduceExchange.publish``."""
+        _chk(_lib.bs_table_compact(_ptr(self.slots), c_ll(self.total), c_int(VTYPE[self.vdtype]),
+                                   _ptr(out_keys), _ptr(out_vals), _ptr(self.status), c_int(1 if clear else 0),
+                                   ctypes.c_ulonglong(self.identity_bits() if clear else 0),
+                                   c_ll(out_keys.numel()), _stream()), "table_compact")
 
     def failed(self) -> int:
         return int(self.status[0])

@@ -1,0 +1,75 @@
+"""Host control plane of the SPMD executor: a shared-memory status board.
+
+All ranks of an SPMD session live on one NVSwitch box, so the per-exchange
+agreement ("did every rank's producers succeed, did every rank issue the same
+invocation?") does not need a collective: every rank *posts* ``(seq, status,
+fingerprint)`` into its row of a small ``/dev/shm`` file and polls the other
+rows.  A post is a handful of plain stores; a wait is a spin of a few
+microseconds when the ranks are in step — no GPU involvement, no gloo round
+trip (0.3-0.5 ms in round 1), and the device pipeline keeps running.
+
+A rank that dies stops posting: the others time out and classify the exchange
+as *lost* (``errors.TaskLostError``), the analogue of the reference's
+keepalive-driven machine loss (``exec/slicemachine.go:148-227``).
+"""
+from __future__ import annotations
+
+import mmap
+import os
+import time
+from typing import List, Optional, Tuple
+
+import numpy as np
+
+RING = 8
+FIELDS = 4  # seq, status, fingerprint, extra
+
+
+class Board:
+    def __init__(self, name: str, world: int, rank: int, create: bool):
+        self.world, self.rank = world, rank
+        self.path = os.path.join("/dev/shm" if os.path.isdir("/dev/shm") else "/tmp", name)
+        nbytes = world * RING * FIELDS * 8
+        if create:
+            with open(self.path + ".tmp", "wb") as fh:
+                fh.write(b"\0" * nbytes)
+            os.replace(self.path + ".tmp", self.path)
+        self.fh = open(self.path, "r+b")
+        self.mm = mmap.mmap(self.fh.fileno(), nbytes)
+        self.a = np.frombuffer(self.mm, dtype=np.int64).reshape(world, RING, FIELDS)
+
+    def post(self, seq: int, status: int, fp: int, extra: int = 0) -> None:
+        row = self.a[self.rank, seq % RING]
+        row[1], row[2], row[3] = status, fp, extra
+        row[0] = seq  # last: readers poll the sequence number (x86 keeps store order)
+
+    def wait_all(self, seq: int, timeout_s: float = 30.0) -> Optional[List[Tuple[int, int, int]]]:
+        """(status, fingerprint, extra) of every rank for exchange ``seq``;
+        ``None`` if some rank did not post within ``timeout_s``."""
+        col = self.a[:, seq % RING, 0]
+        t0 = time.perf_counter()
+        spins = 0
+        while not bool((col >= seq).all()):
+            spins += 1
+            if spins > 200:
+                if time.perf_counter() - t0 > timeout_s:
+                    return None
+                time.sleep(0.00005)
+        slot = self.a[:, seq % RING]
+        return [(int(slot[r, 1]), int(slot[r, 2]), int(slot[r, 3])) for r in range(self.world)]
+
+    def missing(self, seq: int) -> List[int]:
+        return [r for r in range(self.world) if int(self.a[r, seq % RING, 0]) < seq]
+
+    def close(self, unlink: bool = False) -> None:
+        try:
+            del self.a
+            self.mm.close()
+            self.fh.close()
+        except Exception:
+            pass
+        if unlink:
+            try:
+                os.unlink(self.path)
+            except OSError:
+                pass

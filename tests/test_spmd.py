@@ -21,9 +21,10 @@ def free_port():
     return p
 
 
-def launch(nproc, tmp_path, device="cpu", shuffle="auto", timeout=600):
+def launch(nproc, tmp_path, device="cpu", shuffle="auto", timeout=600, extra_env=None):
     out = str(tmp_path / "out.json")
     env = dict(os.environ, BS_TEST_OUT=out, BS_TEST_DEVICE=device, BS_TEST_SHUFFLE=shuffle)
+    env.update(extra_env or {})
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1",
            "--nproc-per-node=%d" % nproc, "--master-addr", "127.0.0.1",
            "--master-port", str(free_port()), os.path.join(HERE, "spmd_worker.py")]
@@ -41,7 +42,8 @@ def check(outs, world):
                   "reshard_placement_ok", "failure_ok"):
             assert o[k], (k, o)
     for o in outs:
-        for k in ("exchange_content_ok", "table_exchange_ok", "exchange_vote_ok", "bigcount_ok"):
+        for k in ("exchange_content_ok", "table_exchange_ok", "exchange_vote_ok", "bigcount_ok",
+                  "sentinel_ok", "distinct_ok", "hints_ok", "overflow_recovered_ok", "recovery_ok"):
             if k in o:
                 assert o[k], (k, o["rank"])
     if world > 1:
@@ -73,3 +75,15 @@ def test_spmd_two_gpus(shuffle, tmp_path):
     outs = launch(2, tmp_path, device="cuda", shuffle=shuffle)
     check(outs, 2)
     assert shuffle in outs[0]["modes"]
+
+
+@pytest.mark.gpu
+def test_spmd_two_ranks_sharing_one_gpu(tmp_path):
+    """Two ranks on ONE device (gloo bootstrap, CUDA IPC between the processes):
+    the whole multi-rank protocol — peer stores, flags, acknowledgements, the
+    shared-memory vote, loss recovery — is exercised on a single-GPU box."""
+    outs = launch(2, tmp_path, device="cuda", shuffle="fused", timeout=900,
+                  extra_env={"BIGSLICE_DIST_BACKEND": "gloo", "BIGSLICE_SHARE_GPU": "1"})
+    check(outs, 2)
+    assert "fused-table" in outs[0]["modes"]
+    assert outs[0]["sentinel_ok"] and outs[0]["distinct_ok"] and outs[0]["overflow_recovered_ok"]
