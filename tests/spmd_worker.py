@@ -255,10 +255,10 @@ def flaky_count(nshard: int):
     def once(k, v):
         if FLAKY["left"] > 0 and bool((k == 0).any()):
             FLAKY["left"] -= 1
-            raise OSError("transient: connection reset by peer")
+            raise bs.errors.Error("transient: connection reset by peer", bs.errors.Kind.Net)
         return k, v
-    return bs.Reduce(bs.Map(bs.Const(nshard, keys, torch.ones(64 * nshard, dtype=torch.int64)), once),
-                     bs.ops.add)
+    return bs.Reduce(bs.Map(bs.Const(nshard, keys, torch.ones(64 * nshard, dtype=torch.int64)), once,
+                            out=[bs.int64, bs.int64]), bs.ops.add)
 
 
 def recovery_check(sess, ex, world, rank):
