@@ -381,12 +381,17 @@ def run(args, json_out):
         l0 = gpu.launches()
         ev0.record()
         last = None
+        host = []
         for _ in range(steps):
+            h0 = time.perf_counter()
             res = step(source)
             if with_d2h:
                 last = fetch(res)
             res.discard()
+            host.append((time.perf_counter() - h0) * 1e3)
         ev1.record()
+        if os.environ.get("BIGSLICE_SPANS") and rank == 0:
+            sys.stderr.write("host ms per step (rank 0, %s): %s\n" % (source, " ".join("%.2f" % h for h in host)))
         barrier()
         ms = ev0.elapsed_time(ev1)
         t = torch.tensor([ms], dtype=torch.float64, device=dev)

@@ -133,6 +133,8 @@ class SpmdExecutor(LocalExecutor):
         self._rx_reset = False                       # a peer timed out: re-establish epochs first
         self._lost_groups: set = set()
         self._cancels: Dict[int, threading.Event] = {}
+        self._dest_tables: Dict[tuple, Any] = {}     # (hint key, capacity) -> destination table
+        self._out_sets: Dict[tuple, list] = {}       # hint key -> [(keys, vals, weakref to the frame)]
         self.group_cancel: Dict[int, threading.Event] = {}
         self.fault_hook = None                       # tests: called as hook(stage, group_name)
 
@@ -570,15 +572,24 @@ class SpmdExecutor(LocalExecutor):
             hints = [self.card_hints.get(k) for k in dkeys]
             pend = None
             first_err = None
+            first_run = not all(h is not None for h in hints)
             with torch.cuda.stream(rx.stream):
                 if all(h is not None for h in hints):
                     dests = []
-                    for j, h in zip(locals_, hints):
-                        dt = gpu.table_pool().get(gpu.table_capacity(int(h * 1.15) + 1024), vdtype, op,
-                                                  self.device, warm=0)
-                        cap = int(h * 1.25) + 4096
-                        dests.append((j, dt, torch.empty(cap, dtype=torch.int64, device=self.device),
-                                      torch.empty(cap, dtype=vdtype, device=self.device), cap))
+                    for j, h, dk in zip(locals_, hints, dkeys):
+                        # The destination table and the output buffers are tied to the
+                        # slice (not pooled): the same pointers every step, so the
+                        # captured graph is replayed instead of re-recorded.
+                        dcap = gpu.table_capacity(int(h * 1.15) + 1024)
+                        dt = self._dest_tables.get((dk, dcap, vdtype, op))
+                        if dt is None:
+                            for k in [k for k in self._dest_tables if k[0] == dk]:
+                                del self._dest_tables[k]
+                            dt = self._dest_tables[(dk, dcap, vdtype, op)] = gpu.HashTable(
+                                dcap, vdtype, op, self.device, warm=0)
+                        cap = gpu.quantise_capacity(int(h * 1.25) + 4096)
+                        ok, ov = self._out_buffers(dk, cap, vdtype)
+                        dests.append((j, dt, ok, ov, cap))
                     with span("xchg/enqueue"):
                         pend = rx.exchange(table, nparts, dests, vote=(1 if bad else 0, acc),
                                            on_report=self._learner(head, lkey, dkeys, nparts))
@@ -607,8 +618,9 @@ class SpmdExecutor(LocalExecutor):
                 done = pend.event
             table.ready = done  # the next user's stream waits for the scatter on the device
             gpu.table_pool().put(table, clean=True)
-            for j, dt, ok, ov, cap in dests:
-                gpu.table_pool().put(dt, clean=True)
+            if first_run:
+                for j, dt, ok, ov, cap in dests:
+                    gpu.table_pool().put(dt, clean=True)
             if self.fault_hook is not None:
                 self.fault_hook("after_enqueue", str(head.name))
             # host-side agreement (shared memory): a fatal producer failure on any
@@ -618,14 +630,37 @@ class SpmdExecutor(LocalExecutor):
                 if first_err.retriable:
                     raise errors.TaskLostError("spmd: exchange of %s was lost (%s)" % (head.name, first_err))
                 raise errors.fatal("spmd: exchange of %s failed: %s" % (head.name, first_err))
-            for j, dt, ok, ov, cap in dests:
-                out[self.rank + j * self.world] = [
-                    DeferredFrame([ok, ov], typ, self._resolver(pend, gid, head, j), ready_event=done)]
+            import weakref
+            for (j, dt, ok, ov, cap), dk in zip(dests, dkeys):
+                fr = DeferredFrame([ok, ov], typ, self._resolver(pend, gid, head, j), ready_event=done)
+                if not first_run:
+                    for ent in self._out_sets.get(dk, ()):
+                        if ent[0] is ok:
+                            ent[2] = weakref.ref(fr)
+                out[self.rank + j * self.world] = [fr]
             mode = "fused-table"
         with self._glock:
             for p in range(self.rank, nparts, self.world):
                 self.exchanged[(gid, p)] = list(out.get(p, []))
         self._log_exchange(head, mode, t0, ev0, sync=False)
+
+    def _out_buffers(self, dk: tuple, cap: int, vdtype):
+        """Output buffers of a destination shard: the first set whose previous
+        result frame is gone (discarded / garbage collected) is reused, so a
+        run-discard loop sees the same pointers every step.  Reuse is ordered on the
+        device: the exchange stream waits for everything queued on the default
+        stream (the consumers of the earlier result) before it writes."""
+        sets = self._out_sets.setdefault(dk, [])
+        for ent in sets:
+            if ent[0].numel() == cap and ent[1].dtype == vdtype and (ent[2] is None or ent[2]() is None):
+                ent[2] = None
+                return ent[0], ent[1]
+        if len(sets) >= 8:  # results are being kept: stop tracking old sets
+            sets[:] = [e for e in sets if e[2] is not None and e[2]() is not None][-4:]
+        ok = torch.empty(cap, dtype=torch.int64, device=self.device)
+        ov = torch.empty(cap, dtype=vdtype, device=self.device)
+        sets.append([ok, ov, None])
+        return ok, ov
 
     def _learner(self, head: Task, lkey, dkeys, nparts: int):
         """Report callback: cardinalities for the next run's table/buffer sizes;
