@@ -425,12 +425,11 @@ class SpmdExecutor(LocalExecutor):
             return False
         from ..ops import gpu
         from ..parallel import rx
-        typ = task.type.typ
-        if task.combiner.builtin not in gpu.OPS or typ.num_out() != 2 or typ.prefix() != 1:
+        # the planner decided the shape (exec/compile.py: _table_lowering); the
+        # executor adds what depends on the device library
+        if task.lowering != "reduce-table":
             return False
-        return (typ.out(0).torch_dtype == torch.int64 and typ.out(0).kind == "int"
-                and typ.out(1).torch_dtype in gpu.VTYPE and typ.out(1).kind != "vec"
-                and task.num_partition <= rx.MAXP)
+        return task.type.typ.out(1).torch_dtype in gpu.VTYPE and task.num_partition <= rx.MAXP
 
     def _hint_key(self, task: Task, what: str = "local") -> tuple:
         """Cardinality hints are keyed on the slice's *creation site* — not on its

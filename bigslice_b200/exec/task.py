@@ -96,6 +96,10 @@ class TaskSubscriber:
 class Task:
     """One shard of a pipelined group of slice operations."""
 
+    #: how the planner lowered this task's output exchange ("frames",
+    #: "reduce-table"); see exec/compile.py
+    lowering = "frames"
+
     def __init__(self, typ: Slice, name: TaskName, invocation=None,
                  do: Optional[Callable] = None, deps: Optional[List[TaskDep]] = None,
                  partitioner=None, num_partition: int = 1, combiner=None,

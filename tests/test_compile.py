@@ -137,3 +137,26 @@ def test_compile_env_writable_vs_frozen(tmp_path):
     t3 = compile_slice(fresh, bs.Reduce(bs.Prefixed(bs.Map(build(), lambda x: (x, x)), 1), ADD))
     prod = t3[0].deps[0].head
     assert fresh.env.is_cached(prod.name, 1) and prod.deps == []
+
+
+def test_plan_ir_and_lowering():
+    """The planner's IR: stages, edges and the lowering chosen for each exchange."""
+    from bigslice_b200.exec.compile import Planner
+    inv = ExecInvocation(Invocation(1, 0, (), False, "<unknown>"))
+
+    def build():
+        s = bs.Map(bs.Const(3, *ints("i", "i")), lambda a, b: (a, b), out=[bs.int64, bs.int64])
+        red = bs.Reduce(s, ADD)                                   # int64 key, int64 value, builtin add
+        return bs.Cogroup(red, bs.Reshard(bs.Const(3, *ints("i", "f")), 3))
+    plan = Planner(inv).plan(build())
+    text = plan.describe()
+    assert "reduce-table" in text and "frames" in text
+    by_name = {s.op_name: s for s in plan.stages}
+    prod = by_name["inv1_const_map"]
+    assert prod.exchange is not None and prod.exchange.lowering == "reduce-table"
+    assert [e.wide for e in by_name["inv1_reduce"].inputs] == [True]
+    assert len(plan.root.inputs) == 2 and all(e.wide for e in plan.root.inputs)
+    tasks = compile_slice(ExecInvocation(Invocation(1, 0, (), False, "<unknown>")), build())
+    lows = {t.name.op: t.lowering for t in tasks[0].all() if t.group is not None}
+    assert lows["inv1_const_map"] == "reduce-table"
+    assert lows["inv1_reduce"] == "frames" and lows["inv1_const"] == "frames"
