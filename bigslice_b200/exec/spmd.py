@@ -347,11 +347,15 @@ class SpmdExecutor(LocalExecutor):
             ev = self.group_done.get(gid)
             try:
                 self._exchange_group(gid, group)
-            except BaseException as e:  # noqa: BLE001
+            except errors.Error as e:
                 # every rank still takes part in the later exchanges of this
                 # invocation (with whatever status its producers reach): skipping
                 # them here would leave the peers waiting
                 self.group_err[gid] = e
+            except BaseException as e:  # noqa: BLE001 - a bug or a CUDA failure, not a lost task
+                import traceback
+                self.group_err[gid] = errors.fatal("spmd: exchange of %s raised %s: %s\n%s" % (
+                    group[0].name, type(e).__name__, e, traceback.format_exc()), e)
             if ev is not None:
                 ev.set()
 

@@ -24,7 +24,7 @@ from .frame import Frame
 class DeferredFrame(Frame):
     """A :class:`Frame` over capacity buffers with a lazily known length."""
 
-    __slots__ = ("_n", "_resolve", "ready_event")
+    __slots__ = ("_n", "_resolve", "ready_event", "__weakref__")
 
     def __init__(self, data: Sequence, typ: Type, resolve: Callable[[], int], ready_event=None):
         # Frame.__init__ is bypassed: it would need the length
