@@ -70,9 +70,14 @@ class PinnedRows(Slice):
     """Source slice over per-shard columns in *pinned host memory*.
 
     Every evaluation copies the shard host->device in ``chunk_rows`` pieces on a
-    dedicated copy stream with two device buffers in flight, so the H2D copy of
-    chunk i+1 overlaps the consumer's kernels on chunk i (the consumer waits on
-    a CUDA event, never on the host)."""
+    dedicated copy stream into a small ring of persistent device staging buffers:
+    the H2D copy of chunk i+1 overlaps the consumer's kernels on chunk i, nothing
+    is allocated per step, and the consumer waits on CUDA events, never on the
+    host.  A staging buffer is reused once the consumer's work on it has been
+    *enqueued* and finished (an event recorded on the consumer's stream when it
+    asks for the next chunk)."""
+
+    RING = 3
 
     def __init__(self, shards: List[Tuple[torch.Tensor, ...]], typ: Type = ROW_TYPE,
                  chunk_rows: int = 1 << 24):
@@ -80,32 +85,58 @@ class PinnedRows(Slice):
         self.shards = shards
         self.chunk_rows = chunk_rows
         self.h2d_bytes = 0
+        self._state = {}   # (shard, device) -> [copy stream, staging buffers, consumed events]
 
     def rows_hint(self, shard: int) -> int:
         return int(self.shards[shard][0].shape[0])
+
+    def _staging(self, shard: int, dev, cols):
+        key = (shard, str(dev))
+        st = self._state.get(key)
+        if st is None:
+            stream = torch.cuda.Stream(device=dev)
+            bufs = [[torch.empty((self.chunk_rows,) + tuple(c.shape[1:]), dtype=c.dtype, device=dev)
+                     for c in cols] for _ in range(self.RING)]
+            st = self._state[key] = [stream, bufs, [None] * self.RING, 0]
+        return st
 
     def reader(self, shard, deps):
         cols = self.shards[shard]
         n = int(cols[0].shape[0]) if cols else 0
         pos = [0]
         dev = _context.current_device()
-        copy_stream = torch.cuda.Stream(device=dev) if dev is not None and dev.type == "cuda" else None
+        on_gpu = dev is not None and dev.type == "cuda" and n > 0
+        st = self._staging(shard, dev, cols) if on_gpu else None
+        last_slot = [None]
 
         def read(k):
+            if on_gpu and last_slot[0] is not None:
+                # the consumer's kernels on the previous chunk are enqueued by now
+                ev = torch.cuda.Event()
+                ev.record(torch.cuda.current_stream(dev))
+                st[2][last_slot[0]] = ev
+                last_slot[0] = None
             if pos[0] >= n:
                 return None
-            j = min(n, pos[0] + (k or self.chunk_rows))
-            if copy_stream is None:
+            j = min(n, pos[0] + min(k or self.chunk_rows, self.chunk_rows))
+            if not on_gpu:
                 out = [c[pos[0]:j] for c in cols]
             else:
-                with torch.cuda.stream(copy_stream):
-                    out = [c[pos[0]:j].to(dev, non_blocking=True) for c in cols]
+                stream, bufs, consumed, turn = st
+                slot = turn % self.RING
+                st[3] = turn + 1
+                with torch.cuda.stream(stream):
+                    if consumed[slot] is not None:
+                        stream.wait_event(consumed[slot])
+                    out = []
+                    for c, b in zip(cols, bufs[slot]):
+                        d = b[:j - pos[0]]
+                        d.copy_(c[pos[0]:j], non_blocking=True)
+                        out.append(d)
                     ev = torch.cuda.Event()
-                    ev.record(copy_stream)
-                cur = torch.cuda.current_stream(dev)
-                cur.wait_event(ev)
-                for t in out:
-                    t.record_stream(cur)
+                    ev.record(stream)
+                torch.cuda.current_stream(dev).wait_event(ev)
+                last_slot[0] = slot
             self.h2d_bytes += sum(t.numel() * t.element_size() for t in out)
             pos[0] = j
             return Frame(out, self.typ)
