@@ -27,7 +27,7 @@ from .sliceio import EOF, Reader, Scanner
 from .slices import (Const, Dep, Exclusive, ExperimentalMaterialize, Filter, Flatmap,
                      Fold, HashShard, Head, Helper, Map, Name, Pragma, Pragmas,
                      Prefixed, Procs, RangeShard, ReaderFunc, ReaderGen, Scan, Slice,
-                     String, Unwrap, WriterFunc, helper, make_name, MakeName, MapExpr, FilterExpr)
+                     String, Unwrap, WriterFunc, helper, make_name, MakeName, MapExpr, FilterExpr, FoldExpr)
 from .reduce import Reduce
 from .cogroup import Cogroup
 from .reshuffle import Repartition, Reshard, Reshuffle

@@ -216,6 +216,89 @@ def run_fused(cols: Sequence[torch.Tensor], in_types: Sequence[DType], stages: S
 
 
 # ---------------------------------------------------------------------------
+# ordered per-key folds: ``acc = expr(acc, c1, ..., cn)`` in row order
+
+def generate_fold(acc_type: DType, val_types: Sequence[DType], expr: str) -> str:
+    """CUDA source of the segmented fold kernel: rows are sorted by key (stable),
+    ``seg[s] .. seg[s+1]`` delimits key ``s``; one thread folds one key's rows in
+    order, starting from the zero accumulator.  Arbitrary (non-associative)
+    expressions are allowed, so a key's rows are inherently sequential — the
+    parallelism is across keys."""
+    check_types([acc_type] + list(val_types))
+    A = CTYPE[acc_type.name]
+    names = {0: None}
+
+    def rep(m):
+        k = int(m.group(1))
+        if k == 0 or k > len(val_types):
+            raise ValueError("fold expression may use acc and c1..c%d (c0 is the key), not c%d"
+                             % (len(val_types), k))
+        return "v%d" % k
+    body = _VAR.sub(rep, expr)
+    loads = "\n".join("      const %s v%d = in%d[i];" % (CTYPE[t.name], j + 1, j + 1)
+                      for j, t in enumerate(val_types))
+    params = ["long long nseg", "const long long* __restrict__ seg"]
+    params += ["const %s* __restrict__ in%d" % (CTYPE[t.name], j + 1) for j, t in enumerate(val_types)]
+    params.append("%s* __restrict__ out" % A)
+    return ("extern \"C\" __global__ void __launch_bounds__(128) bs_fused(%s) {\n"
+            "  for (long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x; s < nseg;\n"
+            "       s += (long long)gridDim.x * blockDim.x) {\n"
+            "    %s acc = (%s)0;\n"
+            "    const long long hi = seg[s + 1];\n"
+            "    for (long long i = seg[s]; i < hi; ++i) {\n%s\n"
+            "      acc = (%s)(%s);\n"
+            "    }\n"
+            "    out[s] = acc;\n  }\n}\n" % (", ".join(params), A, A, loads, A, body))
+
+
+def run_fold(acc_type: DType, val_cols: Sequence[torch.Tensor], val_types: Sequence[DType],
+             seg_offsets: torch.Tensor, expr: str) -> torch.Tensor:
+    """Launch the fold kernel over sorted device columns; one output per segment."""
+    global launch_count
+    fn = _function(generate_fold(acc_type, val_types, expr))
+    nseg = int(seg_offsets.numel()) - 1
+    dev = val_cols[0].device
+    out = torch.empty(max(nseg, 0), dtype=acc_type.torch_dtype, device=dev)
+    if nseg <= 0:
+        return out
+    cols = [c.contiguous() for c in val_cols]
+    seg = seg_offsets.to(device=dev, dtype=torch.int64).contiguous()
+    args = [ctypes.c_longlong(nseg), ctypes.c_void_p(seg.data_ptr())] + \
+           [ctypes.c_void_p(c.data_ptr()) for c in cols] + [ctypes.c_void_p(out.data_ptr())]
+    argv = (ctypes.c_void_p * len(args))(*[ctypes.cast(ctypes.pointer(a), ctypes.c_void_p) for a in args])
+    sms = torch.cuda.get_device_properties(dev).multi_processor_count
+    blocks = min((nseg + 127) // 128, sms * 16)
+    rc = _driver().cuLaunchKernel(fn, blocks, 1, 1, 128, 1, 1, 0,
+                                  ctypes.c_void_p(torch.cuda.current_stream().cuda_stream), argv, None)
+    if rc != 0:
+        raise RuntimeError("cuLaunchKernel failed: %d" % rc)
+    launch_count += 1
+    return out
+
+
+def fold_host(acc_type: DType, val_cols: Sequence[torch.Tensor], seg_offsets: torch.Tensor,
+              expr: str) -> torch.Tensor:
+    """The same fold with torch ops under C semantics: round ``r`` folds the r-th
+    row of every key at once (CPU executors and the reference for the kernel)."""
+    nseg = int(seg_offsets.numel()) - 1
+    dev = val_cols[0].device if val_cols else None
+    acc = torch.zeros(max(nseg, 0), dtype=acc_type.torch_dtype, device=dev)
+    if nseg <= 0:
+        return acc
+    off = seg_offsets.to(dev)
+    lens = off[1:] - off[:-1]
+    rewritten = re.sub(r"\bacc\b", "c0", expr)
+    for r in range(int(lens.max())):
+        live = torch.nonzero(lens > r).flatten()
+        rows = off[:-1][live] + r
+        v = eval_expr(rewritten, [acc[live]] + [c[rows] for c in val_cols])
+        if v.is_floating_point() and not acc.dtype.is_floating_point:
+            v = torch.trunc(v)
+        acc[live] = v.to(acc.dtype)
+    return acc
+
+
+# ---------------------------------------------------------------------------
 # host evaluation with C semantics: a small expression parser (C precedence,
 # casts, && || ! ?:, truncating integer / and %) evaluated with torch ops.
 

@@ -715,11 +715,67 @@ def Flatmap(slice_: Slice, fn: Callable, *pragmas, out=None) -> Slice:
 # Fold
 
 
+#: A vectorised python fold is applied in rounds (round r = the r-th row of every
+#: key); beyond this many rounds — one key owning that many rows — it refuses and
+#: points at the builtin functors / ``FoldExpr``, which have device kernels.
+MAX_FOLD_ROUNDS = 4096
+
+
 class _Fold(Slice):
-    def __init__(self, s, func, typ, pragmas):
+    def __init__(self, s, func, typ, pragmas, expr: Optional[str] = None):
         super().__init__(make_name("fold"), typ, s.num_shard(), [Dep(s, shuffle=True)], pragmas)
         self.func = func
+        self.expr = expr
         self.in_typ = s.typ
+
+    def _fold_frame(self, f: Frame) -> Frame:
+        """Fold one materialised shard.  Three tiers:
+        builtin functor (add/min/max) on a device frame -> the hash-aggregation
+        kernels (no sort at all); expression -> stable sort + the NVRTC segmented
+        fold kernel; python callable -> sort + vectorised rounds / per-row loop."""
+        acc_t = self.typ.out(1)
+        dev = f.device
+        name = self.func.builtin if self.func is not None else None
+        vals = f.cols()[1:]
+        if (name in ("add", "min", "max") and len(vals) == 1 and dev.type == "cuda"
+                and isinstance(vals[0], torch.Tensor) and vals[0].dim() == 1
+                and vals[0].dtype == acc_t.torch_dtype):
+            from .ops import gpu
+            k = f.col(0)
+            if gpu.available() and isinstance(k, torch.Tensor) and k.dtype == torch.int64 \
+                    and vals[0].dtype in gpu.VTYPE:
+                uk, acc = gpu.hash_combine(k, vals[0], name)
+                if name == "min":      # the accumulator starts at zero
+                    acc = torch.clamp(acc, max=0)
+                elif name == "max":
+                    acc = torch.clamp(acc, min=0)
+                order = Frame([uk], Type([self.typ.out(0)], 1)).sort_indices()
+                return Frame([uk[order], acc[order]], self.typ)
+        f = f.prefixed(1).sorted()   # stable: per-key row order is preserved
+        starts = group_starts(f, 1)
+        idx = torch.nonzero(starts).flatten()
+        keys = C.col_take(f.col(0), idx)
+        vals = f.cols()[1:]
+        if self.expr is not None:
+            from .ops import jit
+            off = torch.cat([idx.to(torch.int64), torch.tensor([len(f)], dtype=torch.int64, device=idx.device)])
+            vt = list(self.in_typ.cols[1:])
+            if dev.type == "cuda":
+                acc = jit.run_fold(acc_t, vals, vt, off, self.expr)
+            else:
+                acc = jit.fold_host(acc_t, vals, off, self.expr)
+            return Frame([keys, acc], self.typ)
+        if not self.func.rowwise and isinstance(vals[0], torch.Tensor) and len(idx):
+            seglen = torch.diff(torch.cat([idx, torch.tensor([len(f)], device=idx.device)]))
+            longest = int(seglen.max())
+            if longest > MAX_FOLD_ROUNDS and self.func.builtin not in ("add",):
+                raise errors.fatal(
+                    "fold: one key has %d rows; a python fold function is applied in one vectorised "
+                    "round per row position (limit %d).  Use a builtin functor (ops.add/min/max) or "
+                    "FoldExpr(slice, \"<C expression of acc, c1..>\"), which run as device kernels"
+                    % (longest, MAX_FOLD_ROUNDS))
+        acc = segmented_fold(acc_t, vals, starts, self.func, _context.current())
+        return Frame([keys, acc], self.typ)
 
     def reader(self, shard, deps):
         src = deps[0]
@@ -729,18 +785,11 @@ class _Fold(Slice):
             if done[0]:
                 return None
             done[0] = True
-            # Fold materialises the shard: sort by key (stable, so per-key row
-            # order is preserved) then one segmented, ordered fold.
+            # Fold materialises the shard (reference slice.go:918-933).
             f = read_all(src, self.in_typ, _context.current_device())
             if len(f) == 0:
                 return None
-            f = f.prefixed(1).sorted()
-            starts = group_starts(f, 1)
-            acc = segmented_fold(self.typ.out(1), f.cols()[1:], starts, self.func,
-                                 _context.current())
-            idx = torch.nonzero(starts).flatten()
-            keys = C.col_take(f.col(0), idx)
-            return Frame([keys, acc], self.typ)
+            return self._fold_frame(f)
 
         from .sliceio import Rebatch
         return Rebatch(FuncReader(read, src.close))
@@ -781,6 +830,29 @@ def Fold(slice_: Slice, fold: Callable, *pragmas, acc=None) -> Slice:
             func.In.cols, Type([acc_t] + list(slice_.typ.cols[1:])), func.is_variadic):
         typecheck.panicf("fold: expected func(acc, t2, t3, ..., tn), got %s", _fn_name(fold))
     return _Fold(slice_, func, Type([key, acc_t], 1), pragmas)
+
+
+def FoldExpr(slice_: Slice, expr: str, acc, *pragmas) -> Slice:
+    """Per-key ordered fold with a C expression: ``acc = <expr>`` over the rows of
+    each key in row order, ``acc`` starting at zero; the expression may use ``acc``
+    and the value columns ``c1 .. cn`` (``c0`` is the key).  ``acc`` names the
+    accumulator dtype.  Non-associative expressions are fine (e.g. a polynomial
+    hash ``acc * 31 + c1``): rows are stably sorted by key and one device thread
+    folds one key (NVRTC-compiled for sm_100a, ``ops/jit.py``)."""
+    from .ops import jit
+    _check_slice("foldexpr", slice_)
+    n = slice_.num_out()
+    if n < 2:
+        typecheck.panicf("Fold can be applied only for slices with at least two columns; got %d", n)
+    key = slice_.out(0)
+    if not key.hashable or not key.comparable:
+        typecheck.panicf("foldexpr: key type %s is not partitionable", key)
+    acc_t = slicetype.dtype_of(acc)
+    try:
+        jit.generate_fold(acc_t, list(slice_.typ.cols[1:]), expr)
+    except (TypeError, ValueError) as e:
+        typecheck.panicf("foldexpr: %s", e)
+    return _Fold(slice_, None, Type([key, acc_t], 1), pragmas, expr=expr)
 
 
 # --------------------------------------------------------------------------

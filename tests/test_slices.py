@@ -484,3 +484,38 @@ def test_user_defined_slice_and_cacheable_protocol():
         assert sorted(_CachedDoubling.store.frames) == [0, 1, 2] and _Doubling.calls == 3
         res = sess.run(_custom_pipeline, n, True)  # served from the user's cache
         assert dict(res.rows()) == want and _Doubling.calls == 3
+
+
+def test_fold_expr_non_associative(local_session):
+    """FoldExpr: ordered, non-associative fold (polynomial hash of each key's rows
+    in row order) vs a plain python loop."""
+    import torch
+    n = 5000
+    keys = torch.arange(n) % 17
+    vals = (torch.arange(n) * 7919) % 1000
+
+    @bs.Func
+    def job():
+        return bs.FoldExpr(bs.Const(4, keys, vals), "(acc * 31 + c1) % 1000003", bs.int64)
+    got = dict(local_session.run(job).rows())
+    want = {}
+    for k, v in zip(keys.tolist(), vals.tolist()):
+        want[k] = (want.get(k, 0) * 31 + v) % 1000003
+    # rows of a key are folded in shard order: Const splits rows contiguously and
+    # the shuffle keeps producer order, so the global row order is preserved
+    assert got == want
+
+
+def test_fold_python_rounds_are_capped(local_session, monkeypatch):
+    import torch
+    from bigslice_b200 import slices
+    monkeypatch.setattr(slices, "MAX_FOLD_ROUNDS", 8)
+    keys = torch.zeros(100, dtype=torch.int64)
+    vals = torch.ones(100, dtype=torch.int64)
+
+    @bs.Func
+    def job():
+        return bs.Fold(bs.Const(1, keys, vals), lambda acc, v: acc * 2 + v, acc=bs.int64)
+    with pytest.raises(bs.errors.Error) as ei:
+        local_session.run(job)
+    assert "FoldExpr" in str(ei.value)
