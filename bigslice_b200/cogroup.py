@@ -33,8 +33,46 @@ from .slices import Dep, Slice, _check_slice, make_name
 from .slicetype import Type
 
 
+def _device_join2(frames: Sequence[Frame], out_typ: Type):
+    """Two inputs, one int64 key, rows in HBM: radix sort + the sort-merge union
+    kernels of ``csrc/cogroup.cu`` (run detection, binary-search merge, CSR
+    sizes).  Returns None when the shape is not covered."""
+    if len(frames) != 2 or out_typ.prefix() != 1:
+        return None
+    from .ops import gpu
+    for f in frames:
+        k = f.col(0) if f.num_out() else None
+        if not (isinstance(k, torch.Tensor) and k.is_cuda and k.dtype == torch.int64 and k.dim() == 1):
+            return None
+    if not gpu.available():
+        return None
+    dev = frames[0].device
+    srt, uniq, starts = [], [], []
+    for f in frames:
+        g = f.prefixed(1).sorted() if len(f) > 1 else f.prefixed(1)
+        srt.append(g)
+        k = g.col(0).contiguous()
+        st = gpu.run_starts(k) if len(g) else torch.zeros(0, dtype=torch.int64, device=dev)
+        starts.append(st)
+        uniq.append(gpu.gather_rows(k, st) if len(g) else k)
+    uk, za, zb = gpu.cogroup_union2(uniq[0], starts[0], len(srt[0]), uniq[1], starts[1], len(srt[1]))
+    if uk.numel() == 0:
+        return Frame.empty(out_typ, dev)
+    cols: List = [uk]
+    for g, sizes in zip(srt, (za, zb)):
+        offs = torch.zeros(uk.numel() + 1, dtype=torch.int64, device=dev)
+        torch.cumsum(sizes, 0, out=offs[1:])
+        for j in range(1, g.num_out()):
+            cols.append(ListColumn(offs, g.col(j), g.out(j)))   # the sorted input column, zero copy
+    return Frame(cols, out_typ)
+
+
 def cogroup_frames(frames: Sequence[Frame], nkeys: int, out_typ: Type) -> Frame:
     """Merge-join whole (unsorted) input shards into the cogrouped frame."""
+    if nkeys == 1:
+        out = _device_join2(frames, out_typ)
+        if out is not None:
+            return out
     dev = None
     for f in frames:
         if len(f) and f.device.type != "cpu":

@@ -556,6 +556,48 @@ def topk(values: torch.Tensor, k: int) -> Tuple[torch.Tensor, torch.Tensor]:
     return values.reshape(-1)[idx], idx
 
 
+# ---------------------------------------------------------------- cogroup (sort-merge join)
+
+def run_starts(sorted_keys: torch.Tensor) -> torch.Tensor:
+    """Indices where a new key starts in a key-sorted int64 column (run detection
+    kernel + stream compaction)."""
+    lib = require()
+    n = sorted_keys.numel()
+    flags = torch.empty(n, dtype=torch.uint8, device=sorted_keys.device)
+    _chk(lib.bs_cg_run_flags(_ptr(sorted_keys), c_ll(n), _ptr(flags), _stream()), "cg_run_flags")
+    return compact_indices(flags.view(torch.bool))
+
+
+def cogroup_union2(ka: torch.Tensor, sa: torch.Tensor, na: int, kb: torch.Tensor, sb: torch.Tensor, nb: int
+                   ) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    """Union of two sorted *distinct* key lists with CSR group sizes.
+
+    ``ka``/``kb``: distinct keys of each input (ascending); ``sa``/``sb``: the row
+    index where each key's run starts in its sorted input of ``na``/``nb`` rows.
+    Returns ``(union_keys, sizes_a, sizes_b)``: for every key of the union how many
+    rows each input holds (0 when absent).  Binary-search merge on the device
+    (``csrc/cogroup.cu``)."""
+    lib = require()
+    dev = ka.device
+    a, b = ka.numel(), kb.numel()
+    ra, ma = torch.empty(a, dtype=torch.int64, device=dev), torch.empty(a, dtype=torch.int64, device=dev)
+    rb, mb = torch.empty(b, dtype=torch.int64, device=dev), torch.empty(b, dtype=torch.int64, device=dev)
+    _chk(lib.bs_cg_search(_ptr(ka), c_ll(a), _ptr(kb), c_ll(b), _ptr(ra), _ptr(ma), _stream()), "cg_search")
+    _chk(lib.bs_cg_search(_ptr(kb), c_ll(b), _ptr(ka), c_ll(a), _ptr(rb), _ptr(mb), _stream()), "cg_search")
+    ca = torch.cumsum(ma, 0) - ma   # common keys below (exclusive scan)
+    cb = torch.cumsum(mb, 0) - mb
+    common = int(ma.sum()) if a else 0
+    nu = a + b - common
+    uk = torch.empty(nu, dtype=torch.int64, device=dev)
+    za = torch.zeros(nu, dtype=torch.int64, device=dev)
+    zb = torch.zeros(nu, dtype=torch.int64, device=dev)
+    _chk(lib.bs_cg_place(_ptr(ka), c_ll(a), _ptr(ra), _ptr(ma), _ptr(ca), _ptr(sa), c_ll(na), _ptr(uk),
+                         _ptr(za), c_int(1), _stream()), "cg_place")
+    _chk(lib.bs_cg_place(_ptr(kb), c_ll(b), _ptr(rb), _ptr(mb), _ptr(cb), _ptr(sb), c_ll(nb), _ptr(uk),
+                         _ptr(zb), c_int(0), _stream()), "cg_place")
+    return uk, za, zb
+
+
 def crc32(t: torch.Tensor) -> int:
     """CRC32-IEEE of a device tensor's bytes (device per-block CRCs + host
     GF(2) combine)."""

@@ -365,3 +365,42 @@ def test_fold_device_tiers(gpu):
         for a, b in zip(k2.tolist(), v2.tolist()):
             want[a] = (want.get(a, 0) * 31 + b) % 1000003
         assert got == want
+
+
+def test_cogroup_sort_merge_kernels(gpu):
+    """Device Cogroup (radix sort + run detection + binary-search union + CSR
+    sizes) against a python dict reference, including keys present on one side
+    only, duplicates on both sides and empty inputs."""
+    from bigslice_b200.cogroup import cogroup_frames
+    g = torch.Generator().manual_seed(9)
+    na, nb = 200003, 50021
+    ka = torch.randint(0, 60000, (na,), generator=g)
+    va = torch.rand(na, generator=g)
+    kb = torch.randint(30000, 90000, (nb,), generator=g)
+    vb = torch.randint(0, 1000, (nb,), generator=g)
+    ta = bs.Type([bs.int64, bs.float32], 1)
+    tb = bs.Type([bs.int64, bs.int64], 1)
+    out_t = bs.Type([bs.int64, bs.List(bs.float32), bs.List(bs.int64)], 1)
+    before = gpu.launches()
+    f = cogroup_frames([Frame([ka.cuda(), va.cuda()], ta), Frame([kb.cuda(), vb.cuda()], tb)], 1, out_t)
+    assert gpu.launches() - before >= 6
+    want = {}
+    for k, v in zip(ka.tolist(), va.tolist()):
+        want.setdefault(k, ([], []))[0].append(v)
+    for k, v in zip(kb.tolist(), vb.tolist()):
+        want.setdefault(k, ([], []))[1].append(v)
+    keys = f.col(0).cpu().tolist()
+    assert keys == sorted(want)
+    la, lb = f.col(1), f.col(2)
+    oa, ob = la.offsets.cpu().tolist(), lb.offsets.cpu().tolist()
+    xa, xb = la.values.cpu().tolist(), lb.values.cpu().tolist()
+    for i in (0, 1, 2, len(keys) // 2, len(keys) - 1):
+        k = keys[i]
+        assert sorted(xa[oa[i]:oa[i + 1]]) == pytest.approx(sorted(want[k][0]))
+        assert sorted(xb[ob[i]:ob[i + 1]]) == sorted(want[k][1])
+    assert oa[-1] == na and ob[-1] == nb
+    # one side empty
+    e = Frame([torch.empty(0, dtype=torch.int64).cuda(), torch.empty(0, dtype=torch.int64).cuda()], tb)
+    f2 = cogroup_frames([Frame([ka.cuda(), va.cuda()], ta), e], 1, out_t)
+    assert f2.col(0).cpu().tolist() == sorted(set(ka.tolist()))
+    assert int(f2.col(2).offsets[-1]) == 0
