@@ -88,7 +88,16 @@ def col_take(c, idx):
     if isinstance(c, torch.Tensor):
         if not isinstance(idx, torch.Tensor):
             idx = torch.as_tensor(np.asarray(idx), dtype=torch.int64)
-        return c.index_select(0, idx.to(c.device))
+        idx = idx.to(c.device)
+        if c.is_cuda and c.dim() >= 2 and c.dtype != torch.bool and idx.dtype == torch.int64 \
+                and c.element_size() * (c.numel() // max(c.shape[0], 1)) >= 16:
+            # wide rows: the vectorised gather kernel (24x torch.index_select on
+            # 16-byte rows, profiles/r2_kernels_vs_torch.jsonl); scalar columns stay
+            # with the library, which is ahead there
+            from ..ops import gpu
+            if gpu.available():
+                return gpu.gather_rows(c, idx.contiguous())
+        return c.index_select(0, idx)
     if isinstance(c, ListColumn):
         if not isinstance(idx, torch.Tensor):
             idx = torch.as_tensor(np.asarray(idx), dtype=torch.int64)

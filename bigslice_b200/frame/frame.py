@@ -26,6 +26,10 @@ from . import hashing
 from .ops import ops_for_value
 
 
+import os as _os
+_OWN_SORT = bool(_os.environ.get("BIGSLICE_OWN_SORT"))
+
+
 def _grow_cap(need: int, cap: int) -> int:
     """Growth policy: 2x below 1024 rows, 1.25x above (frame.go:458-484)."""
     newcap = cap
@@ -290,7 +294,11 @@ class Frame:
         keys = [self.col(k) for k in range(self.prefix())]
         if len(keys) == 1 and isinstance(keys[0], torch.Tensor) and keys[0].dim() == 1:
             k0 = keys[0]
-            if k0.is_cuda and k0.dtype == torch.int64:
+            # Device sorts go to the library (CUB onesweep behind torch.sort): the
+            # in-tree LSD radix sort measured 0.53x of it on B200
+            # (profiles/r2_kernels_vs_torch.jsonl) and is kept only as an opt-in
+            # reference (BIGSLICE_OWN_SORT=1).
+            if k0.is_cuda and k0.dtype == torch.int64 and _OWN_SORT:
                 from ..ops import gpu
                 if gpu.available():
                     return gpu.sort_pairs_i64(k0, None)[1]

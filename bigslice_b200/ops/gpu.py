@@ -157,13 +157,8 @@ def gather_rows(col: torch.Tensor, idx: torch.Tensor) -> torch.Tensor:
 
 
 def take_frame(f: Frame, idx: torch.Tensor) -> Frame:
-    cols = []
-    for c in f.cols():
-        if isinstance(c, torch.Tensor) and c.is_cuda and c.dtype != torch.bool:
-            cols.append(gather_rows(c, idx))
-        else:
-            cols.append(C.col_take(c, idx))
-    return Frame(cols, f.typ)
+    # col_take picks the gather kernel for wide rows and the library for scalars
+    return Frame([C.col_take(c, idx) for c in f.cols()], f.typ)
 
 
 def partition_frame(f: Frame, ids: torch.Tensor, npart: int) -> List[Frame]:

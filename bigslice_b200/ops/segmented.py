@@ -20,6 +20,10 @@ from ..frame import columns as C
 from .functors import SCATTER, builtin_name
 
 
+import os as _os
+_OWN_SEGREDUCE = bool(_os.environ.get("BIGSLICE_OWN_SEGREDUCE"))
+
+
 def _neq_prev(c) -> torch.Tensor:
     """mask[i] = (c[i] != c[i-1]) for i>=1, mask[0] = True (on col's device)."""
     n = C.col_len(c)
@@ -69,7 +73,9 @@ def segmented_reduce(values, starts: torch.Tensor, fn: Callable,
     if isinstance(values, torch.Tensor) and not rowwise:
         seg = seg.to(values.device)
         if name in SCATTER and values.dtype not in (torch.bool,) and values.dim() == 1:
-            if values.is_cuda:
+            if values.is_cuda and _OWN_SEGREDUCE:
+                # opt-in: the in-tree kernel measured 0.56x of index_add_ on B200
+                # (profiles/r2_kernels_vs_torch.jsonl), so the library is the default
                 from . import gpu
                 if gpu.available() and values.dtype in gpu.SEGREDUCE_DTYPES:
                     return gpu.segmented_reduce(values, starts.to(values.device), nseg, name)
