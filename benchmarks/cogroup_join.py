@@ -31,12 +31,20 @@ def join():
     return bs.Cogroup(wc._SOURCES["large"], wc._SOURCES["small"])
 
 
+@bs.Func
+def bjoin():
+    """The broadcast-shaped variant: the small side is replicated through the
+    switch (multimem.st), the large side is joined where it is."""
+    return bs.BroadcastJoin(wc._SOURCES["large"], wc._SOURCES["small"])
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--large", type=int, default=1 << 26)
     ap.add_argument("--small", type=int, default=1 << 22)
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--out", default="gpurun_out/cogroup.json")
+    ap.add_argument("--broadcast", action="store_true", help="BroadcastJoin instead of Cogroup")
     a = ap.parse_args()
     init_process_group("cuda")
     rank, world = dist.get_rank(), dist.get_world_size()
@@ -60,7 +68,7 @@ def main():
         dist.barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        res = sess.run(join)
+        res = sess.run(bjoin if a.broadcast else join)
         e1.record()
         torch.cuda.synchronize()
         nkeys = sum(len(f) for f in res.frames())
@@ -72,7 +80,7 @@ def main():
     ms = sorted(times)[len(times) // 2]
     tot = torch.tensor([nkeys], device=dev)
     dist.all_reduce(tot)
-    out = {"metric": "Cogroup join rows/s", "world": world, "rows_large_per_gpu": a.large,
+    out = {"metric": "BroadcastJoin rows/s" if a.broadcast else "Cogroup join rows/s", "world": world, "rows_large_per_gpu": a.large,
            "rows_small_per_gpu": a.small, "ms_per_step": ms,
            "rows_per_s": (a.large + a.small) * world / (ms / 1e3), "distinct_keys": int(tot[0]),
            "modes": sorted(set(x["mode"] for x in sess.executor.exchange_log))}

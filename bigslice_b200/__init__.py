@@ -29,7 +29,7 @@ from .slices import (Const, Dep, Exclusive, ExperimentalMaterialize, Filter, Fla
                      Prefixed, Procs, RangeShard, ReaderFunc, ReaderGen, Scan, Slice,
                      String, Unwrap, WriterFunc, helper, make_name, MakeName, MapExpr, FilterExpr, FoldExpr)
 from .reduce import Reduce
-from .cogroup import Cogroup
+from .cogroup import Cogroup, BroadcastJoin
 from .reshuffle import Repartition, Reshard, Reshuffle
 from .scan import ScanReader
 from .cache import Cache, CachePartial, ReadCache

@@ -122,6 +122,73 @@ def cogroup_frames(frames: Sequence[Frame], nkeys: int, out_typ: Type) -> Frame:
     return Frame(cols, out_typ)
 
 
+def broadcast_partitioner(frame: Frame, nshard: int) -> torch.Tensor:
+    """Marker partitioner of a *replicating* dependency: every row goes to every
+    shard.  Executors recognise the function itself (a partitioner can only name
+    one shard per row); calling it is an error."""
+    raise RuntimeError("broadcast_partitioner marks a replicated dependency; it is not called")
+
+
+class _BroadcastJoin(Slice):
+    def __init__(self, large: Slice, small: Slice, typ: Type):
+        super().__init__(make_name("broadcastjoin"), typ, large.num_shard(),
+                         [Dep(large, shuffle=False), Dep(small, shuffle=True, partitioner=broadcast_partitioner)],
+                         ())
+        self.in_typs = [large.typ, small.typ]
+
+    def reader(self, shard, deps: List[Reader]) -> Reader:
+        done = [False]
+
+        def read(n):
+            if done[0]:
+                return None
+            done[0] = True
+            dev = _context.current_device()
+            frames = [read_all(r, t, dev) for r, t in zip(deps, self.in_typs)]
+            if len(frames[0]) == 0:
+                return None
+            out = cogroup_frames(frames, 1, self.typ)
+            # left join: keep the keys that occur in this shard of the large side
+            la = out.col(1)
+            have = (la.offsets[1:] - la.offsets[:-1]) > 0
+            if not bool(have.all()):
+                out = out.take(torch.nonzero(have).flatten())
+            return out if len(out) else None
+
+        def close():
+            for r in deps:
+                r.close()
+        return Rebatch(FuncReader(read, close))
+
+
+def BroadcastJoin(large: Slice, small: Slice) -> Slice:
+    """Broadcast-shaped join (an extension; the reference has only the shuffled
+    ``Cogroup``): the *small* input is replicated on every shard — on B200 through
+    NVSwitch multicast, one ``multimem.st`` per 16 bytes — and joined against the
+    *large* input **where it already is** (no shuffle of the large side).
+
+    Output, per shard of ``large``: one row ``<key, [large values], [small values]>``
+    for every key of that shard (left join; ``[]`` when the small side lacks the
+    key), sorted by key.  When ``large`` is partitioned by key (the output of a
+    Reduce, Reshuffle, Cogroup…) this equals the rows of ``Cogroup(large, small)``
+    that have a large side; otherwise a key that occurs in several shards of
+    ``large`` yields one row per shard."""
+    for i, s in enumerate((large, small)):
+        _check_slice("broadcastjoin", s)
+        if s.prefix() != 1 or s.num_out() < 1:
+            typecheck.panicf("broadcastjoin: slice %d must have exactly one key column", i)
+    if large.out(0) != small.out(0):
+        typecheck.panicf("broadcastjoin: key column type mismatch: expected %s but got %s",
+                         large.out(0), small.out(0))
+    if not frame_ops.can_hash(large.out(0)) or not frame_ops.can_compare(large.out(0)):
+        typecheck.panicf("broadcastjoin: key type %s cannot be hashed and sorted", large.out(0))
+    cols = [large.out(0)]
+    for s in (large, small):
+        for j in range(1, s.num_out()):
+            cols.append(slicetype.List(s.out(j)))
+    return _BroadcastJoin(large, small, Type(cols, 1))
+
+
 class _Cogroup(Slice):
     def __init__(self, slices_: Sequence[Slice], typ: Type, nshard: int, nkeys: int):
         super().__init__(make_name("cogroup"), typ, nshard,

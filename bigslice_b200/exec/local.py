@@ -529,8 +529,14 @@ class LocalExecutor(Executor):
         t_read = t_write = 0.0
         nrec = 0
 
+        from ..cogroup import broadcast_partitioner
+        replicate = task.partitioner is broadcast_partitioner
+
         def emit(f: Frame) -> None:
-            if npart > 1:
+            if replicate:       # a replicated dependency: every consumer shard reads every row
+                for p in range(npart):
+                    buf.append(p, f)
+            elif npart > 1:
                 parts = split_by_partition(f, task.partitioner(f, npart), npart)
                 # the device partition kernel does not keep the row order inside a
                 # partition; combined output must stay sorted by key for the consumers

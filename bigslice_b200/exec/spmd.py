@@ -352,8 +352,17 @@ class SpmdExecutor(LocalExecutor):
                 # invocation (with whatever status its producers reach): skipping
                 # them here would leave the peers waiting
                 self.group_err[gid] = e
-            except BaseException as e:  # noqa: BLE001 - a bug or a CUDA failure, not a lost task
-                import traceback
+            except BaseException as e:  # noqa: BLE001
+                if _is_comm_failure(e):
+                    # a peer went away mid-collective: the exchange is lost (it is
+                    # retried, and gives up with TooManyTries if the peer stays gone)
+                    self._rx_reset = True
+                    self.group_err[gid] = errors.TaskLostError(
+                        "spmd: exchange of %s lost a peer: %s" % (group[0].name, str(e)[:200]))
+                    if ev is not None:
+                        ev.set()
+                    continue
+                import traceback  # anything else is a bug or a CUDA failure, not a lost task
                 self.group_err[gid] = errors.fatal("spmd: exchange of %s raised %s: %s\n%s" % (
                     group[0].name, type(e).__name__, e, traceback.format_exc()), e)
             if ev is not None:
@@ -407,6 +416,13 @@ class SpmdExecutor(LocalExecutor):
         ctx = slicefunc.Context(None, 0, self.device)
         t0 = time.perf_counter()
         ev0 = self._cuda_event()
+        from ..cogroup import broadcast_partitioner
+        if head.partitioner is broadcast_partitioner:
+            mode, g = self._replicate(f)
+            with self._glock:
+                for p in range(self.rank, nparts, self.world):
+                    self.exchanged[(gid, p)] = [g] if len(g) else []
+            return self._log_exchange(head, mode, t0, ev0, rows_in=len(f))
         with _context.use(ctx):
             if head.combiner is not None and len(f):
                 f = combine_frame(f, head.combiner, ctx)
@@ -494,6 +510,17 @@ class SpmdExecutor(LocalExecutor):
                                      timeout_s=self.exchange_timeout)
         return self.rx
 
+    def _peers_alive(self) -> None:
+        """Before a collective re-initialisation: every rank checks in on the
+        status board (bounded wait) so that a dead peer yields a lost task, not a
+        hang inside a barrier."""
+        if self.board is None:
+            return
+        self.xseq += 1
+        self.board.post(self.xseq, 0, -1)
+        if self.board.wait_all(self.xseq, self.exchange_timeout) is None:
+            raise errors.TaskLostError("spmd: rank(s) %s unreachable" % self.board.missing(self.xseq))
+
     def _board_vote(self, bad: int, acc: int, fps, head: Task) -> None:
         """Host-side agreement for one exchange: post my status + fingerprint and
         read everyone else's from shared memory (no collective, no GPU)."""
@@ -558,7 +585,15 @@ class SpmdExecutor(LocalExecutor):
             if self._rx_reset or self._want_arena:
                 # a lost exchange left epochs or the arena in doubt: start over (collective)
                 with span("xchg/reset"):
-                    rx.reset(max(self._want_arena, rx.arena_bytes))
+                    try:
+                        self._peers_alive()
+                        rx.reset(max(self._want_arena, rx.arena_bytes))
+                    except errors.Error:
+                        raise
+                    except BaseException as e:  # noqa: BLE001
+                        if _is_comm_failure(e):
+                            raise errors.TaskLostError("spmd: cannot re-establish the exchange: %s" % e)
+                        raise
                 self._rx_reset, self._want_arena = False, 0
             if self.world == 1 and rx.arena_bytes < self.arena_bytes:
                 rx.reset(self.arena_bytes)  # single rank: the arena is allocated on first use
@@ -783,6 +818,30 @@ class SpmdExecutor(LocalExecutor):
             dur = int(rec.get("device_ms", rec["seconds"] * 1e3) * 1e3)
             self.tracer.complete(self._pid(), "exchange:%s[%s]" % (head.name, mode), now - dur, dur,
                                  cat="exchange", rows_in=kw.get("rows_in", 0))
+
+    def _replicate(self, f: Frame):
+        """Every rank ends up with the rows of all ranks (a replicated
+        dependency, e.g. the small side of a BroadcastJoin): NVSwitch multicast
+        when the columns are device tensors, the library otherwise."""
+        if self.world == 1:
+            return "replicate-local", f
+        tensor_only = all(isinstance(c, torch.Tensor) for c in f.cols()) and f.num_out() > 0
+        if tensor_only and f.device.type == "cuda":
+            from ..parallel.broadcast import Replicator
+            if getattr(self, "_replicator", None) is None:
+                self._replicator = Replicator(dist.group.WORLD, self.arena_bytes, self.device, self.ctrl_group)
+            cols = self._replicator.all_gather(f.cols())
+            return "replicate-" + self._replicator.mode, Frame(cols, f.typ)
+        if tensor_only:
+            from ..parallel.broadcast import Replicator
+            rep = Replicator(self.ctrl_group, 0, "cpu", self.ctrl_group)
+            return "replicate-library", Frame(rep.all_gather(f.cols()), f.typ)
+        # any column type: codec-encoded frames over the control plane
+        blobs = [None] * self.world
+        dist.all_gather_object(blobs, encode_frame(f.to("cpu") if f.device.type != "cpu" else f) if len(f) else b"",
+                               group=self.ctrl_group)
+        parts = [_decode_one(b, f.typ, self.device) for b in blobs if b]
+        return "replicate-object", (concat(parts, f.typ, self.device) if parts else f)
 
     def _fused_ok(self, f: Frame, head: Task, nparts: int) -> bool:
         from ..parallel import peer
@@ -1015,6 +1074,20 @@ class SpmdExecutor(LocalExecutor):
         for s in sorted(merged):
             out.extend(merged[s])
         return out
+
+
+def _is_comm_failure(e: BaseException) -> bool:
+    """torch.distributed / transport errors that mean "a peer is unreachable"."""
+    for name in ("DistNetworkError", "DistBackendError", "DistStoreError"):
+        cls = getattr(dist, name, None)
+        if cls is not None and isinstance(e, cls):
+            return True
+    if isinstance(e, (ConnectionError, TimeoutError, BrokenPipeError)):
+        return True
+    msg = str(e)
+    return isinstance(e, RuntimeError) and any(
+        s in msg for s in ("Connection closed by peer", "Connection reset", "Broken pipe", "timed out",
+                           "Timed out", "Socket Timeout", "NCCL communicator was aborted", "ncclRemoteError"))
 
 
 def _deferred():

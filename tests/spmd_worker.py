@@ -48,6 +48,13 @@ def join(nshard: int):
 
 
 @bs.Func
+def bjoin(nshard: int):
+    large = bs.Reshuffle(bs.Const(nshard, KEYS, torch.arange(N, dtype=torch.float32)))
+    small = bs.Const(nshard, torch.arange(0, 97, 2), torch.arange(0, 97, 2) * 10)
+    return bs.BroadcastJoin(large, small)
+
+
+@bs.Func
 def reshard(nshard: int, out: int):
     return bs.Reshard(bs.Const(nshard, KEYS, torch.arange(N)), out)
 
@@ -362,6 +369,10 @@ def main():
     for k in range(0, 97, 2):
         wantj.setdefault(k, ([], []))[1].append(k * 10)
     out["join_ok"] = got == {k: (sorted(a), sorted(b)) for k, (a, b) in wantj.items()}
+    rows = ex.gather(sess.run(bjoin, 2 * world))
+    gotb = {k: (sorted(a), sorted(b)) for k, a, b in rows}
+    out["bjoin_ok"] = (len(rows) == len(gotb) and
+                       gotb == {k: (sorted(a), sorted(b)) for k, (a, b) in wantj.items() if a})
     res = sess.run(reshard, world, 2 * world + 1)
     rows = ex.gather(res)
     out["reshard_ok"] = sorted(rows) == sorted(zip(KEYS.tolist(), range(N)))

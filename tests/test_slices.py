@@ -519,3 +519,21 @@ def test_fold_python_rounds_are_capped(local_session, monkeypatch):
     with pytest.raises(bs.errors.Error) as ei:
         local_session.run(job)
     assert "FoldExpr" in str(ei.value)
+
+
+def test_broadcast_join_left_semantics(local_session):
+    """BroadcastJoin: small side replicated, large side stays where it is; one row
+    per key of every large shard, small-only keys dropped."""
+    import torch
+    lk = torch.tensor([5, 1, 5, 9, 2, 2, 7])
+    lv = torch.arange(7, dtype=torch.float32)
+    sk = torch.tensor([2, 5, 100])
+    sv = torch.tensor([20, 50, 1000])
+
+    @bs.Func
+    def job():
+        large = bs.Reshuffle(bs.Const(3, lk, lv))        # partitioned by key
+        return bs.BroadcastJoin(large, bs.Const(2, sk, sv))
+    rows = {k: (sorted(a), sorted(b)) for k, a, b in local_session.run(job).rows()}
+    assert rows == {1: ([1.0], []), 2: ([4.0, 5.0], [20]), 5: ([0.0, 2.0], [50]), 7: ([6.0], []),
+                    9: ([3.0], [])}

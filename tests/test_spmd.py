@@ -38,7 +38,7 @@ def check(outs, world):
     assert scanned == [2 * i for i in range(100)]
     for o in outs:
         assert o["world"] == world
-        for k in ("wordcount_ok", "chain_ok", "strcount_ok", "join_ok", "reshard_ok",
+        for k in ("wordcount_ok", "chain_ok", "strcount_ok", "join_ok", "bjoin_ok", "reshard_ok",
                   "reshard_placement_ok", "failure_ok"):
             assert o[k], (k, o)
     for o in outs:
@@ -57,7 +57,7 @@ def test_spmd_cpu_gloo(world, tmp_path):
     check(outs, world)
     if world > 1:
         # tensor frames ride the gloo all-to-all, string/list frames the object path
-        assert set(outs[0]["modes"]) == {"gloo", "object"}
+        assert set(outs[0]["modes"]) == {"gloo", "object", "replicate-library"}
 
 
 @pytest.mark.gpu
@@ -87,3 +87,49 @@ def test_spmd_two_ranks_sharing_one_gpu(tmp_path):
     check(outs, 2)
     assert "fused-table" in outs[0]["modes"]
     assert outs[0]["sentinel_ok"] and outs[0]["distinct_ok"] and outs[0]["overflow_recovered_ok"]
+
+
+def _spawn_ranks(script, world, tmp_path, env_extra, timeout=120):
+    """Plain subprocesses (not torchrun: its agent would kill the survivors as
+    soon as one rank dies)."""
+    out = str(tmp_path / "out.json")
+    port = free_port()
+    procs = []
+    for r in range(world):
+        env = dict(os.environ, RANK=str(r), LOCAL_RANK=str(r), WORLD_SIZE=str(world),
+                   MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), BS_TEST_OUT=out)
+        env.update(env_extra)
+        procs.append(subprocess.Popen([sys.executable, os.path.join(HERE, script)], env=env,
+                                      stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True))
+    res = []
+    for p in procs:
+        try:
+            o, e = p.communicate(timeout=timeout)
+        except subprocess.TimeoutExpired:
+            p.kill()
+            o, e = p.communicate()
+            e += "\n[killed: timeout]"
+        res.append((p.returncode, o, e))
+    return out, res
+
+
+def _check_rank_death(out, res):
+    assert res[1][0] == 17, res[1][2][-2000:]          # rank 1 died as scripted
+    assert os.path.exists(out + ".0"), res[0][2][-3000:]
+    o = json.load(open(out + ".0"))
+    assert o["ok_first"]
+    assert o["error"] is not None and o["lost_classified"], o
+    assert o["seconds"] < 35, o
+
+
+def test_rank_death_is_a_lost_task_not_a_hang_cpu(tmp_path):
+    out, res = _spawn_ranks("kill_worker.py", 2, tmp_path, {"BS_TEST_DEVICE": "cpu", "BS_TEST_TIMEOUT": "3"})
+    _check_rank_death(out, res)
+
+
+@pytest.mark.gpu
+def test_rank_death_is_a_lost_task_not_a_hang_gpu(tmp_path):
+    out, res = _spawn_ranks("kill_worker.py", 2, tmp_path,
+                            {"BS_TEST_DEVICE": "cuda", "BS_TEST_TIMEOUT": "3", "BIGSLICE_DIST_BACKEND": "gloo",
+                             "BIGSLICE_SHARE_GPU": "1", "LOCAL_RANK": "0"}, timeout=180)
+    _check_rank_death(out, res)
