@@ -33,10 +33,11 @@ from .slices import Dep, Slice, _check_slice, make_name
 from .slicetype import Type
 
 
-def _device_join2(frames: Sequence[Frame], out_typ: Type):
+def _device_join2(frames: Sequence[Frame], out_typ: Type, left: bool = False):
     """Two inputs, one int64 key, rows in HBM: radix sort + the sort-merge union
     kernels of ``csrc/cogroup.cu`` (run detection, binary-search merge, CSR
-    sizes).  Returns None when the shape is not covered."""
+    sizes).  ``left``: only the keys of the first input (BroadcastJoin).  Returns
+    None when the shape is not covered."""
     if len(frames) != 2 or out_typ.prefix() != 1:
         return None
     from .ops import gpu
@@ -55,6 +56,8 @@ def _device_join2(frames: Sequence[Frame], out_typ: Type):
         st = gpu.run_starts(k) if len(g) else torch.zeros(0, dtype=torch.int64, device=dev)
         starts.append(st)
         uniq.append(gpu.gather_rows(k, st) if len(g) else k)
+    if left:
+        return _left_join(srt, uniq, starts, out_typ, dev)
     uk, za, zb = gpu.cogroup_union2(uniq[0], starts[0], len(srt[0]), uniq[1], starts[1], len(srt[1]))
     if uk.numel() == 0:
         return Frame.empty(out_typ, dev)
@@ -64,6 +67,35 @@ def _device_join2(frames: Sequence[Frame], out_typ: Type):
         torch.cumsum(sizes, 0, out=offs[1:])
         for j in range(1, g.num_out()):
             cols.append(ListColumn(offs, g.col(j), g.out(j)))   # the sorted input column, zero copy
+    return Frame(cols, out_typ)
+
+
+def _left_join(srt, uniq, starts, out_typ: Type, dev) -> Frame:
+    """Rows for the distinct keys of input 0 only.  The large side's value columns
+    are its sorted columns (zero copy, CSR offsets = its run starts); of the small
+    side only the rows whose key occurs on the large side are gathered."""
+    from .ops import gpu
+    ka, kb = uniq
+    na, nb = len(srt[0]), len(srt[1])
+    if ka.numel() == 0:
+        return Frame.empty(out_typ, dev)
+    ra, ma = gpu.cogroup_search(ka, kb)
+    cols: List = [ka]
+    offs_a = torch.cat([starts[0], torch.tensor([na], dtype=torch.int64, device=dev)])
+    for j in range(1, srt[0].num_out()):
+        cols.append(ListColumn(offs_a, srt[0].col(j), srt[0].out(j)))
+    if kb.numel():
+        run_b = torch.diff(torch.cat([starts[1], torch.tensor([nb], dtype=torch.int64, device=dev)]))
+        sizes_b = torch.where(ma.bool(), run_b[ra.clamp(max=kb.numel() - 1)], torch.zeros_like(ra))
+        _, mb = gpu.cogroup_search(kb, ka)
+        keep = torch.nonzero(torch.repeat_interleave(mb.bool(), run_b)).flatten()
+    else:
+        sizes_b = torch.zeros(ka.numel(), dtype=torch.int64, device=dev)
+        keep = torch.zeros(0, dtype=torch.int64, device=dev)
+    offs_b = torch.zeros(ka.numel() + 1, dtype=torch.int64, device=dev)
+    torch.cumsum(sizes_b, 0, out=offs_b[1:])
+    for j in range(1, srt[1].num_out()):
+        cols.append(ListColumn(offs_b, C.col_take(srt[1].col(j), keep), srt[1].out(j)))
     return Frame(cols, out_typ)
 
 
@@ -147,6 +179,9 @@ class _BroadcastJoin(Slice):
             frames = [read_all(r, t, dev) for r, t in zip(deps, self.in_typs)]
             if len(frames[0]) == 0:
                 return None
+            out = _device_join2(frames, self.typ, left=True)
+            if out is not None:
+                return out if len(out) else None
             out = cogroup_frames(frames, 1, self.typ)
             # left join: keep the keys that occur in this shard of the large side
             la = out.col(1)

@@ -563,6 +563,18 @@ def run_starts(sorted_keys: torch.Tensor) -> torch.Tensor:
     return compact_indices(flags.view(torch.bool))
 
 
+def cogroup_search(mine: torch.Tensor, other: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    """For every key of the ascending list ``mine``: its lower-bound rank in the
+    ascending list ``other`` and whether it occurs there (0/1)."""
+    lib = require()
+    n = mine.numel()
+    r = torch.empty(n, dtype=torch.int64, device=mine.device)
+    m = torch.empty(n, dtype=torch.int64, device=mine.device)
+    _chk(lib.bs_cg_search(_ptr(mine), c_ll(n), _ptr(other), c_ll(other.numel()), _ptr(r), _ptr(m), _stream()),
+         "cg_search")
+    return r, m
+
+
 def cogroup_union2(ka: torch.Tensor, sa: torch.Tensor, na: int, kb: torch.Tensor, sb: torch.Tensor, nb: int
                    ) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
     """Union of two sorted *distinct* key lists with CSR group sizes.

@@ -404,3 +404,26 @@ def test_cogroup_sort_merge_kernels(gpu):
     f2 = cogroup_frames([Frame([ka.cuda(), va.cuda()], ta), e], 1, out_t)
     assert f2.col(0).cpu().tolist() == sorted(set(ka.tolist()))
     assert int(f2.col(2).offsets[-1]) == 0
+
+
+def test_broadcast_join_device_left_join(gpu):
+    from bigslice_b200.cogroup import _device_join2
+    g = torch.Generator().manual_seed(4)
+    ka = torch.randint(0, 5000, (60000,), generator=g)
+    va = torch.rand(60000, 4, generator=g)
+    kb = torch.randint(2500, 7500, (9000,), generator=g)
+    vb = torch.randint(0, 99, (9000,), generator=g)
+    ta = bs.Type([bs.int64, bs.Vec(bs.float32, 4)], 1)
+    tb = bs.Type([bs.int64, bs.int64], 1)
+    out_t = bs.Type([bs.int64, bs.List(bs.Vec(bs.float32, 4)), bs.List(bs.int64)], 1)
+    f = _device_join2([Frame([ka.cuda(), va.cuda()], ta), Frame([kb.cuda(), vb.cuda()], tb)], out_t, left=True)
+    keys = f.col(0).cpu().tolist()
+    assert keys == sorted(set(ka.tolist()))
+    want_b = {}
+    for k, v in zip(kb.tolist(), vb.tolist()):
+        want_b.setdefault(k, []).append(v)
+    ob = f.col(2).offsets.cpu().tolist()
+    xb = f.col(2).values.cpu().tolist()
+    for i, k in enumerate(keys):
+        assert sorted(xb[ob[i]:ob[i + 1]]) == sorted(want_b.get(k, [])), k
+    assert int(f.col(1).offsets[-1]) == 60000
