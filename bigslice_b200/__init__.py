@@ -37,7 +37,7 @@ from .func import Func, FuncValue, Invocation
 from .ops import functors as ops
 from . import exec  # noqa: A004 - mirrors the reference package name
 from . import slicetest, sliceio, sortio, frame  # noqa: F401,E402
-from .exec import (Local, LocalDevice, MachineCombiners, MaxLoad, Parallelism, Result,
+from .exec import (Local, LocalDevice, MachineCombiners, MaxLoad, Parallelism, Result, StoreOpt, Journal,
                    Session, Spmd, TracePath, start, Start)
 
 __version__ = "0.1.0"

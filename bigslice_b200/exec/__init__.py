@@ -8,7 +8,7 @@ from .eval import Executor, Eval, evaluate, MAX_CONSECUTIVE_LOST
 from .local import LocalExecutor, TaskBuffer
 from .combiner import Combiner, CombiningFrame
 from .session import (Bigmachine, DefaultMaxLoad, EventerOpt, ListEventer, Local,
-                      LocalDevice, MachineCombiners, MaxLoad, NopEventer, Option,
+                      LocalDevice, MachineCombiners, MaxLoad, NopEventer, Option, StoreOpt, Journal,
                       Parallelism, Result, Session, Spmd, Start, StatusOpt, TracePath,
                       start)
 from .tracer import Tracer
@@ -24,7 +24,7 @@ __all__ = [
     "Executor", "Eval", "evaluate", "MAX_CONSECUTIVE_LOST", "LocalExecutor",
     "TaskBuffer", "Combiner", "CombiningFrame", "Bigmachine", "DefaultMaxLoad",
     "Eventer", "EventerOpt", "ListEventer", "Local", "LocalDevice",
-    "MachineCombiners", "MaxLoad", "NopEventer", "Option", "Parallelism", "Result",
+    "MachineCombiners", "MaxLoad", "NopEventer", "Option", "StoreOpt", "Journal", "Parallelism", "Result",
     "Session", "Spmd", "Start", "Status", "StatusOpt", "TracePath", "start",
     "Tracer", "top_n",
 ]

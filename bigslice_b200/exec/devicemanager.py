@@ -178,9 +178,39 @@ class DeviceManager:
             self.devs[index].health = OK
             self.cond.notify_all()
 
-    def status(self) -> List[str]:
+    def poll(self) -> List[dict]:
+        """Per-device health snapshot: procs, load, tasks resident, and for CUDA
+        devices free/total HBM and bytes held by the caching allocator (the
+        analogue of the reference's periodic mem/disk/load polling of machines,
+        ``exec/slicemachine.go:238-257``)."""
+        out = []
         with self.cond:
-            return [repr(d) for d in self.devs]
+            devs = list(self.devs)
+        for d in devs:
+            rec = {"index": d.index, "device": str(d.device), "health": d.health, "procs": d.curprocs,
+                   "maxprocs": d.maxprocs, "load": round(d.load(), 3), "tasks": len(d.tasks),
+                   "done": d.done_count, "errors": d.err_count}
+            if d.device.type == "cuda" and d.health != LOST:
+                try:
+                    free, total = torch.cuda.mem_get_info(d.device)
+                    rec.update(hbm_free=free, hbm_total=total,
+                               hbm_allocated=torch.cuda.memory_allocated(d.device))
+                except Exception as e:  # noqa: BLE001 - a dying device must not kill the poller
+                    rec["poll_error"] = str(e)[:80]
+            out.append(rec)
+        return out
+
+    def status(self) -> List[str]:
+        """One line per device (rendered under ``machines`` in /debug/status)."""
+        lines = []
+        for r in self.poll():
+            mem = ""
+            if "hbm_total" in r:
+                mem = " hbm %.1f/%.1f GiB" % ((r["hbm_total"] - r["hbm_free"]) / 2**30, r["hbm_total"] / 2**30)
+            lines.append("dev%d(%s %d/%d %s)%s load %.2f tasks %d done %d err %d" % (
+                r["index"], r["device"], r["procs"], r["maxprocs"], r["health"], mem, r["load"],
+                r["tasks"], r["done"], r["errors"]))
+        return lines
 
 
 class MultiDeviceExecutor(LocalExecutor):

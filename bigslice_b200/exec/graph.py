@@ -98,5 +98,20 @@ def register(sess, mux: DebugMux) -> None:
     mux.handle("/debug/tasks/graph", lambda: ("application/json", task_graph_json(roots())))
     mux.handle("/debug/tasks", lambda: ("text/html", _HTML))
     mux.handle("/debug/trace", lambda: ("application/json", sess.tracer.marshal()))
-    mux.handle("/debug/status", lambda: ("text/plain",
-                                         sess.status_.marshal() if sess.status_ else ""))
+    def status_text():
+        """Status groups plus the executor's machine lines (per-GPU HBM, load,
+        exchange counters — reference: the ``machines`` status group,
+        ``exec/slicemachine.go:238-257``) and the last invocation's plan."""
+        parts = []
+        lines = None
+        ex = sess.executor
+        if hasattr(ex, "status_lines"):
+            lines = ex.status_lines()
+        elif hasattr(ex, "mgr"):
+            lines = ex.mgr.status()
+        if lines:
+            parts.append("machines\n" + "\n".join("  " + ln for ln in lines))
+        if sess.status_:
+            parts.append(sess.status_.marshal())
+        return "\n".join(parts)
+    mux.handle("/debug/status", lambda: ("text/plain", status_text()))

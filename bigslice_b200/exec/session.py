@@ -70,12 +70,12 @@ def _set_executor(factory):
 
 
 #: Run everything in-process on CPU tensors (``exec.Local``).
-Local = _set_executor(lambda s: LocalExecutor(s.p, None))
+Local = _set_executor(lambda s: LocalExecutor(s.p, None, store=s.store_))
 
 
 def LocalDevice(device) -> Option:
     """In-process executor with frames resident on ``device`` (one B200)."""
-    return _set_executor(lambda s: LocalExecutor(s.p, device))
+    return _set_executor(lambda s: LocalExecutor(s.p, device, store=s.store_))
 
 
 def Spmd(**kw) -> Option:
@@ -115,8 +115,34 @@ def TracePath(path: str) -> Option:
 
 
 #: Share combiners per machine/rank rather than per task (experimental in the
-#: reference, ``exec/session.go:166-176``; no loss recovery in this mode).
+#: reference, ``exec/session.go:166-176``).  On the Local executors the planner tags
+#: the producers with a shared combine key.  On the SPMD executor this is how the
+#: Reduce fast path *always* works — all producer tasks of a rank aggregate into
+#: one per-rank HBM table (``SpmdExecutor._group_table``) — so the option changes
+#: nothing there.
 MachineCombiners = Option(lambda s: setattr(s, "machine_combiners", True))
+
+
+def StoreOpt(store_or_path) -> Option:
+    """Keep task outputs in a :class:`~bigslice_b200.exec.store.Store` (a path
+    selects a ``FileStore``): outputs survive in files, are read back with
+    resumable readers and can be lost/discarded individually (``exec/store.go``)."""
+    def apply(s: "Session"):
+        from .store import FileStore
+        s.store_ = FileStore(store_or_path) if isinstance(store_or_path, str) else store_or_path
+    return Option(apply)
+
+
+def Journal(directory: Optional[str] = None) -> Option:
+    """Record every invocation (Func index, arguments, ``Result`` references) in a
+    compressed on-disk journal (``exec/invocation.py: InvDiskCache``), the way the
+    reference's driver keeps encoded invocations for its workers
+    (``exec/bigmachine_inv_disk_cache.go``).  An argument that cannot be encoded
+    fails the run immediately, naming the type."""
+    def apply(s: "Session"):
+        from .invocation import InvDiskCache
+        s.journal_ = InvDiskCache(directory)
+    return Option(apply)
 
 
 class Session:
@@ -135,6 +161,8 @@ class Session:
         self.eventer_ = NopEventer()
         self.trace_path = ""
         self.machine_combiners = False
+        self.store_ = None
+        self.journal_ = None
         self._executor_factory = None
         self.executor: Optional[Executor] = None
         self.tracer = Tracer()
@@ -152,7 +180,7 @@ class Session:
         if self.max_load_ == 0:
             self.max_load_ = DefaultMaxLoad
         if self._executor_factory is None:
-            self._executor_factory = lambda s: LocalExecutor(s.p, None)
+            self._executor_factory = lambda s: LocalExecutor(s.p, None, store=s.store_)
         self.executor = self._executor_factory(self)
         self._shutdown = self.executor.start(self)
         self.eventer_.event("bigslice:sessionStart", "executorType", self.executor.name(),
@@ -223,6 +251,14 @@ class Session:
             with self._status_lock:
                 inv = funcv.invocation(location, *args)
             einv = ExecInvocation(inv)
+            if self.journal_ is not None:
+                from .invocation import encode_invocation
+                try:
+                    self.journal_.get_or_create(inv.index, lambda w: w.write(encode_invocation(einv))).close()
+                except errors.Error:
+                    raise
+                except Exception as e:  # noqa: BLE001
+                    raise errors.fatal("session.run: invocation %d cannot be encoded: %s" % (inv.index, e), e)
 
             def do_compile(ei):
                 sl = ei.invoke()

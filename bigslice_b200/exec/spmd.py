@@ -203,6 +203,29 @@ class SpmdExecutor(LocalExecutor):
             raise errors.fatal("bigslice.Func registry changed after session start (%d -> %d)"
                                % (self.registry_size, n))
 
+    def health(self) -> dict:
+        """This rank's "machine" line: HBM, exchange counters, pool state (the
+        reference reports mem/disk/load per machine, exec/slicemachine.go:238-257)."""
+        rec = {"rank": self.rank, "world": self.world, "device": str(self.device),
+               "exchanges": len(self.exchange_log), "hints": len(self.card_hints)}
+        if self.device is not None and self.device.type == "cuda":
+            free, total = torch.cuda.mem_get_info(self.device)
+            rec.update(hbm_used_gib=round((total - free) / 2**30, 2), hbm_total_gib=round(total / 2**30, 2),
+                       hbm_allocated_gib=round(torch.cuda.memory_allocated(self.device) / 2**30, 2))
+        if self.rx is not None:
+            rec.update(rx=dict(self.rx.stats), rx_arena_mib=self.rx.arena_bytes >> 20)
+        return rec
+
+    def status_lines(self) -> List[str]:
+        h = self.health()
+        mem = ""
+        if "hbm_total_gib" in h:
+            mem = " hbm %.1f/%.1f GiB" % (h["hbm_used_gib"], h["hbm_total_gib"])
+        rx = ""
+        if "rx" in h:
+            rx = " exchanges %d (graph %d)" % (h["rx"]["exchanges"], h["rx"]["graph_launches"])
+        return ["rank%d/%d %s%s%s" % (h["rank"], h["world"], h["device"], mem, rx)]
+
     def owner(self, shard: int) -> int:
         return shard % self.world
 

@@ -120,3 +120,35 @@ def test_exclusive_takes_whole_device():
     sess = bs.start(MultiDevice([CPU], procs_per_device=4), bs.Parallelism(4))
     slicetest.run(bs.Map(bs.Const(6, torch.arange(6)), slow, bs.Exclusive, out=[bs.int64]), session=sess)
     assert peak[0] == 1
+
+
+@pytest.mark.gpu
+def test_multidevice_executor_on_real_gpus():
+    """The resource manager on actual devices: frames resident in HBM, per-device
+    health polling (free/total HBM), device loss -> resident tasks LOST ->
+    recomputed on the surviving device.  On a one-GPU box the same device is
+    registered twice (two logical 'machines' sharing it)."""
+    n = torch.cuda.device_count()
+    devs = [torch.device("cuda", i) for i in range(min(n, 2))]
+    if len(devs) == 1:
+        devs = devs * 2
+    ex = MultiDeviceExecutor(devs, procs_per_device=2)
+    keys = torch.arange(200000) % 1000
+    vals = torch.ones(200000, dtype=torch.int64)
+
+    @bs.Func
+    def job():
+        return bs.Reduce(bs.Map(bs.Const(8, keys, vals), lambda k, v: (k % 100, v)), bs.ops.add)
+    from bigslice_b200.exec.session import _set_executor
+    with bs.start(_set_executor(lambda s: ex), bs.Parallelism(4)) as sess:
+        r = sess.run(job)
+        assert all(f.device.type == "cuda" for f in r.frames())
+        assert dict(r.rows()) == {k: 2000 for k in range(100)}
+        polled = ex.mgr.poll()
+        assert len(polled) == 2 and all(p["hbm_total"] > 0 and p["hbm_free"] > 0 for p in polled)
+        assert any("hbm" in line for line in ex.mgr.status())
+        lost = ex.lose_device(0)          # everything resident on device 0 is gone
+        assert lost >= 0
+        r2 = sess.run(job)                # recomputed on what is left
+        assert dict(r2.rows()) == {k: 2000 for k in range(100)}
+        assert ex.mgr.devs[0].health == dm.LOST

@@ -390,3 +390,27 @@ def test_start_gate_never_blocks_dependent_work():
     with bs.start(bs.Local, bs.Parallelism(2)) as sess:
         rows = sess.run(two).rows()
     assert len(rows) == 4 and time.time() - t0 < 10
+
+
+def test_store_and_journal_session_options(tmp_path):
+    """StoreOpt: task outputs live in files of a FileStore; Journal: every
+    invocation is recorded (and an unencodable argument fails the run)."""
+    import torch
+    import bigslice_b200 as bs
+    from bigslice_b200.exec.invocation import decode_invocation
+
+    @bs.Func
+    def job(n: int, tag):
+        return bs.Reduce(bs.Const(2, torch.arange(n) % 5, torch.ones(n, dtype=torch.int64)), bs.ops.add)
+    store_dir, jdir = str(tmp_path / "store"), str(tmp_path / "journal")
+    with bs.start(bs.Local, bs.StoreOpt(store_dir), bs.Journal(jdir)) as sess:
+        r = sess.run(job, 50, "x")
+        assert dict(r.rows()) == {k: 10 for k in range(5)}
+        files = [os.path.join(d, f) for d, _, fs in os.walk(store_dir) for f in fs]
+        assert files, "no task output was written to the store"
+        assert r.inv_index in sess.journal_
+        with sess.journal_.get_or_create(r.inv_index, lambda w: None) as fh:
+            inv = decode_invocation(fh.read())
+        assert tuple(inv.inv.args) == (50, "x")
+        with pytest.raises(bs.errors.Error):
+            sess.run(job, 5, lambda: 0)   # a lambda cannot be encoded
