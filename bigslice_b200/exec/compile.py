@@ -218,20 +218,20 @@ pipeline = fused_chain  # the reference's name for it
 
 def _table_lowering(stage: Stage) -> str:
     """``reduce-table`` when the exchange can run as device hash aggregation plus
-    the fused table exchange: default partitioner, a builtin combiner, one int64
-    key and one scalar numeric value."""
+    the fused table exchange: default partitioner, a builtin combiner, a key prefix
+    that packs into 64 bits (one scalar column, or two of at most 4 bytes each;
+    ``ops/keypack.py``) and one scalar numeric value."""
+    from ..ops import keypack
     x = stage.exchange
     if x is None or x.combiner is None or x.partitioner is not None:
         return "frames"
     if getattr(x.combiner, "builtin", None) not in ("add", "min", "max"):
         return "frames"
     typ = stage.head.typ
-    if typ.num_out() != 2 or typ.prefix() != 1:
+    if typ.num_out() != typ.prefix() + 1 or keypack.layout_for(typ) is None:
         return "frames"
-    k, v = typ.out(0), typ.out(1)
-    if getattr(k, "kind", "") != "int" or str(getattr(k, "torch_dtype", "")) != "torch.int64":
-        return "frames"
-    if getattr(v, "kind", "") == "vec":
+    v = typ.out(typ.prefix())
+    if not getattr(v, "is_tensor", False) or getattr(v, "kind", "") in ("vec", "list", "bool"):
         return "frames"
     return "reduce-table"
 

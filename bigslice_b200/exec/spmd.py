@@ -466,13 +466,16 @@ class SpmdExecutor(LocalExecutor):
             return False
         if self.shuffle not in ("fused", "nccl-table"):
             return False
-        from ..ops import gpu
+        from ..ops import gpu, keypack
         from ..parallel import rx
         # the planner decided the shape (exec/compile.py: _table_lowering); the
         # executor adds what depends on the device library
         if task.lowering != "reduce-table":
             return False
-        return task.type.typ.out(1).torch_dtype in gpu.VTYPE and task.num_partition <= rx.MAXP
+        typ = task.type.typ
+        if self.shuffle == "nccl-table" and not keypack.layout_for(typ).plain_int64:
+            return False  # the library baseline hashes plain int64 keys only
+        return typ.out(typ.prefix()).torch_dtype in gpu.VTYPE and task.num_partition <= rx.MAXP
 
     def _hint_key(self, task: Task, what: str = "local") -> tuple:
         """Cardinality hints are keyed on the slice's *creation site* — not on its
@@ -505,7 +508,8 @@ class SpmdExecutor(LocalExecutor):
                     cap = gpu.table_capacity(max(rows, rows_hint, 1 << 15))
                 # pooled: a table emptied by its last reader (clearing exchange or
                 # compaction) is reused without an init pass
-                t = gpu.table_pool().get(cap, task.type.typ.out(1).torch_dtype, task.combiner.builtin,
+                typ = task.type.typ
+                t = gpu.table_pool().get(cap, typ.out(typ.prefix()).torch_dtype, task.combiner.builtin,
                                          self.device)
                 self.group_tables[gid] = t
             return t
@@ -569,8 +573,14 @@ class SpmdExecutor(LocalExecutor):
     def _exchange_table(self, gid: int, head: Task, table, nparts: int, bad: int = 0) -> None:
         from ..frame.deferred import DeferredFrame
         from ..ops import gpu
+        from ..ops import keypack
         typ = head.type.typ
-        vdtype, op = typ.out(1).torch_dtype, head.combiner.builtin
+        lay = keypack.layout_for(typ)
+        vdtype, op = typ.out(typ.prefix()).torch_dtype, head.combiner.builtin
+        # result buffers hold <packed key word, value>; anything but a plain int64
+        # key is unpacked into its key columns when the frame is first looked at
+        fin = None if lay.plain_int64 else (
+            lambda d, n, lay=lay: keypack.unpack(d[0][:n], lay) + [d[1][:n]])
         t0 = time.perf_counter()
         ev0 = self._cuda_event()
         if self.shuffle == "nccl-table" and not (self.world == 1 and nparts == 1):
@@ -602,7 +612,7 @@ class SpmdExecutor(LocalExecutor):
                         self.card_hints[key] = 4 * max(self.card_hints.get(key, 0), int(rep.out_rows[0]), 1 << 14)
                 pend = rx.publish(table.status, cap, on_report=learned)
                 gpu.table_pool().put(table, clean=True)
-                out[0] = [DeferredFrame([ok, ov], typ, self._resolver(pend, gid, head, 0))]
+                out[0] = [DeferredFrame([ok, ov], typ, self._resolver(pend, gid, head, 0), finalize=fin)]
             mode = "table-local"
         else:
             if self._rx_reset or self._want_arena:
@@ -653,12 +663,14 @@ class SpmdExecutor(LocalExecutor):
                         dests.append((j, dt, ok, ov, cap))
                     with span("xchg/enqueue"):
                         pend = rx.exchange(table, nparts, dests, vote=(1 if bad else 0, acc),
-                                           on_report=self._learner(head, lkey, dkeys, nparts))
+                                           on_report=self._learner(head, lkey, dkeys, nparts),
+                                           keymode=lay.mode)
                 else:
                     # first run of this slice: one synchronisation to learn how much
                     # arrives, then everything is sized exactly
                     with span("xchg/first_run_sync"):
-                        probe = rx.exchange_probe(table, nparts, vote=(1 if bad else 0, acc))
+                        probe = rx.exchange_probe(table, nparts, vote=(1 if bad else 0, acc),
+                                                  keymode=lay.mode)
                         rep = probe.resolve()
                     dests = []
                     if rep.error == 0:
@@ -693,7 +705,8 @@ class SpmdExecutor(LocalExecutor):
                 raise errors.fatal("spmd: exchange of %s failed: %s" % (head.name, first_err))
             import weakref
             for (j, dt, ok, ov, cap), dk in zip(dests, dkeys):
-                fr = DeferredFrame([ok, ov], typ, self._resolver(pend, gid, head, j), ready_event=done)
+                fr = DeferredFrame([ok, ov], typ, self._resolver(pend, gid, head, j), ready_event=done,
+                                   finalize=fin)
                 if not first_run:
                     for ent in self._out_sets.get(dk, ()):
                         if ent[0] is ok:
@@ -1008,6 +1021,10 @@ class SpmdExecutor(LocalExecutor):
         nrec = 0
         table = None
         fast = self._table_path_ok(task)
+        if fast:
+            from ..ops import keypack
+            lay = keypack.layout_for(task.type.typ)
+            npre = task.type.typ.prefix()
         try:
             while True:
                 with span("task/read"):
@@ -1020,7 +1037,9 @@ class SpmdExecutor(LocalExecutor):
                         with span("task/group_table"):
                             table = self._group_table(task, len(f))
                     with span("task/combine_launch"):
-                        table.combine(f.col(0), f.col(1))  # async: overlaps the next read
+                        # async: overlaps the next read
+                        table.combine(f.col(0) if lay.plain_int64 else
+                                      keypack.pack([f.col(i) for i in range(npre)], lay), f.col(npre))
                 else:
                     buf.append(0, f)
         finally:

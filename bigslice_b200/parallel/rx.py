@@ -282,17 +282,17 @@ class ReduceExchange:
         return 2 * (pl * self.world * 16 * int(region_rows) + 256)
 
     # -- the exchange ----------------------------------------------------------------
-    def _enqueue_send(self, pe: RxPeers, table, nparts: int) -> None:
+    def _enqueue_send(self, pe: RxPeers, table, nparts: int, keymode: int = 0) -> None:
         lib, st = self.lib, c_void_p(self.state.data_ptr())
         s = gpu._stream()
         bits = c_ull(table.identity_bits())
         self._chk(lib.bs_rx_scatter(ctypes.byref(pe), st, c_void_p(table.slots.data_ptr()), c_ll(table.total),
-                                    c_int(nparts), c_int(1), bits, c_void_p(table.status.data_ptr()), s),
-                  "rx_scatter")
+                                    c_int(nparts), c_int(1), bits, c_void_p(table.status.data_ptr()),
+                                    c_int(keymode), s), "rx_scatter")
         self._chk(lib.bs_rx_wait(ctypes.byref(pe), st, c_int(nparts), s), "rx_wait")
 
-    def _enqueue(self, pe: RxPeers, table, nparts: int, dests, max_rows: int) -> None:
-        self._enqueue_send(pe, table, nparts)
+    def _enqueue(self, pe: RxPeers, table, nparts: int, dests, max_rows: int, keymode: int = 0) -> None:
+        self._enqueue_send(pe, table, nparts, keymode)
         self._enqueue_recv(pe, table, nparts, dests, max_rows)
 
     def _enqueue_recv(self, pe: RxPeers, table, nparts: int, dests, max_rows: int) -> None:
@@ -315,7 +315,7 @@ class ReduceExchange:
         self._chk(lib.bs_rx_end(ctypes.byref(pe), st, c_int(n), stp, caps, bits, self.xring.ptr,
                                 c_int(NSLOTS), c_int(1), s), "rx_end")
 
-    def exchange_probe(self, table, nparts: int, vote: Tuple[int, int] = (0, 0)) -> Pending:
+    def exchange_probe(self, table, nparts: int, vote: Tuple[int, int] = (0, 0), keymode: int = 0) -> Pending:
         """First half of an exchange whose destination sizes are unknown (first
         run of a slice): scatter + wait, then publish how many rows arrived for
         every local shard.  Call on the exchange stream; follow with
@@ -324,7 +324,7 @@ class ReduceExchange:
         lib, st = self.lib, c_void_p(self.state.data_ptr())
         s = gpu._stream()
         self._chk(lib.bs_rx_set_vote(st, c_ull(vote[0]), c_ull(vote[1]), s), "rx_set_vote")
-        self._enqueue_send(pe, table, nparts)
+        self._enqueue_send(pe, table, nparts, keymode)
         pl = pe.shards_per_rank
         stp, caps = (c_void_p * pl)(), (c_ll * pl)()
         self._chk(lib.bs_rx_end(ctypes.byref(pe), st, c_int(pl), stp, caps, c_ull(0), self.xring.ptr,
@@ -350,7 +350,7 @@ class ReduceExchange:
         return p
 
     def exchange(self, table, nparts: int, dests: Sequence[tuple], vote: Tuple[int, int] = (0, 0),
-                 on_report=None) -> Pending:
+                 on_report=None, keymode: int = 0) -> Pending:
         """Enqueue one exchange of ``table`` on the exchange stream (the caller
         has made that stream wait for the producers' combines).
 
@@ -372,7 +372,7 @@ class ReduceExchange:
             self._chk(lib.bs_rx_set_vote(c_void_p(self.state.data_ptr()), c_ull(vote[0]), c_ull(vote[1]), s),
                       "rx_set_vote")
             key = (table.slots.data_ptr(), table.total, table.status.data_ptr(), nparts, rows, table.vdtype,
-                   table.op) + tuple((j, dt.slots.data_ptr(), dt.total, dt.status.data_ptr(), ok.data_ptr(),
+                   table.op, keymode) + tuple((j, dt.slots.data_ptr(), dt.total, dt.status.data_ptr(), ok.data_ptr(),
                                       ov.data_ptr(), cap) for j, dt, ok, ov, cap in dests)
             g = self.graphs.get(key) if self.use_graphs else None
             if g is not None:
@@ -382,7 +382,7 @@ class ReduceExchange:
                 # second occurrence of the same launch sequence: capture it
                 self._chk(lib.bs_graph_begin(s), "graph_begin")
                 try:
-                    self._enqueue(pe, table, nparts, dests, max_rows)
+                    self._enqueue(pe, table, nparts, dests, max_rows, keymode)
                 finally:
                     ex, nodes = c_void_p(), c_ll()
                     rc = lib.bs_graph_end(s, ctypes.byref(ex), ctypes.byref(nodes))
@@ -396,7 +396,7 @@ class ReduceExchange:
                 self._chk(lib.bs_graph_launch(c_void_p(g.exec), c_ll(g.nodes), s), "graph_launch")
                 self.stats["graph_launches"] += 1
             else:
-                self._enqueue(pe, table, nparts, dests, max_rows)
+                self._enqueue(pe, table, nparts, dests, max_rows, keymode)
                 self.seen[key] = self.seen.get(key, 0) + 1
                 if len(self.seen) > 256:
                     self.seen.clear()

@@ -103,8 +103,16 @@ __device__ __forceinline__ unsigned char* rx_region(const RxPeers& pe, int dst_r
   return pe.arena[dst_rank] + (unsigned long long)par * pe.half_bytes + idx * pe.region_rows * 16ULL;
 }
 
-__device__ __forceinline__ int rx_dest(long long key, int P) {
-  return (int)(bs_murmur3_u64((uint64_t)key, 0u) % (uint32_t)P);
+// Destination shard of a packed key (bigslice_b200/ops/keypack.py): the same
+// value Frame.hash computes from the key columns — mode 0: one 8-byte column,
+// mode 1: one column of <= 4 bytes (its 32-bit image), mode 2: two such columns
+// (XOR of the per-column hashes, frame/frame.go:389-401).
+__device__ __forceinline__ int rx_dest(long long key, int P, int mode) {
+  uint32_t h;
+  if (mode == 0) h = bs_murmur3_u64((uint64_t)key, 0u);
+  else if (mode == 1) h = bs_murmur3_u32((uint32_t)key, 0u);
+  else h = bs_murmur3_u32((uint32_t)key, 0u) ^ bs_murmur3_u32((uint32_t)((uint64_t)key >> 32), 0u);
+  return (int)(h % (uint32_t)P);
 }
 
 // ---------------------------------------------------------------------------
@@ -167,7 +175,7 @@ __device__ __forceinline__ void rx_flush(const RxPeers& pe, RxState* st, int par
 
 __global__ void __launch_bounds__(RX_THREADS, 1) rx_scatter_kernel(
     RxPeers pe, RxState* st, int4* __restrict__ slots, long long total, int P, int clear,
-    unsigned long long clear_bits, BsCombineStatus* tst) {
+    unsigned long long clear_bits, BsCombineStatus* tst, int keymode) {
   const unsigned long long my_status = st->vote_in[0], my_fp = st->vote_in[1];
   extern __shared__ __align__(128) unsigned char rx_smem[];
   int4* stage = (int4*)rx_smem;  // [P][B] rows
@@ -216,7 +224,7 @@ __global__ void __launch_bounds__(RX_THREADS, 1) rx_scatter_kernel(
         dest[j] = -1;
         rank[j] = 0;
         if (__any_sync(0xffffffffu, occupied)) {
-          const int d = ok ? rx_dest(key, P) : 0;
+          const int d = ok ? rx_dest(key, P, keymode) : 0;
           rank[j] = rx_rank(hist, d, ok);
           if (ok) dest[j] = d;
           if (occupied) {
@@ -291,7 +299,7 @@ __global__ void __launch_bounds__(RX_THREADS, 1) rx_scatter_kernel(
     if (!status && tst->failed) status = RX_TABLE_OVERFLOW;
     if (!status && st->error) status = (unsigned long long)st->error;
     if (!status && tst->has_special) {
-      const int d = rx_dest(BS_EMPTY_KEY, P);
+      const int d = rx_dest(BS_EMPTY_KEY, P, keymode);
       const unsigned long long at = atomicAdd(&st->cursor[d], 1ULL);
       if (at + 1 > pe.region_rows) {
         atomicMax(&st->need_rows, at + 1);
@@ -571,7 +579,7 @@ BS_EXPORT int bs_rx_set_vote(void* state_d, unsigned long long status, unsigned 
 }
 
 BS_EXPORT int bs_rx_scatter(const void* peers_h, void* state_d, void* slots, long long total, int nparts,
-                            int clear, unsigned long long clear_bits, void* table_status,
+                            int clear, unsigned long long clear_bits, void* table_status, int keymode,
                             cudaStream_t stream) {
   RxPeers pe = *(const RxPeers*)peers_h;
   if (pe.world > RX_MAXW || nparts > RX_MAXP || nparts < 1) return -1;
@@ -590,7 +598,7 @@ BS_EXPORT int bs_rx_scatter(const void* peers_h, void* state_d, void* slots, lon
   int blocks = (int)(ntiles < sms ? ntiles : sms);
   if (blocks < 1) blocks = 1;
   rx_scatter_kernel<<<blocks, RX_THREADS, smem, stream>>>(pe, st, (int4*)slots, total, nparts, clear, clear_bits,
-                                                          (BsCombineStatus*)table_status);
+                                                          (BsCombineStatus*)table_status, keymode);
   BS_LAUNCH_CHECK();
   return 0;
 }

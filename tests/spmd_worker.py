@@ -47,6 +47,24 @@ def join(nshard: int):
     return bs.Cogroup(a, b)
 
 
+PA = (torch.arange(N) % 11).to(torch.int32) - 5
+PB = ((torch.arange(N) % 7).to(torch.float32) - 3) / 2
+P8 = ((torch.arange(N) * 37) % 200 - 100).to(torch.int8)
+
+
+@bs.Func
+def pairsum(nshard: int):
+    """Two-column key (int32, float32): packs into one 64-bit word on the device path."""
+    s = bs.Prefixed(bs.Const(nshard, PA, PB, torch.ones(N, dtype=torch.int64)), 2)
+    return bs.Reduce(s, bs.ops.add)
+
+
+@bs.Func
+def bytemax(nshard: int):
+    """int8 key, float32 value, max."""
+    return bs.Reduce(bs.Const(nshard, P8, (torch.arange(N) % 1000).to(torch.float32)), bs.ops.max)
+
+
 @bs.Func
 def bjoin(nshard: int):
     large = bs.Reshuffle(bs.Const(nshard, KEYS, torch.arange(N, dtype=torch.float32)))
@@ -369,6 +387,18 @@ def main():
     for k in range(0, 97, 2):
         wantj.setdefault(k, ([], []))[1].append(k * 10)
     out["join_ok"] = got == {k: (sorted(a), sorted(b)) for k, (a, b) in wantj.items()}
+    rows = ex.gather(sess.run(pairsum, world))
+    wantp = {}
+    for a, b in zip(PA.tolist(), PB.tolist()):
+        wantp[(a, b)] = wantp.get((a, b), 0) + 1
+    out["pairsum_ok"] = {(a, b): c for a, b, c in rows} == wantp and len(rows) == len(wantp)
+    out["pairsum_mode"] = ex.exchange_log[-1]["mode"] if ex.exchange_log else ""
+    rows = ex.gather(sess.run(bytemax, 2 * world))
+    wantm = {}
+    for k, v in zip(P8.tolist(), (torch.arange(N) % 1000).tolist()):
+        wantm[k] = max(wantm.get(k, -1.0), float(v))
+    out["bytemax_ok"] = dict(rows) == wantm
+    out["bytemax_mode"] = ex.exchange_log[-1]["mode"] if ex.exchange_log else ""
     rows = ex.gather(sess.run(bjoin, 2 * world))
     gotb = {k: (sorted(a), sorted(b)) for k, a, b in rows}
     out["bjoin_ok"] = (len(rows) == len(gotb) and
