@@ -53,14 +53,17 @@ def main():
         _sorted = [c.index_select(0, _order).contiguous() for c in cols]
         _in, _out = _cnt.tolist(), _rc.tolist()
         _recv = [torch.empty(int(_rc.sum()), dtype=c.dtype, device=dev) for c in cols]
-        for mode in ("fused", "nccl", "a2a_only"):
+        for mode in ("fused", "fused_cols", "nccl", "a2a_only"):
             times = []
             for it in range(a.iters + 2):
                 torch.cuda.synchronize()
                 dist.barrier()
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record()
-                if mode == "fused":
+                if mode == "fused":        # row records + TMA bulk stores (+ unpack on arrival)
+                    got = peers.exchange(cols, nparts, nkeys=1)
+                    nrecv = sum(c[0].shape[0] for c in got.values())
+                elif mode == "fused_cols":  # round-1 column mover (zero-copy views of the arena)
                     got = peers.exchange(cols, nparts, nkeys=1, zero_copy=True)
                     nrecv = sum(c[0].shape[0] for c in got.values())
                 elif mode == "a2a_only":

@@ -162,6 +162,10 @@ class PeerGroup:
         order."""
         if nparts > MAXP or len(cols) > MAXC or nkeys > MAXK:
             raise ExchangeError("exchange shape outside fused-kernel limits")
+        if self.ROW_RECORDS and not skip_empty and not zero_copy:
+            got = self.exchange_rows(cols, nparts, nkeys, ids)
+            if got is not None:
+                return got
         cols = [c.contiguous() for c in cols]
         n = int(cols[0].shape[0]) if cols else 0
         desc = []
@@ -170,6 +174,69 @@ class PeerGroup:
                                      int(np.prod(c.shape[1:])) if c.dim() > 1 else 1)
             desc.append((c.data_ptr(), rb, rb, c.dtype, tuple(c.shape[1:])))
         return self.exchange_raw(desc, n, nparts, nkeys, ids, skip_empty, zero_copy, keep=cols)
+
+    ROW_RECORDS = os.environ.get("BIGSLICE_XCHG", "rows") != "cols"
+
+    def exchange_rows(self, cols: Sequence[torch.Tensor], nparts: int, nkeys: int = 1,
+                      ids: Optional[torch.Tensor] = None, vote: Tuple[int, int] = (0, 0)
+                      ) -> Optional[Dict[int, List[torch.Tensor]]]:
+        """Row-record exchange (``xchg_scatter_rows``: rows packed into 16-byte
+        aligned records in shared memory, per-destination write combining, TMA bulk
+        stores over NVLink; ``xchg_unpack_rows`` on arrival).  Returns None when the
+        shape is outside the kernel's limits (the column mover handles it)."""
+        cols = [c.contiguous() for c in cols]
+        n = int(cols[0].shape[0]) if cols else 0
+        spec = XcSpec()
+        spec.n, spec.nparts, spec.ncols, spec.nkeys = n, nparts, len(cols), nkeys
+        if ids is not None:
+            ids = ids.to(torch.int64).contiguous()
+            spec.ids = ids.data_ptr()
+        rbs = []
+        for i, c in enumerate(cols):
+            rb = c.element_size() * (int(np.prod(c.shape[1:])) if c.dim() > 1 else 1)
+            spec.cols[i], spec.es[i], spec.stride[i] = c.data_ptr(), rb, rb
+            rbs.append(rb)
+        rec = int(self.lib.bs_xc_rec_bytes(ctypes.byref(spec)))
+        if nparts > 64 or nparts * rec * 8 > 128 * 1024:
+            return None
+        self.epoch += 1
+        rc = self.lib.bs_xc_exchange_rows(ctypes.byref(self.peers), ctypes.byref(spec),
+                                          c_void_p(self.plan.data_ptr()), c_ull(self.epoch),
+                                          c_ull(vote[0]), c_ull(vote[1]), gpu._stream())
+        if rc == -3:
+            self.epoch -= 1
+            return None
+        self._chk(rc, "exchange_rows")
+        with span("xchg/plan_d2h_sync"):
+            plan = self.plan.cpu().numpy()
+        err = int(plan[self.off_error:self.off_error + 4].view(np.int32)[0])
+        if err == 1:
+            raise ExchangeError("receive arena overflow (%d bytes): raise arena_bytes" % self.arena_bytes)
+        if err in (3, 4):
+            raise ExchangeVoteError(err)
+        if err:
+            raise ExchangeError("peer exchange aborted (timeout or peer failure)")
+        recv_total = plan[self.off_recv_total:self.off_recv_total + 8 * MAXP].view(np.int64)
+        recv_off = plan[self.off_recv_off:self.off_recv_off + 8 * MAXP * MAXC].view(np.uint64).reshape(MAXP, MAXC)
+        send = plan[self.off_send_count:self.off_send_count + 8 * MAXP].view(np.int64)
+        self.last_sent = int(send[:nparts].sum())
+        self.stats["exchanges"] += 1
+        self.stats["rows_sent"] += self.last_sent
+        self.stats["bytes_sent"] += self.last_sent * rec
+        out: Dict[int, List[torch.Tensor]] = {}
+        for d in range(self.rank, nparts, self.world):
+            rows = int(recv_total[d])
+            got = [torch.empty((rows,) + tuple(c.shape[1:]), dtype=c.dtype, device=self.device) for c in cols]
+            if rows:
+                ospec = XcSpec()
+                ospec.ncols = len(cols)
+                for i, (g, rb) in enumerate(zip(got, rbs)):
+                    ospec.cols[i], ospec.es[i], ospec.stride[i] = g.data_ptr(), rb, rb
+                self._chk(self.lib.bs_xc_unpack_rows(c_void_p(self._arena.value + int(recv_off[d, 0])),
+                                                     c_ll(rows), ctypes.byref(ospec), gpu._stream()),
+                          "unpack_rows")
+            out[d] = got
+        return out
 
     def exchange_raw(self, desc, n: int, nparts: int, nkeys: int = 1,
                      ids: Optional[torch.Tensor] = None, skip_empty: bool = False,
