@@ -760,6 +760,8 @@ __global__ void __launch_bounds__(XR_THREADS, 1) xchg_scatter_rows_kernel(XcPeer
   const int tid = threadIdx.x;
   const int rec = rc.rec_bytes;
   const int B = XR_BYTES / (P * rec);  // records per destination buffer
+  bool small_cols = true;
+  for (int c = 0; c < sp.ncols; ++c) small_cols = small_cols && (sp.es[c] == 4 || sp.es[c] == 8);
   if (tid < XR_MAXP) fill[tid] = 0;
   __syncthreads();
   auto flush = [&](int d, int n) {  // one thread: n staged records of destination d -> peer memory
@@ -808,19 +810,41 @@ __global__ void __launch_bounds__(XR_THREADS, 1) xchg_scatter_rows_kernel(XcPeer
           if (k >= 0 && k < room) {
             unsigned char* out = xr_stage + ((size_t)d * B + fill[d] + k) * rec;
             const long long r = row0 + tid + (long long)j * XR_THREADS;
-            for (int c = 0; c < sp.ncols; ++c) {
-              const unsigned char* src = sp.cols[c] + (size_t)r * sp.stride[c];
-              const int es = sp.es[c];
-              unsigned char* o = out + rc.off[c];
-              if (es == 4) *(int*)o = *(const int*)src;
-              else if (es == 8) *(long long*)o = *(const long long*)src;
-              else if (es == 16) *(int4*)o = *(const int4*)src;
-              else if (es % 16 == 0 && ((uintptr_t)src & 15) == 0)
-                for (int q = 0; q < es; q += 16) *(int4*)(o + q) = *(const int4*)(src + q);
-              else if (es % 4 == 0 && ((uintptr_t)src & 3) == 0)
-                for (int q = 0; q < es; q += 4) *(int*)(o + q) = *(const int*)(src + q);
-              else
-                for (int q = 0; q < es; ++q) o[q] = src[q];
+            if (small_cols) {
+              // all columns are 4 or 8 bytes wide: issue every column's load before
+              // the first store (independent loads in flight instead of a chain of
+              // dependent round trips through the loop)
+              unsigned long long v[XC_MAXC];
+#pragma unroll
+              for (int c = 0; c < XC_MAXC; ++c) {
+                if (c < sp.ncols) {
+                  const unsigned char* src = sp.cols[c] + (size_t)r * sp.stride[c];
+                  v[c] = sp.es[c] == 8 ? *(const unsigned long long*)src
+                                       : (unsigned long long)*(const unsigned int*)src;
+                }
+              }
+#pragma unroll
+              for (int c = 0; c < XC_MAXC; ++c) {
+                if (c < sp.ncols) {
+                  if (sp.es[c] == 8) *(unsigned long long*)(out + rc.off[c]) = v[c];
+                  else *(unsigned int*)(out + rc.off[c]) = (unsigned int)v[c];
+                }
+              }
+            } else {
+              for (int c = 0; c < sp.ncols; ++c) {
+                const unsigned char* src = sp.cols[c] + (size_t)r * sp.stride[c];
+                const int es = sp.es[c];
+                unsigned char* o = out + rc.off[c];
+                if (es == 4) *(int*)o = *(const int*)src;
+                else if (es == 8) *(long long*)o = *(const long long*)src;
+                else if (es == 16) *(int4*)o = *(const int4*)src;
+                else if (es % 16 == 0 && ((uintptr_t)src & 15) == 0)
+                  for (int q = 0; q < es; q += 16) *(int4*)(o + q) = *(const int4*)(src + q);
+                else if (es % 4 == 0 && ((uintptr_t)src & 3) == 0)
+                  for (int q = 0; q < es; q += 4) *(int*)(o + q) = *(const int*)(src + q);
+                else
+                  for (int q = 0; q < es; ++q) o[q] = src[q];
+              }
             }
             dest[j] = -1;  // done
           } else if (k >= room) {

@@ -353,6 +353,10 @@ def async_table_checks(sess, ex, world, rank):
 
 
 def main():
+    import faulthandler
+    # a hang prints every thread's stack and exits instead of running into the
+    # harness timeout with no information
+    faulthandler.dump_traceback_later(int(os.environ.get("BS_TEST_WATCHDOG", "420")), exit=True)
     device = os.environ.get("BS_TEST_DEVICE", "cpu")
     shuffle = os.environ.get("BS_TEST_SHUFFLE", "auto")
     sess = bs.start(bs.Spmd(device=None if device == "cpu" else "cuda", shuffle=shuffle,
@@ -426,6 +430,7 @@ def main():
     except Exception:
         out["launches"] = 0
     sess.shutdown()
+    faulthandler.cancel_dump_traceback_later()
     path = os.environ["BS_TEST_OUT"] + ".%d" % rank
     with open(path, "w") as fh:
         json.dump(out, fh)
