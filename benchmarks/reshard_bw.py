@@ -61,7 +61,7 @@ def main():
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record()
                 if mode == "fused":        # row records + TMA bulk stores (+ unpack on arrival)
-                    got = peers.exchange(cols, nparts, nkeys=1)
+                    got = peers.exchange_rows(cols, nparts, nkeys=1)
                     nrecv = sum(c[0].shape[0] for c in got.values())
                 elif mode == "fused_cols":  # round-1 column mover (zero-copy views of the arena)
                     got = peers.exchange(cols, nparts, nkeys=1, zero_copy=True)

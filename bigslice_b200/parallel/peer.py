@@ -175,7 +175,10 @@ class PeerGroup:
             desc.append((c.data_ptr(), rb, rb, c.dtype, tuple(c.shape[1:])))
         return self.exchange_raw(desc, n, nparts, nkeys, ids, skip_empty, zero_copy, keep=cols)
 
-    ROW_RECORDS = os.environ.get("BIGSLICE_XCHG", "rows") != "cols"
+    #: generic frames move column by column by default; ``BIGSLICE_XCHG=rows`` selects
+    #: the row-record kernel (TMA bulk stores), which measured slower at N=2
+    #: (profiles/r2_reshard_bw_n2.jsonl) and stays opt-in until it wins
+    ROW_RECORDS = os.environ.get("BIGSLICE_XCHG", "cols") == "rows"
 
     def exchange_rows(self, cols: Sequence[torch.Tensor], nparts: int, nkeys: int = 1,
                       ids: Optional[torch.Tensor] = None, vote: Tuple[int, int] = (0, 0)
