@@ -548,15 +548,16 @@ class SpmdExecutor(LocalExecutor):
         if self.board.wait_all(self.xseq, self.exchange_timeout) is None:
             raise errors.TaskLostError("spmd: rank(s) %s unreachable" % self.board.missing(self.xseq))
 
-    def _board_vote(self, bad: int, acc: int, fps, head: Task) -> None:
-        """Host-side agreement for one exchange: post my status + fingerprint and
-        read everyone else's from shared memory (no collective, no GPU)."""
+    def _board_vote(self, bad: int, acc: int, fps, head: Task, extra: int = 0) -> List[int]:
+        """Host-side agreement for one exchange: post my status + fingerprint (and
+        one free integer) and read everyone else's from shared memory (no
+        collective, no GPU).  Returns every rank's integer."""
         if self.board is None:
             if bad:
                 raise errors.fatal("spmd: a producer of %s failed" % head.name)
-            return
+            return [extra]
         self.xseq += 1
-        self.board.post(self.xseq, int(bad), acc)
+        self.board.post(self.xseq, int(bad), acc, int(extra))
         with span("xchg/board_vote"):
             votes = self.board.wait_all(self.xseq, self.exchange_timeout)
         if votes is None:
@@ -569,6 +570,7 @@ class SpmdExecutor(LocalExecutor):
             where = ", ".join("inv%d at %s (func #%d)" % f[:3] for f in fps) or "an earlier invocation"
             raise errors.fatal("ranks issued different invocations (%s, rank %d); SPMD programs must "
                                "run identical Session.run sequences" % (where, self.rank))
+        return [v[2] for v in votes]
 
     def _exchange_table(self, gid: int, head: Task, table, nparts: int, bad: int = 0) -> None:
         from ..frame.deferred import DeferredFrame
@@ -637,7 +639,7 @@ class SpmdExecutor(LocalExecutor):
             after = torch.cuda.Event()
             after.record(torch.cuda.default_stream(self.device))
             rx.stream.wait_event(after)
-            pl, region_rows = rx.geometry(nparts)
+            pl, _ = rx.geometry(nparts)
             locals_ = [j for j in range(pl) if self.rank + j * self.world < nparts]
             dkeys = [self._hint_key(head, "dest%d" % (self.rank + j * self.world)) for j in locals_]
             hints = [self.card_hints.get(k) for k in dkeys]
@@ -647,11 +649,17 @@ class SpmdExecutor(LocalExecutor):
             with torch.cuda.stream(rx.stream):
                 if all(h is not None for h in hints):
                     dests = []
+                    # destination tables that do not fit in L2 are combined region by
+                    # region (rows are bucketed by region at the source); the region count
+                    # must be the same on every rank: every rank derives it from the
+                    # largest shard's hint, which the report of the last run carried
+                    regions = int(self.card_hints.get(self._hint_key(head, "regions"), 1))
                     for j, h, dk in zip(locals_, hints, dkeys):
                         # The destination table and the output buffers are tied to the
                         # slice (not pooled): the same pointers every step, so the
                         # captured graph is replayed instead of re-recorded.
-                        dcap = gpu.table_capacity(int(h * 1.15) + 1024)
+                        dcap = gpu.quantise_capacity(
+                            (gpu.table_capacity(int(h * 1.15) + 1024) + regions - 1) // regions) * regions
                         dt = self._dest_tables.get((dk, dcap, vdtype, op))
                         if dt is None:
                             for k in [k for k in self._dest_tables if k[0] == dk]:
@@ -664,7 +672,7 @@ class SpmdExecutor(LocalExecutor):
                     with span("xchg/enqueue"):
                         pend = rx.exchange(table, nparts, dests, vote=(1 if bad else 0, acc),
                                            on_report=self._learner(head, lkey, dkeys, nparts),
-                                           keymode=lay.mode)
+                                           keymode=lay.mode, regions=regions)
                 else:
                     # first run of this slice: one synchronisation to learn how much
                     # arrives, then everything is sized exactly
@@ -698,7 +706,13 @@ class SpmdExecutor(LocalExecutor):
                 self.fault_hook("after_enqueue", str(head.name))
             # host-side agreement (shared memory): a fatal producer failure on any
             # rank fails the invocation everywhere, now, without draining the GPU
-            self._board_vote(bad, acc, fps, head)
+            # the vote also carries the size of my largest destination table: every rank
+            # derives the same region count for the *next* run of this slice from it
+            mine = max([gpu.table_capacity(int(self.card_hints[k] * 1.15) + 1024) * 16
+                        for k in dkeys if self.card_hints.get(k) is not None] or [0])
+            sizes = self._board_vote(bad, acc, fps, head, extra=mine)
+            if all(x > 0 for x in sizes):
+                self.card_hints[self._hint_key(head, "regions")] = rx.regions_for(max(sizes), nparts)
             if first_err is not None:
                 if first_err.retriable:
                     raise errors.TaskLostError("spmd: exchange of %s was lost (%s)" % (head.name, first_err))

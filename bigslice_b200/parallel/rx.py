@@ -50,7 +50,7 @@ RETRIABLE = (LANDING_OVERFLOW, TABLE_OVERFLOW, TIMEOUT, DEST_OVERFLOW)
 class RxPeers(ctypes.Structure):
     _fields_ = [("world", c_int), ("rank", c_int), ("ctrl", c_void_p * MAXW),
                 ("arena", c_void_p * MAXW), ("region_rows", c_ull), ("half_bytes", c_ull),
-                ("shards_per_rank", c_int), ("pad", c_int)]
+                ("shards_per_rank", c_int), ("regions", c_int)]
 
 
 class ExchangeFailed(RuntimeError):
@@ -263,23 +263,34 @@ class ReduceExchange:
         self.pring.close()
 
     # -- geometry ------------------------------------------------------------------
-    def geometry(self, nparts: int) -> Tuple[int, int]:
-        """(shards per rank, rows per landing region) for ``nparts`` shards."""
+    def geometry(self, nparts: int, regions: int = 1) -> Tuple[int, int]:
+        """(shards per rank, rows per landing region) for ``nparts`` shards whose
+        destination tables are split into ``regions`` L2-sized parts."""
         pl = (nparts + self.world - 1) // self.world
         half = (self.arena_bytes // 2) & ~0xFF
-        rows = half // (pl * self.world * 16)
+        rows = half // (pl * regions * self.world * 16)
         return pl, rows
 
-    def _peers_for(self, nparts: int) -> RxPeers:
-        pl, rows = self.geometry(nparts)
+    def _peers_for(self, nparts: int, regions: int = 1) -> RxPeers:
+        pl, rows = self.geometry(nparts, regions)
         p = self.peers
-        p.shards_per_rank, p.region_rows = pl, rows
+        p.shards_per_rank, p.region_rows, p.regions = pl * regions, rows, regions
         p.half_bytes = (self.arena_bytes // 2) & ~0xFF
         return p
 
-    def bytes_for(self, nparts: int, region_rows: int) -> int:
+    def bytes_for(self, nparts: int, region_rows: int, regions: int = 1) -> int:
         pl = (nparts + self.world - 1) // self.world
-        return 2 * (pl * self.world * 16 * int(region_rows) + 256)
+        return 2 * (pl * regions * self.world * 16 * int(region_rows) + 256)
+
+    @staticmethod
+    def regions_for(table_bytes: int, nparts: int, l2_part: int = 48 << 20) -> int:
+        """Table regions per destination shard: the smallest power of two that makes
+        a region's part of the table at most ``l2_part`` bytes (so combining on
+        arrival runs out of L2), bounded by the kernel's 64 virtual partitions."""
+        r = 1
+        while table_bytes // r > l2_part and r < 8 and nparts * r * 2 <= MAXP:
+            r *= 2
+        return r
 
     # -- the exchange ----------------------------------------------------------------
     def _enqueue_send(self, pe: RxPeers, table, nparts: int, keymode: int = 0) -> None:
@@ -303,10 +314,15 @@ class ReduceExchange:
         n = len(dests)
         stp = (c_void_p * max(n, 1))()
         caps = (c_ll * max(n, 1))()
+        R = int(pe.regions)
         for i, (j, dt, ok, ov, cap) in enumerate(dests):
-            self._chk(lib.bs_rx_combine(ctypes.byref(pe), st, c_int(j), vt, op, c_void_p(dt.slots.data_ptr()),
-                                        c_ll(dt.total), c_void_p(dt.status.data_ptr()), c_ll(max_rows), s),
-                      "rx_combine")
+            if dt.total % R:
+                raise RuntimeError("destination table of %d slots does not split into %d regions" % (dt.total, R))
+            rcap = dt.total // R
+            for r in range(R):  # region after region: each part of the table stays in L2
+                self._chk(lib.bs_rx_combine(ctypes.byref(pe), st, c_int(j * R + r), vt, op,
+                                            c_void_p(dt.slots.data_ptr() + r * rcap * 16), c_ll(rcap),
+                                            c_void_p(dt.status.data_ptr()), c_ll(max_rows), s), "rx_combine")
             self._chk(lib.bs_table_compact(c_void_p(dt.slots.data_ptr()), c_ll(dt.total), vt,
                                            c_void_p(ok.data_ptr()), c_void_p(ov.data_ptr()),
                                            c_void_p(dt.status.data_ptr()), c_int(1), bits, c_ll(cap), s),
@@ -320,7 +336,7 @@ class ReduceExchange:
         run of a slice): scatter + wait, then publish how many rows arrived for
         every local shard.  Call on the exchange stream; follow with
         :meth:`exchange_finish` after sizing the destination tables."""
-        pe = self._peers_for(nparts)
+        pe = self._peers_for(nparts, 1)
         lib, st = self.lib, c_void_p(self.state.data_ptr())
         s = gpu._stream()
         self._chk(lib.bs_rx_set_vote(st, c_ull(vote[0]), c_ull(vote[1]), s), "rx_set_vote")
@@ -336,7 +352,7 @@ class ReduceExchange:
 
     def exchange_finish(self, table, nparts: int, dests: Sequence[tuple], on_report=None) -> Pending:
         """Second half: combine on arrival, compaction, acknowledgement."""
-        pe = self._peers_for(nparts)
+        pe = self._peers_for(nparts, 1)
         self._enqueue_recv(pe, table, nparts, dests, int(pe.region_rows) * self.world)
         ev = torch.cuda.Event()
         ev.record()
@@ -350,7 +366,7 @@ class ReduceExchange:
         return p
 
     def exchange(self, table, nparts: int, dests: Sequence[tuple], vote: Tuple[int, int] = (0, 0),
-                 on_report=None, keymode: int = 0) -> Pending:
+                 on_report=None, keymode: int = 0, regions: int = 1) -> Pending:
         """Enqueue one exchange of ``table`` on the exchange stream (the caller
         has made that stream wait for the producers' combines).
 
@@ -358,12 +374,12 @@ class ReduceExchange:
         local shard ``rank + j*world`` — all buffers allocated by the caller
         *before* this call (nothing is allocated while a graph is captured).
         Collective and ordered: every rank issues the same sequence."""
-        if nparts > MAXP:
-            raise RuntimeError("reduce exchange supports at most %d shards" % MAXP)
+        if nparts * regions > MAXP:
+            raise RuntimeError("reduce exchange supports at most %d (shards x regions)" % MAXP)
         for j, dt, ok, ov, cap in dests:
             if dt.warm:
                 raise RuntimeError("destination tables have no warm level")
-        pe = self._peers_for(nparts)
+        pe = self._peers_for(nparts, regions)
         pl, rows = pe.shards_per_rank, int(pe.region_rows)
         max_rows = rows * self.world
         lib = self.lib
@@ -372,7 +388,7 @@ class ReduceExchange:
             self._chk(lib.bs_rx_set_vote(c_void_p(self.state.data_ptr()), c_ull(vote[0]), c_ull(vote[1]), s),
                       "rx_set_vote")
             key = (table.slots.data_ptr(), table.total, table.status.data_ptr(), nparts, rows, table.vdtype,
-                   table.op, keymode) + tuple((j, dt.slots.data_ptr(), dt.total, dt.status.data_ptr(), ok.data_ptr(),
+                   table.op, keymode, regions) + tuple((j, dt.slots.data_ptr(), dt.total, dt.status.data_ptr(), ok.data_ptr(),
                                       ov.data_ptr(), cap) for j, dt, ok, ov, cap in dests)
             g = self.graphs.get(key) if self.use_graphs else None
             if g is not None:

@@ -68,8 +68,8 @@ struct RxPeers {
   unsigned char* arena[RX_MAXW];
   unsigned long long region_rows;  // capacity C of one (parity, local shard, source) region
   unsigned long long half_bytes;   // the arena is split into two parity halves of this size
-  int shards_per_rank;             // Pl = ceil(P / world): regions per (parity, source)
-  int pad;
+  int shards_per_rank;             // Pl * R: landing regions per (parity, source)
+  int regions;                     // R (power of two): table regions per destination shard
 };
 
 // Per-rank private device state of the exchange in flight.
@@ -96,6 +96,19 @@ struct RxReport {
   long long out_rows[RX_MAXP];
   long long dest_failed[RX_MAXP];
 };
+
+// Virtual partitions.  A destination shard d is split into R *table regions*
+// (r = a few bits of the table hash): v = d * R + r.  Rows of one region land
+// together, and the destination combines region after region, each region's part
+// of the table (tens of MB) staying L2-resident — instead of random DRAM accesses
+// over the whole table when it does not fit in L2 (few ranks, many keys each).
+__device__ __forceinline__ int rx_vowner(const RxPeers& pe, int v) { return (v / pe.regions) % pe.world; }
+__device__ __forceinline__ int rx_vlocal(const RxPeers& pe, int v) {
+  return ((v / pe.regions) / pe.world) * pe.regions + (v % pe.regions);
+}
+__device__ __forceinline__ int rx_table_region(long long key, int R) {
+  return (int)(bs_mix_u64((uint64_t)key) & (uint32_t)(R - 1));
+}
 
 __device__ __forceinline__ unsigned char* rx_region(const RxPeers& pe, int dst_rank, int par, int j,
                                                     int src) {
@@ -168,7 +181,7 @@ __device__ __forceinline__ void rx_flush(const RxPeers& pe, RxState* st, int par
     *cta_err = RX_LANDING_OVERFLOW;
     return;
   }
-  unsigned char* dst = rx_region(pe, d % pe.world, par, d / pe.world, pe.rank) + at * 16ULL;
+  unsigned char* dst = rx_region(pe, rx_vowner(pe, d), par, rx_vlocal(pe, d), pe.rank) + at * 16ULL;
   bs_tma_store_1d(dst, stage_d, (uint32_t)n * 16u);
   bs_tma_store_commit();
 }
@@ -183,7 +196,8 @@ __global__ void __launch_bounds__(RX_THREADS, 1) rx_scatter_kernel(
   __shared__ unsigned long long dbase[RX_MAXP];
   __shared__ int cta_err;
   __shared__ unsigned int is_last;
-  const int B = RX_ROWS / P;
+  const int PV = P * pe.regions;  // virtual partitions: (destination shard, table region)
+  const int B = RX_ROWS / PV;
   const int tid = threadIdx.x;
   const unsigned long long epoch = st->epoch;
   const int par = (int)(epoch & 1ULL);
@@ -209,7 +223,7 @@ __global__ void __launch_bounds__(RX_THREADS, 1) rx_scatter_kernel(
     };
     load_tile(blockIdx.x);
     for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-      if (tid < P) hist[tid] = 0;
+      if (tid < PV) hist[tid] = 0;
       __syncthreads();
       int4 row[RX_PER];
       int dest[RX_PER], rank[RX_PER];
@@ -224,7 +238,7 @@ __global__ void __launch_bounds__(RX_THREADS, 1) rx_scatter_kernel(
         dest[j] = -1;
         rank[j] = 0;
         if (__any_sync(0xffffffffu, occupied)) {
-          const int d = ok ? rx_dest(key, P, keymode) : 0;
+          const int d = ok ? rx_dest(key, P, keymode) * pe.regions + rx_table_region(key, pe.regions) : 0;
           rank[j] = rx_rank(hist, d, ok);
           if (ok) dest[j] = d;
           if (occupied) {
@@ -241,7 +255,7 @@ __global__ void __launch_bounds__(RX_THREADS, 1) rx_scatter_kernel(
       // rows would not fit; a tile with more rows for one destination than a whole
       // buffer is written directly
       int need = 0;
-      if (tid < P) {
+      if (tid < PV) {
         const int f = fill[tid], h = hist[tid];
         const int dir = h > B;
         need = (f + h > B) && f > 0;
@@ -266,7 +280,7 @@ __global__ void __launch_bounds__(RX_THREADS, 1) rx_scatter_kernel(
         const int d = dest[j];
         if (d >= 0) {
           if (direct[d] == 1) {
-            int4* dst = (int4*)rx_region(pe, d % pe.world, par, d / pe.world, pe.rank);
+            int4* dst = (int4*)rx_region(pe, rx_vowner(pe, d), par, rx_vlocal(pe, d), pe.rank);
             dst[dbase[d] + (unsigned long long)rank[j]] = row[j];
           } else if (direct[d] == 0) {
             stage[(size_t)d * B + off[d] + rank[j]] = row[j];
@@ -277,9 +291,9 @@ __global__ void __launch_bounds__(RX_THREADS, 1) rx_scatter_kernel(
     }
     // drain what is still staged
     __syncthreads();
-    if (tid < P && fill[tid] > 0) rx_flush(pe, st, par, tid, stage + (size_t)tid * B, fill[tid], &cta_err);
+    if (tid < PV && fill[tid] > 0) rx_flush(pe, st, par, tid, stage + (size_t)tid * B, fill[tid], &cta_err);
   }
-  if (tid < P) {
+  if (tid < PV) {
     bs_tma_store_wait_all();  // my bulk stores are complete (written, not just read)
     asm volatile("fence.proxy.async;" ::: "memory");  // async-proxy writes ordered before the flag
   }
@@ -299,13 +313,13 @@ __global__ void __launch_bounds__(RX_THREADS, 1) rx_scatter_kernel(
     if (!status && tst->failed) status = RX_TABLE_OVERFLOW;
     if (!status && st->error) status = (unsigned long long)st->error;
     if (!status && tst->has_special) {
-      const int d = rx_dest(BS_EMPTY_KEY, P, keymode);
+      const int d = rx_dest(BS_EMPTY_KEY, P, keymode) * pe.regions + rx_table_region(BS_EMPTY_KEY, pe.regions);
       const unsigned long long at = atomicAdd(&st->cursor[d], 1ULL);
       if (at + 1 > pe.region_rows) {
         atomicMax(&st->need_rows, at + 1);
         status = RX_LANDING_OVERFLOW;
       } else {
-        int4* dst = (int4*)rx_region(pe, d % pe.world, par, d / pe.world, pe.rank);
+        int4* dst = (int4*)rx_region(pe, rx_vowner(pe, d), par, rx_vlocal(pe, d), pe.rank);
         dst[at] = make_int4(0, (int)0x80000000, (int)(unsigned int)tst->special_val,
                             (int)(unsigned int)(tst->special_val >> 32));
       }
@@ -320,10 +334,10 @@ __global__ void __launch_bounds__(RX_THREADS, 1) rx_scatter_kernel(
   }
   __syncthreads();
   long long sent = 0;
-  if (tid < P) {
+  if (tid < PV) {
     unsigned long long c = st->cursor[tid];
     if (c > pe.region_rows) c = pe.region_rows;
-    pe.ctrl[tid % pe.world]->cnt[par][pe.rank][tid] = (long long)c;
+    pe.ctrl[rx_vowner(pe, tid)]->cnt[par][pe.rank][tid] = (long long)c;
     sent = (long long)c;
   }
   for (int o = 16; o > 0; o >>= 1) sent += __shfl_down_sync(0xffffffffu, sent, o);
@@ -381,9 +395,10 @@ __global__ void __launch_bounds__(64) rx_wait_kernel(RxPeers pe, RxState* st, in
     if (need > st->need_rows) st->need_rows = need;
   }
   for (int x = tid; x < pe.shards_per_rank * pe.world; x += blockDim.x) {
-    const int j = x / pe.world, s = x - j * pe.world;
-    const int d = pe.rank + j * pe.world;
-    st->recv[j][s] = (d < P && verdict == 0) ? mine->cnt[par][s][d] : 0;
+    const int jv = x / pe.world, s = x - jv * pe.world;       // local virtual index, source
+    const int d = pe.rank + (jv / pe.regions) * pe.world;    // destination shard
+    const int v = d * pe.regions + (jv % pe.regions);
+    st->recv[jv][s] = (d < P && verdict == 0) ? mine->cnt[par][s][v] : 0;
   }
 }
 
@@ -482,7 +497,8 @@ __global__ void __launch_bounds__(64) rx_end_kernel(RxPeers pe, RxState* st, int
     long long err = st->error;
     for (int j = 0; j < nlocal; ++j) {
       long long rows = 0;
-      for (int s = 0; s < pe.world; ++s) rows += st->recv[j][s];
+      for (int r = 0; r < pe.regions; ++r)
+        for (int s = 0; s < pe.world; ++s) rows += st->recv[j * pe.regions + r][s];
       rep->recv_rows[j] = rows;
       BsCombineStatus* d = a.st[j];
       rep->out_rows[j] = d ? (long long)d->out_count : 0;
@@ -582,7 +598,9 @@ BS_EXPORT int bs_rx_scatter(const void* peers_h, void* state_d, void* slots, lon
                             int clear, unsigned long long clear_bits, void* table_status, int keymode,
                             cudaStream_t stream) {
   RxPeers pe = *(const RxPeers*)peers_h;
-  if (pe.world > RX_MAXW || nparts > RX_MAXP || nparts < 1) return -1;
+  if (pe.world > RX_MAXW || nparts < 1 || pe.regions < 1 || (pe.regions & (pe.regions - 1)) ||
+      nparts * pe.regions > RX_MAXP)
+    return -1;
   RxState* st = (RxState*)state_d;
   rx_begin_kernel<<<1, 64, 0, stream>>>(pe, st, nparts);
   BS_LAUNCH_CHECK();
