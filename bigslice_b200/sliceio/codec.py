@@ -231,6 +231,51 @@ class Encoder:
     encode = write
 
 
+#: Object columns are pickles, and the same decoder reads cache shards and task
+#: stores from disk: whoever can write there must not get code execution in every
+#: rank that reads.  Only plain data is admitted — builtin containers/scalars,
+#: numpy/torch arrays and scalars — plus whatever the application registers.
+_SAFE_GLOBALS = {
+    ("builtins", n) for n in ("list", "tuple", "dict", "set", "frozenset", "bytes", "bytearray", "str", "int",
+                              "float", "complex", "bool", "NoneType", "slice", "range")}
+_SAFE_GLOBALS |= {("numpy", "ndarray"), ("numpy", "dtype"), ("numpy.core.multiarray", "_reconstruct"),
+                  ("numpy._core.multiarray", "_reconstruct"), ("numpy.core.multiarray", "scalar"),
+                  ("numpy._core.multiarray", "scalar"), ("numpy.core.numeric", "_frombuffer"),
+                  ("numpy._core.numeric", "_frombuffer"), ("collections", "OrderedDict"),
+                  ("datetime", "datetime"), ("datetime", "date"), ("datetime", "timedelta"),
+                  ("decimal", "Decimal"), ("fractions", "Fraction")}
+
+
+def allow_object_class(cls) -> None:
+    """Admit instances of ``cls`` in object columns read from streams and files
+    (the decoder refuses classes it was not told about)."""
+    _SAFE_GLOBALS.add((cls.__module__, cls.__qualname__))
+
+
+class _RestrictedUnpickler(pickle.Unpickler):
+    def find_class(self, module, name):
+        if (module, name) in _SAFE_GLOBALS:
+            return super().find_class(module, name)
+        raise errors.IntegrityError(
+            "sliceio: object column refers to %s.%s, which is not on the allow-list "
+            "(sliceio.allow_object_class registers application types)" % (module, name))
+
+
+def _restricted_loads(data: bytes):
+    import io as _io
+    try:
+        return _RestrictedUnpickler(_io.BytesIO(data)).load()
+    except errors.Error:
+        raise
+    except Exception as e:  # noqa: BLE001 - a corrupt pickle is an integrity problem
+        raise errors.IntegrityError("sliceio: corrupt object column", e)
+
+
+#: upper bound on one batch body (a corrupt or hostile length field must not make
+#: the reader allocate unbounded memory)
+MAX_BODY_BYTES = 1 << 36
+
+
 def _read_exact(r: BinaryIO, n: int) -> bytes:
     chunks, got = [], 0
     while got < n:
@@ -296,7 +341,7 @@ def _decode_column(buf: memoryview, pos: int, n: int, dt: DType, session: Sessio
     if tag in (1, 2):
         return _decode_varlen(payload, n, tag == 1), pos
     if tag == 3:
-        vals = pickle.loads(bytes(payload))
+        vals = _restricted_loads(bytes(payload))
         a = np.empty(len(vals), dtype=object)
         for i, v in enumerate(vals):
             a[i] = v
@@ -373,6 +418,9 @@ class Decoder(Reader):
         magic, blen = struct.unpack("<IQ", head)
         if magic != MAGIC:
             raise errors.IntegrityError("sliceio: bad batch magic %#x" % magic)
+        if blen > MAX_BODY_BYTES:
+            raise errors.IntegrityError("sliceio: batch length %d exceeds the %d-byte limit (corrupt header?)"
+                                        % (blen, MAX_BODY_BYTES))
         body = _read_exact(self.r, blen + 4)
         if len(body) < blen + 4:
             raise errors.IntegrityError("sliceio: unexpected EOF in batch body")

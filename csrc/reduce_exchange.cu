@@ -37,10 +37,13 @@
 
 #define RX_MAXW 16
 #define RX_MAXP 64
-#define RX_THREADS 1024
+// Two CTAs per SM (512 threads, 64 KB of staging each): the per-tile barrier chain
+// (rank -> reserve -> stage) of one CTA overlaps the other's.
+#define RX_THREADS 512
 #define RX_PER 4
 #define RX_TILE (RX_THREADS * RX_PER)
-#define RX_ROWS 8192  // staged rows per CTA (16 B each = 128 KB of shared memory)
+#define RX_ROWS 4096  // staged rows per CTA (16 B each = 64 KB of shared memory)
+#define RX_CTAS_PER_SM 2
 
 enum RxError {
   RX_OK = 0,
@@ -186,7 +189,7 @@ __device__ __forceinline__ void rx_flush(const RxPeers& pe, RxState* st, int par
   bs_tma_store_commit();
 }
 
-__global__ void __launch_bounds__(RX_THREADS, 1) rx_scatter_kernel(
+__global__ void __launch_bounds__(RX_THREADS, RX_CTAS_PER_SM) rx_scatter_kernel(
     RxPeers pe, RxState* st, int4* __restrict__ slots, long long total, int P, int clear,
     unsigned long long clear_bits, BsCombineStatus* tst, int keymode) {
   const unsigned long long my_status = st->vote_in[0], my_fp = st->vote_in[1];
@@ -613,7 +616,7 @@ BS_EXPORT int bs_rx_scatter(const void* peers_h, void* state_d, void* slots, lon
   }
   const int sms = bs_num_sms();
   long long ntiles = (total + RX_TILE - 1) / RX_TILE;
-  int blocks = (int)(ntiles < sms ? ntiles : sms);
+  int blocks = (int)(ntiles < (long long)sms * RX_CTAS_PER_SM ? ntiles : (long long)sms * RX_CTAS_PER_SM);
   if (blocks < 1) blocks = 1;
   rx_scatter_kernel<<<blocks, RX_THREADS, smem, stream>>>(pe, st, (int4*)slots, total, nparts, clear, clear_bits,
                                                           (BsCombineStatus*)table_status, keymode);

@@ -213,3 +213,31 @@ def test_crc32_matches_zlib():
     data = bytes(range(256)) * 37
     assert sliceio.crc32(data) == zlib.crc32(data) & 0xFFFFFFFF
     assert sliceio.crc32(data[100:], sliceio.crc32(data[:100])) == zlib.crc32(data) & 0xFFFFFFFF
+
+
+def test_object_columns_refuse_unknown_classes():
+    """Object columns are restricted pickles: data types load, anything else (here a
+    class whose unpickling would run code) is refused with an IntegrityError unless
+    the application registered it."""
+    import io
+    import pickle
+    import numpy as np
+    from bigslice_b200 import errors, slicetype
+    from bigslice_b200.frame import Frame
+    from bigslice_b200 import sliceio
+    from bigslice_b200.sliceio import codec
+
+    class Evil:
+        def __reduce__(self):
+            return (print, ("pwned",))
+    typ = slicetype.Type([slicetype.dtype_of(object)], 1)
+    good = np.empty(3, dtype=object)
+    good[:] = [{"a": 1}, (1, 2.5, "x"), [b"b", None]]
+    data = codec.encode_frame(Frame([good], typ))
+    back = sliceio.read_all(codec.Decoder(io.BytesIO(data), typ), typ)
+    assert back.col(0).tolist() == good.tolist()
+    bad = np.empty(1, dtype=object)
+    bad[0] = Evil()
+    data = codec.encode_frame(Frame([bad], typ))
+    with pytest.raises(errors.IntegrityError):
+        sliceio.read_all(codec.Decoder(io.BytesIO(data), typ), typ)
