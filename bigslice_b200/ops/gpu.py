@@ -551,6 +551,34 @@ def topk(values: torch.Tensor, k: int) -> Tuple[torch.Tensor, torch.Tensor]:
     return values.reshape(-1)[idx], idx
 
 
+# ---------------------------------------------------------------- merge path
+
+def merge_sorted_i64(ka: torch.Tensor, kb: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Stable merge of two ascending int64 key columns (``csrc/merge.cu``):
+    ``(keys, src)`` where ``src[i]`` is the position of output row ``i`` in the
+    concatenation ``[a | b]`` (rows of ``a`` first among equal keys)."""
+    lib = require()
+    lib.bs_merge_scratch_elems.restype = c_ll
+    ka, kb = ka.contiguous(), kb.contiguous()
+    na, nb = ka.numel(), kb.numel()
+    dev = ka.device
+    keys = torch.empty(na + nb, dtype=torch.int64, device=dev)
+    src = torch.empty(na + nb, dtype=torch.int64, device=dev)
+    scratch = torch.empty(int(lib.bs_merge_scratch_elems(c_ll(na), c_ll(nb))), dtype=torch.int64, device=dev)
+    _chk(lib.bs_merge_sorted_i64(_ptr(ka), c_ll(na), _ptr(kb), c_ll(nb), _ptr(keys), _ptr(src), _ptr(scratch),
+                                 _stream()), "merge_sorted_i64")
+    return keys, src
+
+
+def merge_frames(fa: Frame, fb: Frame) -> Frame:
+    """Merge two frames sorted by one int64 key column (device)."""
+    keys, src = merge_sorted_i64(fa.col(0), fb.col(0))
+    cols = [keys]
+    for j in range(1, fa.num_out()):
+        cols.append(C.col_take(C.col_concat([fa.col(j), fb.col(j)], fa.out(j)), src))
+    return Frame(cols, fa.typ)
+
+
 # ---------------------------------------------------------------- cogroup (sort-merge join)
 
 def run_starts(sorted_keys: torch.Tensor) -> torch.Tensor:

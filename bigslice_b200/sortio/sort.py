@@ -171,6 +171,9 @@ class MergeReader(Reader):
             return f
         # Safe bound: the smallest buffered last-key (Python tuple compare is
         # lexicographic); every unbuffered row of every stream is >= it.
+        dev_out = self._device_step(live)
+        if dev_out is not None:
+            return dev_out
         bound = min(_key_at(b.frame, len(b.frame) - 1, self.nkeys) for b in live)
         parts = []
         for b in live:
@@ -182,6 +185,35 @@ class MergeReader(Reader):
                 b.frame = f.slice(cnt, len(f)) if cnt < len(f) else None
         out = concat(parts, self.typ)
         return out.sorted()
+
+    def _device_step(self, live) -> Optional[Frame]:
+        """Device tiles keyed by one int64 column: the emit bound and the per-stream
+        cuts are computed on the device (one searchsorted per stream instead of
+        host-side masks) and the cuts are merged with the merge-path kernel
+        (``csrc/merge.cu``) instead of being concatenated and sorted again."""
+        if self.nkeys != 1:
+            return None
+        for b in live:
+            k = b.frame.col(0)
+            if not (isinstance(k, torch.Tensor) and k.is_cuda and k.dtype == torch.int64 and k.dim() == 1):
+                return None
+        from ..ops import gpu
+        if not gpu.available():
+            return None
+        lasts = torch.stack([b.frame.col(0)[-1] for b in live])
+        bound = lasts.min()
+        cuts = [int(torch.searchsorted(b.frame.col(0), bound, right=True)) for b in live]
+        parts = []
+        for b, cnt in zip(live, cuts):
+            if cnt:
+                parts.append(b.frame.slice(0, cnt))
+                b.frame = b.frame.slice(cnt, len(b.frame)) if cnt < len(b.frame) else None
+        while len(parts) > 1:   # pairwise tree of stable merges
+            nxt = [gpu.merge_frames(parts[i], parts[i + 1]) for i in range(0, len(parts) - 1, 2)]
+            if len(parts) % 2:
+                nxt.append(parts[-1])
+            parts = nxt
+        return parts[0]
 
     def close(self):
         for b in self.bufs:
@@ -224,6 +256,7 @@ class _SortReader(Reader):
         eof = False
         spiller: Optional[Spiller] = None
         first_run: Optional[Frame] = None
+        first_dev = canary.device if canary.device.type == "cuda" else None
         nruns = 0
         while not eof or pending:
             while not eof and pending_rows < run_rows:
@@ -242,7 +275,12 @@ class _SortReader(Reader):
                 first_run = run
                 break
             if spiller is None:
-                spiller = Spiller("sort")
+                # device runs are parked in pinned host memory first, files second
+                if run.device.type == "cuda":
+                    from ..sliceio.tiers import TieredSpiller
+                    spiller = TieredSpiller("sort", run.device)
+                else:
+                    spiller = Spiller("sort")
             spiller.spill(run)
             # Re-estimate the run size from what we have observed (the
             # reference adjusts within +-5% of the spill target).
@@ -253,7 +291,8 @@ class _SortReader(Reader):
             self._out = FrameReader(first_run) if first_run is not None else EmptyReader()
             return
         self._spiller = spiller
-        self._out = merge_reader(self.typ, spiller.closing_readers(self.device))
+        dev = self.device if self.device is not None else (first_dev if first_dev is not None else None)
+        self._out = merge_reader(self.typ, spiller.closing_readers(dev))
 
     def read(self, n=None):
         if self._err is not None:
