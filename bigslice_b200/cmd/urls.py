@@ -7,11 +7,12 @@ and counts domains with Reduce (``cmd/urls/urls.go:37-126``).  There is no
 network here, so inputs are local files (one URL per line / any column
 containing a URL) or a synthetic generator with Zipf-distributed domains.
 
-Pipeline: ``ScanReader/ReaderFunc -> Flatmap(extract domain) -> Map(domain ->
-(hash id, 1)) -> Reduce(add) -> per-shard top-K``.  Domains are dictionary-
-encoded to int64 ids (murmur3 of the domain; the id->domain table is a host
-side-output), so on the GPU executors the count runs on the fused int64
-hash-aggregation path.
+Pipeline: ``ScanReader/ReaderGen -> Tokenize -> UrlDomains -> StringIds ->
+Reduce(add) -> per-shard top-K``.  On a GPU executor the lines are moved to HBM
+as a CSR string column once; tokenising, host extraction (lower-cased) and the
+64-bit dictionary ids are string kernels (``csrc/strings.cu``), the count runs on
+the int64 hash-aggregation + fused NVLink exchange path, and the id -> domain
+dictionary stays on the device until the top-K rows are printed.
 """
 from __future__ import annotations
 
@@ -28,8 +29,10 @@ import bigslice_b200 as bs
 from bigslice_b200 import sliceconfig
 from bigslice_b200.frame import hashing
 
-_domains: Dict[int, str] = {}
-_domains_lock = threading.Lock()
+from bigslice_b200 import text as _text  # noqa: E402
+
+#: id -> domain, learned while the pipeline runs (device resident on GPU executors)
+DOMAINS = _text.IdDictionary()
 
 
 def domain_of(url: str) -> str:
@@ -64,28 +67,13 @@ def count_domains(nshard: int, files: list, synthetic: int, ndomain: int, top: i
             yield (synthetic_urls(per, ndomain, shard),)
         lines = bs.ReaderGen(nshard, gen, [bs.string])
 
-    @bs.rowwise
-    def extract(line):
-        out = []
-        for tok in line.replace(",", " ").replace("\t", " ").split():
-            if "." in tok and ("/" in tok or tok.startswith("http")):
-                d = domain_of(tok)
-                if d:
-                    out.append(d)
-        return (out,)
-    domains = bs.Flatmap(lines, extract, out=[bs.string])
-
-    def encode(d):
-        ids = hashing.hash_objects(d, 0) | (hashing.hash_objects(d, 1) << 32)
-        with _domains_lock:
-            for i, s in zip(ids.tolist(), d.tolist()):
-                _domains.setdefault(i, s)
-        from bigslice_b200 import context as _ctx
-        dev = _ctx.current_device()
-        ids = ids.to(dev) if dev is not None else ids
-        return ids, torch.ones_like(ids)
-    pairs = bs.Map(domains, encode, out=[bs.int64, bs.int64])
-    counts = bs.Reduce(pairs, bs.ops.add)
+    # URL column -> host -> 64-bit dictionary id; on a GPU executor all three steps
+    # are string kernels over a CSR column in HBM (bigslice_b200/text.py), and the
+    # count then runs on the int64 hash-aggregation + fused exchange path.
+    from bigslice_b200 import text
+    tokens = text.Tokenize(text.ToDevice(lines), b" ,\t\r\n")
+    domains = text.UrlDomains(tokens)
+    counts = bs.Reduce(text.StringIds(domains, DOMAINS), bs.ops.add)
 
     def topk(k, v):
         kk = min(top, v.numel())
@@ -110,8 +98,10 @@ def main(argv=None) -> int:
     finally:
         sess.shutdown()
     rows.sort(key=lambda r: -r[1])
-    for k, v in rows[:a.top]:
-        print("%s\t%d" % (_domains.get(k, "<%d>" % k), v))
+    rows = rows[:a.top]
+    names = DOMAINS.lookup_global([k for k, _ in rows])
+    for k, v in rows:
+        print("%s\t%d" % (names.get(k) or "<%d>" % k, v))
     return 0
 
 

@@ -54,12 +54,55 @@ class ListColumn:
         return "ListColumn(%r)" % (self.tolist(),)
 
 
+class StringColumn:
+    """``n`` variable-length strings as CSR ``offsets[n+1]`` (int64) + ``data``
+    (uint8), on CPU or in HBM: the device form of a ``string``/``bytes`` column
+    (host frames may equally hold numpy object arrays).  The kernels that hash,
+    tokenise and gather such columns are in :mod:`bigslice_b200.ops.strings`."""
+
+    __slots__ = ("offsets", "data", "is_str")
+
+    def __init__(self, offsets: torch.Tensor, data: torch.Tensor, is_str: bool = True):
+        self.offsets, self.data, self.is_str = offsets, data, is_str
+
+    def __len__(self) -> int:
+        return int(self.offsets.shape[0]) - 1
+
+    @property
+    def device(self) -> torch.device:
+        return self.offsets.device
+
+    def to(self, device) -> "StringColumn":
+        return StringColumn(self.offsets.to(device), self.data.to(device), self.is_str)
+
+    def lengths(self) -> torch.Tensor:
+        return self.offsets[1:] - self.offsets[:-1]
+
+    def nbytes(self) -> int:
+        return self.offsets.numel() * 8 + self.data.numel()
+
+    def to_objects(self) -> np.ndarray:
+        offs = self.offsets.cpu().numpy()
+        raw = self.data.cpu().numpy().tobytes()
+        out = np.empty(len(self), dtype=object)
+        for i in range(len(self)):
+            b = raw[offs[i]:offs[i + 1]]
+            out[i] = b.decode("utf-8", errors="replace") if self.is_str else b
+        return out
+
+    def tolist(self) -> list:
+        return self.to_objects().tolist()
+
+    def __repr__(self):
+        return "StringColumn(n=%d, bytes=%d, %s)" % (len(self), self.data.numel(), self.device)
+
+
 def is_column(v) -> bool:
-    return isinstance(v, (torch.Tensor, np.ndarray, ListColumn))
+    return isinstance(v, (torch.Tensor, np.ndarray, ListColumn, StringColumn))
 
 
 def col_len(c) -> int:
-    if isinstance(c, ListColumn):
+    if isinstance(c, (ListColumn, StringColumn)):
         return len(c)
     return int(c.shape[0])
 
@@ -67,12 +110,18 @@ def col_len(c) -> int:
 def col_device(c) -> torch.device:
     if isinstance(c, torch.Tensor):
         return c.device
-    if isinstance(c, ListColumn):
+    if isinstance(c, (ListColumn, StringColumn)):
         return c.offsets.device
     return torch.device("cpu")
 
 
 def col_slice(c, i: int, j: int):
+    if isinstance(c, StringColumn):
+        offs = c.offsets[i:j + 1]
+        if offs.numel() == 0:
+            return StringColumn(torch.zeros(1, dtype=torch.int64, device=c.device), c.data[:0], c.is_str)
+        a, b = int(offs[0]), int(offs[-1])
+        return StringColumn(offs - offs[0], c.data[a:b], c.is_str)
     if isinstance(c, ListColumn):
         offs = c.offsets[i:j + 1]
         if offs.numel() == 0:
@@ -85,6 +134,11 @@ def col_slice(c, i: int, j: int):
 
 def col_take(c, idx):
     """Gather rows by index (``idx``: int64 tensor / ndarray / list)."""
+    if isinstance(c, StringColumn):
+        from ..ops import strings
+        if not isinstance(idx, torch.Tensor):
+            idx = torch.as_tensor(np.asarray(idx), dtype=torch.int64)
+        return strings.take(c, idx)
     if isinstance(c, torch.Tensor):
         if not isinstance(idx, torch.Tensor):
             idx = torch.as_tensor(np.asarray(idx), dtype=torch.int64)
@@ -182,6 +236,17 @@ def col_concat(cols: Sequence, dt: Optional[DType] = None, device=None):
         if len(cols) == 1:
             return first
         return torch.cat(list(cols), 0)
+    if isinstance(first, StringColumn) or any(isinstance(c, StringColumn) for c in cols):
+        if len(cols) == 1:
+            return first
+        from ..ops import strings
+        dev = next(c.device for c in cols if isinstance(c, StringColumn))
+        cs = [c if isinstance(c, StringColumn) else strings.from_objects(c, device=dev) for c in cols]
+        offs, base = [cs[0].offsets], cs[0].offsets[-1]
+        for c in cs[1:]:
+            offs.append(c.offsets[1:] + base)
+            base = base + c.offsets[-1]
+        return StringColumn(torch.cat(offs), torch.cat([c.data for c in cs]), cs[0].is_str)
     if isinstance(first, ListColumn):
         if len(cols) == 1:
             return first
@@ -211,6 +276,11 @@ def col_to(c, device):
         return c.to(dev, non_blocking=(dev.type == "cuda"))
     if isinstance(c, ListColumn):
         return ListColumn(c.offsets.to(device), col_to(c.values, device), c.child_dtype)
+    if isinstance(c, StringColumn):
+        # strings live as object arrays on the host side of the framework (user
+        # functions, the scanner) and as CSR on devices
+        dev = torch.device(device)
+        return c.to_objects() if dev.type == "cpu" else c.to(dev)
     return c
 
 
@@ -219,6 +289,8 @@ def col_clone(c):
         return c.clone()
     if isinstance(c, ListColumn):
         return ListColumn(c.offsets.clone(), col_clone(c.values), c.child_dtype)
+    if isinstance(c, StringColumn):
+        return StringColumn(c.offsets.clone(), c.data.clone(), c.is_str)
     return c.copy()
 
 
@@ -239,7 +311,7 @@ def col_copy(dst, doff: int, src, soff: int, n: int):
 def col_tolist(c) -> list:
     if isinstance(c, torch.Tensor):
         return c.tolist()
-    if isinstance(c, ListColumn):
+    if isinstance(c, (ListColumn, StringColumn)):
         return c.tolist()
     if isinstance(c, np.ndarray):
         return c.tolist()
@@ -282,6 +354,8 @@ def as_column(v, dt: Optional[DType] = None, device=None):
     """Coerce a user-supplied value (tensor/ndarray/list) into a column."""
     if isinstance(v, ListColumn):
         return col_to(v, device)
+    if isinstance(v, StringColumn):
+        return v if device is None else col_to(v, device)
     if isinstance(v, torch.Tensor):
         if dt is not None and dt.is_tensor and v.dtype != dt.torch_dtype:
             v = v.to(dt.torch_dtype)
@@ -309,6 +383,8 @@ def col_nbytes(c) -> int:
         return c.numel() * c.element_size()
     if isinstance(c, ListColumn):
         return col_nbytes(c.offsets) + col_nbytes(c.values)
+    if isinstance(c, StringColumn):
+        return c.nbytes()
     n = 0
     for e in c:
         n += len(e) if isinstance(e, (str, bytes, bytearray)) else 8

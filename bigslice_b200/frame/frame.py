@@ -124,7 +124,7 @@ class Frame:
     def col(self, i: int):
         """Column ``i`` as a view over rows [0, len)."""
         c = self._data[i]
-        if isinstance(c, C.ListColumn):
+        if isinstance(c, (C.ListColumn, C.StringColumn)):
             if self._off == 0 and self._len == len(c):
                 return c
             return C.col_slice(c, self._off, self._off + self._len)
@@ -138,7 +138,7 @@ class Frame:
     @property
     def device(self) -> torch.device:
         for c in self._data:
-            if isinstance(c, (torch.Tensor, C.ListColumn)):
+            if isinstance(c, (torch.Tensor, C.ListColumn, C.StringColumn)):
                 return C.col_device(c)
         return torch.device("cpu")
 
@@ -390,6 +390,9 @@ def _argsort_objects(c: np.ndarray) -> np.ndarray:
 
 def hash_column(c, seed: int = 0) -> torch.Tensor:
     """Per-element seeded murmur3 of one column -> int64 tensor of uint32."""
+    if isinstance(c, C.StringColumn):
+        from ..ops import strings
+        return strings.hash32(c, seed)
     if isinstance(c, torch.Tensor):
         if c.is_cuda:
             from ..ops import gpu

@@ -118,6 +118,12 @@ def _encode_column(col, dt: DType, session: Session) -> bytes:
     if dt.is_tensor:
         payload = _tensor_bytes(col)
         return hdr.pack(0, _DT_INDEX[_base(dt).name], dt.width, len(payload)) + bytes(payload)
+    if dt.kind in ("str", "bytes") and hasattr(col, "offsets") and hasattr(col, "data"):
+        # device string column: the CSR form *is* the wire form
+        payload = (col.offsets.detach().cpu().numpy().astype("<i8").tobytes()
+                   + col.data.detach().cpu().numpy().tobytes())
+        tag = 1 if dt.kind == "str" else 2
+        return hdr.pack(tag, _DT_INDEX["string" if tag == 1 else "bytes"], 0, len(payload)) + payload
     if dt.kind == "str":
         payload = _encode_varlen(col, True)
         return hdr.pack(1, _DT_INDEX["string"], 0, len(payload)) + payload

@@ -40,6 +40,18 @@ def strcount(nshard: int):
     return bs.Reduce(s, lambda a, b: a + b)
 
 
+from bigslice_b200 import text as _text  # noqa: E402
+WORD_DICT = _text.IdDictionary()
+
+
+@bs.Func
+def textcount(nshard: int):
+    """String keys on the device path: lines -> tokens -> 64-bit ids -> Reduce(add)."""
+    lines = np.array([" ".join(WORDS[i:i + 5].tolist()) for i in range(0, N, 5)], dtype=object)
+    s = _text.ToDevice(bs.Const(nshard, lines))
+    return bs.Reduce(_text.StringIds(_text.Tokenize(s), WORD_DICT), bs.ops.add)
+
+
 @bs.Func
 def join(nshard: int):
     a = bs.Const(nshard, KEYS, torch.arange(N, dtype=torch.float32))
@@ -383,6 +395,10 @@ def main():
     for w in WORDS.tolist():
         wants[w] = wants.get(w, 0) + 1
     out["strcount_ok"] = dict(rows) == wants
+    rows = ex.gather(sess.run(textcount, 2 * world))
+    names = WORD_DICT.lookup_global([k for k, _ in rows], group=ex.ctrl_group)
+    out["textcount_ok"] = {names[k]: v for k, v in rows} == wants
+    out["textcount_mode"] = ex.exchange_log[-1]["mode"] if ex.exchange_log else ""
     rows = ex.gather(sess.run(join, 2 * world))
     got = {k: (sorted(a), sorted(b)) for k, a, b in rows}
     wantj = {}

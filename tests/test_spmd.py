@@ -38,7 +38,8 @@ def check(outs, world):
     assert scanned == [2 * i for i in range(100)]
     for o in outs:
         assert o["world"] == world
-        for k in ("wordcount_ok", "chain_ok", "strcount_ok", "join_ok", "bjoin_ok", "pairsum_ok", "bytemax_ok",
+        for k in ("wordcount_ok", "chain_ok", "strcount_ok", "textcount_ok", "join_ok", "bjoin_ok", "pairsum_ok",
+                  "bytemax_ok",
                   "reshard_ok",
                   "reshard_placement_ok", "failure_ok"):
             assert o[k], (k, o)
@@ -69,6 +70,8 @@ def test_spmd_single_gpu_fused_self_exchange(tmp_path):
     assert outs[0]["exchange_content_ok"] and outs[0]["bigcount_ok"] and outs[0]["table_exchange_ok"]
     # packed two-column / narrow keys take the device table path too
     assert outs[0]["pairsum_mode"] in ("fused-table", "table-local") and outs[0]["bytemax_mode"] == "fused-table"
+    # string keys: tokenised and hashed by the string kernels, counted on the table path
+    assert outs[0]["textcount_mode"] == "fused-table"
 
 
 @pytest.mark.gpu
