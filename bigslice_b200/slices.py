@@ -546,7 +546,7 @@ class _Map(Slice):
 
 def _coerce(c, t: DType, n: int, device):
     """Make a user-returned column conform to dtype ``t`` and length ``n``."""
-    if isinstance(c, C.ListColumn):
+    if isinstance(c, (C.ListColumn, C.StringColumn)):
         return c
     if t.is_tensor:
         if not isinstance(c, torch.Tensor):

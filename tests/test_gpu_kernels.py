@@ -461,6 +461,7 @@ def test_tiered_external_sort_on_device(gpu, monkeypatch):
             made.append(self)
     monkeypatch.setattr(tiers, "TieredSpiller", Spy)
     monkeypatch.setattr(tiers, "HOST_BUDGET", 2 << 20)       # ~2 runs fit in the host tier
+    monkeypatch.setattr(sortio.sort.MergeReader, "EAGER_ROWS", 1000)   # merge run by run, not sort-it-all
     before = gpu.launches()
     r = sortio.sort_reader(FrameReader(f), 1 << 20, typ, device="cuda")   # 1 MiB runs -> several runs
     out = []

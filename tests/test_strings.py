@@ -65,3 +65,30 @@ def test_strings_device_kernels():
     words = np.array(["w%d" % i for i in rng.integers(0, 50000, 200000)], dtype=object)
     col = S.from_objects(words, device="cuda")
     assert torch.equal(S.hash32(col, 0).cpu(), hashing.hash_objects(words, 0))
+
+
+def test_csr_columns_flow_through_combinators(local_session):
+    """StringColumn (CSR) columns through Map/Flatmap/Filter/Reduce/shuffles on the
+    CPU executor — the same column type the device pipelines carry."""
+    import bigslice_b200 as bs
+    from bigslice_b200 import text
+    lines = np.array(["a b a", "c  b", "", "a"] * 50, dtype=object)
+    D = text.IdDictionary()
+
+    @bs.Func
+    def job():
+        s = bs.Map(bs.Const(3, lines), lambda c: (S.from_objects(c),), out=[bs.string])   # host CSR
+        toks = text.Tokenize(s)
+        toks = bs.Filter(toks, lambda c: torch.as_tensor([t != "c" for t in c.tolist()]))
+        keyed = bs.Map(toks, lambda c: (c, torch.ones(len(c), dtype=torch.int64)), out=[bs.string, bs.int64])
+        return bs.Reduce(keyed, bs.ops.add)          # string-keyed shuffle + combine
+    rows = dict(local_session.run(job).rows())
+    assert rows == {"a": 150, "b": 100}
+
+    @bs.Func
+    def ids():
+        s = bs.Map(bs.Const(2, lines), lambda c: (S.from_objects(c),), out=[bs.string])
+        return bs.Reduce(text.StringIds(text.Tokenize(s), D), bs.ops.add)
+    got = local_session.run(ids).rows()
+    names = D.lookup([k for k, _ in got])
+    assert {names[k]: v for k, v in got} == {"a": 150, "b": 100, "c": 50}
