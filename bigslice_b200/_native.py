@@ -23,6 +23,20 @@ def lib():
     _tried = True
     if os.environ.get("BIGSLICE_NO_NATIVE"):
         return None
+    alt = os.environ.get("BIGSLICE_NATIVE_DIR")
+    if alt:
+        # an alternative build of the module (scripts/sanitize_native.sh: ASan/TSan)
+        import importlib.util
+        import sysconfig
+        if "bigslice_b200._bsnative" in sys.modules:   # one pybind11 module per process
+            _lib = sys.modules["bigslice_b200._bsnative"]
+            return _lib
+        path = os.path.join(alt, "_bsnative" + (sysconfig.get_config_var("EXT_SUFFIX") or ".so"))
+        spec = importlib.util.spec_from_file_location("bigslice_b200._bsnative", path)
+        _lib = importlib.util.module_from_spec(spec)
+        sys.modules["bigslice_b200._bsnative"] = _lib
+        spec.loader.exec_module(_lib)
+        return _lib
     try:
         _lib = importlib.import_module("bigslice_b200._bsnative")
     except Exception:
