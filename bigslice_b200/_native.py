@@ -8,8 +8,10 @@ returns ``None`` in that case.
 from __future__ import annotations
 
 import importlib
+import importlib.util
 import os
 import sys
+import sysconfig
 
 _lib = None
 _tried = False
@@ -26,8 +28,6 @@ def lib():
     alt = os.environ.get("BIGSLICE_NATIVE_DIR")
     if alt:
         # an alternative build of the module (scripts/sanitize_native.sh: ASan/TSan)
-        import importlib.util
-        import sysconfig
         if "bigslice_b200._bsnative" in sys.modules:   # one pybind11 module per process
             _lib = sys.modules["bigslice_b200._bsnative"]
             return _lib
