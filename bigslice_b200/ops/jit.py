@@ -43,10 +43,41 @@ class Stage:
     """One Map (``exprs``/``out``) or Filter (``pred``) step."""
 
     def __init__(self, exprs: Optional[Sequence[str]] = None, out: Optional[Sequence[DType]] = None,
-                 pred: Optional[str] = None):
+                 pred: Optional[str] = None, eager=None, fn=None):
         self.exprs = list(exprs) if exprs is not None else None
         self.out = [slicetype.dtype_of(o) for o in out] if out is not None else None
         self.pred = pred
+        #: for stages traced from a python function (ops/trace.py): ``eager(cols, n, device)``
+        #: runs the original function (host frames, first-tile cross-check); ``fn`` is that function
+        self.eager = eager
+        self.fn = fn
+
+
+#: helpers every generated kernel may call: python-semantics ``%`` and ``//`` (floor, sign of
+#: the divisor), NaN-propagating min/max, abs — what traced python functions lower to.
+PRELUDE = r"""
+template <class T> __device__ __forceinline__ T bs_abs(T a) { return a < (T)0 ? (T)(-a) : a; }
+__device__ __forceinline__ float bs_abs(float a) { return fabsf(a); }
+__device__ __forceinline__ double bs_abs(double a) { return fabs(a); }
+template <class T> __device__ __forceinline__ T bs_min(T a, T b) {
+  return (a != a) ? a : ((b != b) ? b : (b < a ? b : a)); }
+template <class T> __device__ __forceinline__ T bs_max(T a, T b) {
+  return (a != a) ? a : ((b != b) ? b : (a < b ? b : a)); }
+template <class T> __device__ __forceinline__ T bs_floordiv(T a, T b) {
+  const T q = (T)(a / b);
+  return ((a % b) != 0 && ((a < (T)0) != (b < (T)0))) ? (T)(q - 1) : q; }
+template <class T> __device__ __forceinline__ T bs_pymod(T a, T b) {
+  const T r = (T)(a % b);
+  return (r != (T)0 && ((r < (T)0) != (b < (T)0))) ? (T)(r + b) : r; }
+__device__ __forceinline__ float bs_pymod(float a, float b) {
+  const float r = fmodf(a, b);
+  return (r != 0.f && ((r < 0.f) != (b < 0.f))) ? r + b : r; }
+__device__ __forceinline__ double bs_pymod(double a, double b) {
+  const double r = fmod(a, b);
+  return (r != 0.0 && ((r < 0.0) != (b < 0.0))) ? r + b : r; }
+"""
+
+_PASS = re.compile(r"^c(\d+)$")
 
 
 def check_types(dts: Sequence[DType]) -> None:
@@ -55,9 +86,11 @@ def check_types(dts: Sequence[DType]) -> None:
             raise TypeError("expression stages support scalar numeric/bool columns, not %s" % d)
 
 
-def generate(in_types: Sequence[DType], stages: Sequence[Stage]) -> Tuple[str, List[DType], bool]:
-    """CUDA source of the fused kernel, its output dtypes, and whether it has
-    a predicate."""
+def generate_ex(in_types: Sequence[DType], stages: Sequence[Stage]
+                ) -> Tuple[str, List[DType], bool, List[Optional[int]]]:
+    """CUDA source of the fused kernel, its output dtypes, whether it has a
+    predicate, and for every output the input column it merely passes through
+    (such outputs get no kernel parameter: the caller reuses the input column)."""
     check_types(in_types)
     cur = list(in_types)
     body = []
@@ -80,23 +113,37 @@ def generate(in_types: Sequence[DType], stages: Sequence[Stage]) -> Tuple[str, L
             check_types(st.out)
             new = []
             for j, (e, t) in enumerate(zip(st.exprs, st.out)):
+                m = _PASS.match(e.strip())
+                if m and int(m.group(1)) < len(names) and cur[int(m.group(1))].name == t.name:
+                    new.append(names[int(m.group(1))])   # pass-through: no new value
+                    continue
                 body.append("    const %s v%d_%d = (%s)(%s);" % (CTYPE[t.name], s, j, CTYPE[t.name], sub(e)))
                 new.append("v%d_%d" % (s, j))
             names, cur = new, list(st.out)
+    alias: List[Optional[int]] = [int(nm[3:]) if nm.startswith("v0_") else None for nm in names]
+    used = set(int(m.group(1)) for m in re.finditer(r"\bv0_(\d+)\b", "\n".join(
+        body[len(in_types):] + [nm for nm, a in zip(names, alias) if a is None])))
+    body = [ln for j, ln in enumerate(body) if j >= len(in_types) or j in used]
     params = ["long long n"]
     params += ["const %s* __restrict__ in%d" % (CTYPE[t.name], j) for j, t in enumerate(in_types)]
-    params += ["%s* __restrict__ out%d" % (CTYPE[t.name], j) for j, t in enumerate(cur)]
+    params += ["%s* __restrict__ out%d" % (CTYPE[t.name], j) for j, t in enumerate(cur) if alias[j] is None]
     if preds:
         params.append("unsigned char* __restrict__ keep")
     for j, nm in enumerate(names):
-        body.append("    out%d[i] = %s;" % (j, nm))
+        if alias[j] is None:
+            body.append("    out%d[i] = %s;" % (j, nm))
     if preds:
         body.append("    keep[i] = (%s) ? 1 : 0;" % " && ".join(preds))
-    src = ("extern \"C\" __global__ void __launch_bounds__(256) bs_fused(%s) {\n"
+    src = (PRELUDE + "extern \"C\" __global__ void __launch_bounds__(256) bs_fused(%s) {\n"
            "  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;\n"
            "       i += (long long)gridDim.x * blockDim.x) {\n%s\n  }\n}\n"
            % (", ".join(params), "\n".join(body)))
-    return src, cur, bool(preds)
+    return src, cur, bool(preds), alias
+
+
+def generate(in_types: Sequence[DType], stages: Sequence[Stage]) -> Tuple[str, List[DType], bool]:
+    """``generate_ex`` without the pass-through map."""
+    return generate_ex(in_types, stages)[:3]
 
 
 # ---------------------------------------------------------------------------
@@ -191,17 +238,18 @@ launch_count = 0
 def run_fused(cols: Sequence[torch.Tensor], in_types: Sequence[DType], stages: Sequence[Stage]):
     """Launch the fused kernel over device columns; returns (outputs, mask)."""
     global launch_count
-    src, out_types, has_pred = generate(in_types, stages)
-    fn = _function(src)
+    src, out_types, has_pred, alias = generate_ex(in_types, stages)
     n = int(cols[0].shape[0]) if cols else 0
     dev = cols[0].device
-    outs = [torch.empty(n, dtype=t.torch_dtype, device=dev) for t in out_types]
-    mask = torch.empty(n, dtype=torch.uint8, device=dev) if has_pred else None
-    if n == 0:
-        return outs, mask
     cols = [c.contiguous() for c in cols]
+    outs = [cols[a] if a is not None else torch.empty(n, dtype=t.torch_dtype, device=dev)
+            for t, a in zip(out_types, alias)]
+    mask = torch.empty(n, dtype=torch.uint8, device=dev) if has_pred else None
+    if n == 0 or (not has_pred and all(a is not None for a in alias)):
+        return outs, mask
+    fn = _function(src)
     args = [ctypes.c_longlong(n)] + [ctypes.c_void_p(c.data_ptr()) for c in cols] + \
-           [ctypes.c_void_p(o.data_ptr()) for o in outs]
+           [ctypes.c_void_p(o.data_ptr()) for o, a in zip(outs, alias) if a is None]
     if mask is not None:
         args.append(ctypes.c_void_p(mask.data_ptr()))
     argv = (ctypes.c_void_p * len(args))(*[ctypes.cast(ctypes.pointer(a), ctypes.c_void_p) for a in args])
@@ -240,7 +288,7 @@ def generate_fold(acc_type: DType, val_types: Sequence[DType], expr: str) -> str
     params = ["long long nseg", "const long long* __restrict__ seg"]
     params += ["const %s* __restrict__ in%d" % (CTYPE[t.name], j + 1) for j, t in enumerate(val_types)]
     params.append("%s* __restrict__ out" % A)
-    return ("extern \"C\" __global__ void __launch_bounds__(128) bs_fused(%s) {\n"
+    return (PRELUDE + "extern \"C\" __global__ void __launch_bounds__(128) bs_fused(%s) {\n"
             "  for (long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x; s < nseg;\n"
             "       s += (long long)gridDim.x * blockDim.x) {\n"
             "    %s acc = (%s)0;\n"
@@ -311,7 +359,10 @@ _BIN = [("||",), ("&&",), ("|",), ("^",), ("&",), ("==", "!="), ("<", "<=", ">",
         ("<<", ">>"), ("+", "-"), ("*", "/", "%")]
 _FUNCS = {"abs": torch.abs, "fabs": torch.abs, "sqrt": torch.sqrt, "floor": torch.floor,
           "ceil": torch.ceil, "exp": torch.exp, "log": torch.log,
-          "min": torch.minimum, "max": torch.maximum, "fmin": torch.minimum, "fmax": torch.maximum}
+          "min": torch.minimum, "max": torch.maximum, "fmin": torch.minimum, "fmax": torch.maximum,
+          "bs_abs": torch.abs, "bs_min": torch.minimum, "bs_max": torch.maximum,
+          "bs_pymod": torch.remainder, "bs_floordiv": lambda a, b: torch.div(a, b, rounding_mode="floor"),
+          "fmod": torch.fmod, "pow": torch.pow}
 
 
 def _tokens(expr: str):
@@ -421,7 +472,10 @@ class _Parser:
             if words and j < len(self.toks) and self.toks[j][1] == ")":
                 self.i = j + 1
                 v = self.unary()
-                dt = torch.int64 if "long" in words else _CAST[words[-1] if words[-1] != "unsigned" else "long"]
+                if words[:1] == ["unsigned"] and words[-1] == "char":
+                    dt = torch.uint8
+                else:
+                    dt = torch.int64 if "long" in words else _CAST[words[-1] if words[-1] != "unsigned" else "long"]
                 v = self.tensor(v)
                 if not dt.is_floating_point and dt != torch.bool and v.is_floating_point():
                     v = torch.trunc(v)

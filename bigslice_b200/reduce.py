@@ -75,4 +75,9 @@ def Reduce(slice_: Slice, reduce: Callable) -> Slice:
         typecheck.panicf("reduce: invalid reduce function %s, expected func(%s, %s) %s",
                          _fn_name(reduce), vt, vt, vt)
     func.Out = Type([vt])
+    if func.builtin is None and not func.rowwise and not func.takes_ctx:
+        # ``lambda a, b: a + b`` is the builtin ``add``: recognise it so python combiners take
+        # the fused hash-combine/exchange lowering too (ops/trace.py)
+        from .ops import trace
+        func.builtin = trace.recognise_combiner(reduce, vt)
     return _Reduce(slice_, func)

@@ -516,6 +516,11 @@ def _resolve_out(op: str, func: slicefunc.Func, arg: Type, out, fn, flat=False) 
     if func.Out is not None:
         return func.Out
     t = func.infer_out(arg, flat)
+    if t is None and not flat:
+        from .ops import trace   # the zero-row probe failed: the symbolic trace also knows the types
+        tys = trace.infer_out(func, arg.cols)
+        if tys is not None:
+            t = func.Out = Type(tys)
     if t is None:
         typecheck.panicf("%s: cannot infer output types of %s; annotate it or pass out=",
                          op, _fn_name(fn))
@@ -526,20 +531,40 @@ class _Map(Slice):
     def __init__(self, s, func, typ, pragmas):
         super().__init__(make_name("map"), typ, s.num_shard(), [Dep(s)], pragmas)
         self.func = func
+        self.in_typ = s.typ
+        self._stage = False   # not traced yet (None: not traceable)
+
+    def _apply(self, cols, n, device):
+        func, typ = self.func, self.typ
+        out = func.call(_context.current(), cols)
+        if len(out) != typ.num_out():
+            raise errors.fatal("map: function returned %d columns, want %d"
+                               % (len(out), typ.num_out()))
+        return [_coerce(c, t, n, device) for c, t in zip(out, typ.cols)]
+
+    def traced(self):
+        """The function as a fused-kernel stage (``ops/trace.py``), or None."""
+        if self._stage is False:
+            from .ops import trace
+            st = None
+            if not trace.rejected(self.func.fn):
+                st = trace.trace_map(self.func, self.in_typ.cols, self.typ.cols)
+            if st is not None:
+                st.eager, st.fn = self._apply, self.func.fn
+            self._stage = st
+        return self._stage
 
     def reader(self, shard, deps):
-        src, func, typ = deps[0], self.func, self.typ
+        src, typ = deps[0], self.typ
+        st = self.traced()
+        if st is not None:
+            return _chain_stage(src, self.in_typ, st, typ)
 
         def read(n):
             f = src.read(n)
             if f is None:
                 return None
-            cols = func.call(_context.current(), f.cols())
-            if len(cols) != typ.num_out():
-                raise errors.fatal("map: function returned %d columns, want %d"
-                                   % (len(cols), typ.num_out()))
-            cols = [_coerce(c, t, len(f), f.device) for c, t in zip(cols, typ.cols)]
-            return Frame(cols, typ)
+            return Frame(self._apply(f.cols(), len(f), f.device), typ)
 
         return FuncReader(read, src.close)
 
@@ -587,19 +612,37 @@ class _Filter(Slice):
     def __init__(self, s, func, pragmas):
         super().__init__(make_name("filter"), s.typ, s.num_shard(), [Dep(s)], pragmas)
         self.func = func
+        self._stage = False
+
+    def _mask(self, cols, n, device):
+        (m,) = self.func.call(_context.current(), cols)
+        if not isinstance(m, torch.Tensor):
+            m = torch.as_tensor(np.asarray(m, dtype=bool))
+        return m.to(torch.bool)
+
+    def traced(self):
+        if self._stage is False:
+            from .ops import trace
+            st = None
+            if not trace.rejected(self.func.fn):
+                st = trace.trace_filter(self.func, self.typ.cols)
+            if st is not None:
+                st.eager, st.fn = self._mask, self.func.fn
+            self._stage = st
+        return self._stage
 
     def reader(self, shard, deps):
-        src, func = deps[0], self.func
+        src = deps[0]
+        st = self.traced()
+        if st is not None:
+            return _chain_stage(src, self.typ, st, self.typ)
 
         def read(n):
             while True:
                 f = src.read(n)
                 if f is None:
                     return None
-                (m,) = func.call(_context.current(), f.cols())
-                if not isinstance(m, torch.Tensor):
-                    m = torch.as_tensor(np.asarray(m, dtype=bool))
-                m = m.to(torch.bool)
+                m = self._mask(f.cols(), len(f), f.device)
                 if m.is_cuda:
                     from .ops import gpu
                     if gpu.available():
@@ -727,6 +770,42 @@ class _Fold(Slice):
         self.func = func
         self.expr = expr
         self.in_typ = s.typ
+        self._traced = False
+
+    def traced_expr(self) -> Optional[str]:
+        """The python fold function as a device-kernel expression (``ops/trace.py``)."""
+        if self._traced is False:
+            from .ops import trace
+            e = None
+            if self.func is not None and self.func.fn is not None and not trace.rejected(self.func.fn):
+                e = trace.trace_fold(self.func, self.typ.out(1), list(self.in_typ.cols[1:]))
+                if e is not None:
+                    from .ops import jit
+                    try:
+                        jit.generate_fold(self.typ.out(1), list(self.in_typ.cols[1:]), e)
+                    except (TypeError, ValueError):
+                        e = None
+            self._traced = e
+        return self._traced
+
+    def _traced_fold(self, acc_t, vals, starts, off) -> Optional[torch.Tensor]:
+        """Device fold with the traced expression; the first use of a function is
+        cross-checked on a bounded prefix against the function itself."""
+        from .ops import jit, trace
+        expr, fn = self.traced_expr(), self.func.fn
+        vt = list(self.in_typ.cols[1:])
+        if not trace.verified(fn):
+            m = min(int(vals[0].shape[0]), 1024)
+            soff = torch.cat([off[off < m], torch.tensor([m], dtype=torch.int64, device=off.device)])
+            got = jit.run_fold(acc_t, [v[:m] for v in vals], vt, soff, expr)
+            want = segmented_fold(acc_t, [v[:m] for v in vals], starts[:m], self.func, _context.current())
+            if not _same_columns([got], [want]):
+                trace.reject(fn)
+                self._traced = None
+                log.warning("fused form of %s disagrees with the function; running it eagerly", _fn_name(fn))
+                return None
+            trace.mark_verified(fn)
+        return jit.run_fold(acc_t, vals, vt, off, expr)
 
     def _fold_frame(self, f: Frame) -> Frame:
         """Fold one materialised shard.  Three tiers:
@@ -765,6 +844,11 @@ class _Fold(Slice):
             else:
                 acc = jit.fold_host(acc_t, vals, off, self.expr)
             return Frame([keys, acc], self.typ)
+        if dev.type == "cuda" and _gpu_ok() and len(idx) and self.traced_expr() is not None:
+            off = torch.cat([idx.to(torch.int64), torch.tensor([len(f)], dtype=torch.int64, device=idx.device)])
+            acc = self._traced_fold(acc_t, vals, starts, off)
+            if acc is not None:
+                return Frame([keys, acc], self.typ)
         if not self.func.rowwise and isinstance(vals[0], torch.Tensor) and len(idx):
             seglen = torch.diff(torch.cat([idx, torch.tensor([len(f)], device=idx.device)]))
             longest = int(seglen.max())
@@ -829,6 +913,12 @@ def Fold(slice_: Slice, fold: Callable, *pragmas, acc=None) -> Slice:
     if func.In is not None and not typecheck.can_apply(
             func.In.cols, Type([acc_t] + list(slice_.typ.cols[1:])), func.is_variadic):
         typecheck.panicf("fold: expected func(acc, t2, t3, ..., tn), got %s", _fn_name(fold))
+    if func.builtin is None and n == 2 and slice_.out(1) == acc_t and not func.rowwise and not func.takes_ctx:
+        # ``lambda acc, v: acc + v`` is the builtin add (ops/trace.py): hash-aggregation kernels
+        from .ops import trace
+        func.builtin = trace.recognise_combiner(fold, acc_t)
+        if func.builtin == "first":    # fold(acc, v) = acc is not the combiner "first"
+            func.builtin = None
     return _Fold(slice_, func, Type([key, acc_t], 1), pragmas)
 
 
@@ -1006,40 +1096,125 @@ def default_partitioner(frame: Frame, nshard: int) -> torch.Tensor:
 
 class _ExprReader(Reader):
     """Evaluates a chain of expression stages over each tile in one fused
-    kernel (device) or with torch ops under C semantics (host)."""
+    kernel (device) or stage by stage on the host: traced python stages run their
+    original function there, string-expression stages are interpreted with torch
+    ops under C semantics."""
 
     def __init__(self, src: Reader, in_typ: Type, stages: list, out_typ: Type):
         self.src, self.in_typ, self.stages, self.out_typ = src, in_typ, stages, out_typ
         self.started = False
+        self.eager_only = False
+
+    def _host(self, cols, n, device):
+        """Stage-by-stage evaluation; rows are dropped at every Filter, so a later
+        stage never sees a row an earlier predicate rejected."""
+        from .ops import jit
+        cur, types = list(cols), list(self.in_typ.cols)
+        for st in self.stages:
+            if st.eager is not None:
+                r = st.eager(cur, n, device)
+                mask = r if st.pred is not None else None
+                cur = cur if st.pred is not None else r
+            else:
+                cur, mask = jit.eval_host(cur, types, [st])
+            if st.pred is None:
+                types = list(st.out)
+            elif mask is not None:
+                if mask.is_cuda and _gpu_ok():
+                    from .ops import gpu
+                    idx = gpu.compact_indices(mask.view(torch.bool) if mask.dtype == torch.uint8 else mask)
+                    cur = [C.col_take(c, idx) for c in cur]
+                    n = int(idx.numel())
+                else:
+                    cur = [c[mask] for c in cur]
+                    n = int(cur[0].shape[0]) if cur else 0
+        return cur
+
+    def _device(self, cols, n, device):
+        from .ops import gpu, jit, trace
+        try:
+            outs, mask = jit.run_fused(cols, self.in_typ.cols, self.stages)
+        except RuntimeError as e:
+            traced = [st for st in self.stages if st.fn is not None]
+            if not traced or "does not compile" not in str(e):
+                raise
+            # a traced function produced source NVRTC rejects: the function still runs eagerly
+            for st in traced:
+                trace.reject(st.fn)
+            log.warning("fused form of %s does not compile (%s); running it eagerly",
+                        ", ".join(_fn_name(st.fn) for st in traced), str(e).splitlines()[0])
+            self.eager_only = True
+            return self._host(cols, n, device)
+        if mask is not None:
+            idx = gpu.compact_indices(mask.view(torch.bool))
+            outs = [gpu.gather_rows(o, idx) if o.dtype != torch.bool else o[idx] for o in outs]
+        unchecked = [st for st in self.stages if st.fn is not None and not trace.verified(st.fn)]
+        if unchecked:
+            # first tile of a traced python function: its fused result must equal what the
+            # function itself computes (a bounded prefix is enough to catch an impure or
+            # mis-traced function; it then runs eagerly from here on)
+            m = min(n, 4096)
+            ref = self._host([c[:m] for c in cols], m, device)
+            if mask is not None:
+                k = int(mask[:m].sum())
+            else:
+                k = m
+            if _same_columns(ref, [o[:k] for o in outs]):
+                for st in unchecked:
+                    trace.mark_verified(st.fn)
+            else:
+                for st in unchecked:
+                    trace.reject(st.fn)
+                log.warning("fused form of %s disagrees with the function; running it eagerly",
+                            ", ".join(_fn_name(st.fn) for st in unchecked))
+                self.eager_only = True
+                return self._host(cols, n, device)
+        return outs
 
     def read(self, n=None):
-        from .ops import jit
         self.started = True
         while True:
             f = self.src.read(n)
             if f is None:
                 return None
             cols = f.cols()
-            on_gpu = f.device.type == "cuda"
-            if on_gpu:
-                from .ops import gpu
-                on_gpu = gpu.available()
-            if on_gpu and len(f):
-                outs, mask = jit.run_fused(cols, self.in_typ.cols, self.stages)
-                if mask is not None:
-                    from .ops import gpu
-                    idx = gpu.compact_indices(mask.view(torch.bool))
-                    outs = [gpu.gather_rows(o, idx) if o.dtype != torch.bool else o[idx] for o in outs]
-            else:
-                outs, mask = jit.eval_host(cols, self.in_typ.cols, self.stages)
-                if mask is not None:
-                    outs = [o[mask] for o in outs]
+            on_gpu = f.device.type == "cuda" and _gpu_ok() and len(f) > 0 and not self.eager_only
+            outs = self._device(cols, len(f), f.device) if on_gpu else self._host(cols, len(f), f.device)
             out = Frame(list(outs), self.out_typ)
             if len(out) or n is None:
                 return out
 
     def close(self):
         self.src.close()
+
+
+def _gpu_ok() -> bool:
+    from .ops import gpu
+    return gpu.available()
+
+
+def _same_columns(a, b) -> bool:
+    if len(a) != len(b):
+        return False
+    for x, y in zip(a, b):
+        if x.shape != y.shape or x.dtype != y.dtype:
+            return False
+        if x.is_floating_point():
+            if not torch.allclose(x, y, rtol=1e-4, atol=1e-6, equal_nan=True):
+                return False
+        elif not torch.equal(x, y):
+            return False
+    return True
+
+
+def _chain_stage(src: Reader, in_typ: Type, stage, out_typ: Type) -> Reader:
+    """Append ``stage`` to the fused chain feeding ``src`` (one kernel for the
+    whole chain) or start a new chain."""
+    from .sliceio import LabelReader
+    inner = src.reader if isinstance(src, LabelReader) else src
+    if isinstance(inner, _ExprReader) and not inner.started:
+        return _ExprReader(inner.src, inner.in_typ, inner.stages + [stage], out_typ)
+    return _ExprReader(src, in_typ, [stage], out_typ)
 
 
 class _ExprSlice(Slice):
@@ -1049,13 +1224,7 @@ class _ExprSlice(Slice):
         self.in_typ = s.typ
 
     def reader(self, shard, deps):
-        from .sliceio import LabelReader
-        src = deps[0]
-        inner = src.reader if isinstance(src, LabelReader) else src
-        if isinstance(inner, _ExprReader) and not inner.started:
-            # fuse with the upstream expression stage(s): one kernel for the chain
-            return _ExprReader(inner.src, inner.in_typ, inner.stages + [self.stage], self.typ)
-        return _ExprReader(src, self.in_typ, [self.stage], self.typ)
+        return _chain_stage(deps[0], self.in_typ, self.stage, self.typ)
 
 
 def _check_expr_cols(op: str, s: Slice, exprs):
