@@ -69,7 +69,7 @@ def segmented_reduce(values, starts: torch.Tensor, fn: Callable,
         return values
     seg = torch.cumsum(starts.to(torch.int64), 0) - 1
     nseg = int(seg[-1]) + 1
-    name = builtin_name(fn)
+    name = builtin_name(fn) or (func.builtin if func is not None else None)
     if isinstance(values, torch.Tensor) and not rowwise:
         seg = seg.to(values.device)
         if name in SCATTER and values.dtype not in (torch.bool,) and values.dim() == 1:
