@@ -136,6 +136,7 @@ class SpmdExecutor(LocalExecutor):
         self._dest_tables: Dict[tuple, Any] = {}     # (hint key, capacity) -> destination table
         self._out_sets: Dict[tuple, list] = {}       # hint key -> [(keys, vals, weakref to the frame)]
         self.group_cancel: Dict[int, threading.Event] = {}
+        self._attempts: Dict[tuple, int] = {}        # (invocation, group name) -> exchanges issued
         self.fault_hook = None                       # tests: called as hook(stage, group_name)
 
     def name(self) -> str:
@@ -527,6 +528,21 @@ class SpmdExecutor(LocalExecutor):
             acc = (acc * 1000003 + fp) & ((1 << 61) - 1)
         return acc, fps
 
+    def _tag_exchange(self, acc: int, head: Task) -> int:
+        """Fold *which* exchange this is — invocation, group, attempt — into the
+        fingerprint the ranks compare.  Ranks whose exchange sequences diverged (one
+        of them retrying a group the others consider done) then fail the vote on
+        both sides instead of pairing two different exchanges."""
+        import zlib
+        key = (head.name.inv_index, str(head.name))
+        with self._glock:
+            n = self._attempts[key] = self._attempts.get(key, 0) + 1
+            if len(self._attempts) > 4096:
+                for k in list(self._attempts)[:2048]:
+                    del self._attempts[k]
+        tag = zlib.crc32(("%d/%s/%d" % (key[0], key[1], n)).encode())
+        return (acc * 1000003 + tag) & ((1 << 61) - 1)
+
     def _rx(self):
         """The Reduce exchange state (created collectively on first use: every
         rank takes the table path for the same groups)."""
@@ -568,8 +584,9 @@ class SpmdExecutor(LocalExecutor):
             raise errors.fatal("spmd: a producer of %s failed on some rank" % head.name)
         if any(v[1] != acc for v in votes):
             where = ", ".join("inv%d at %s (func #%d)" % f[:3] for f in fps) or "an earlier invocation"
-            raise errors.fatal("ranks issued different invocations (%s, rank %d); SPMD programs must "
-                               "run identical Session.run sequences" % (where, self.rank))
+            raise errors.fatal("ranks issued different invocations, or their exchange sequences diverged "
+                               "(%s; rank %d is at the exchange of %s); SPMD programs must run identical "
+                               "Session.run sequences" % (where, self.rank, head.name))
         return [v[2] for v in votes]
 
     def _exchange_table(self, gid: int, head: Task, table, nparts: int, bad: int = 0) -> None:
@@ -635,6 +652,7 @@ class SpmdExecutor(LocalExecutor):
             if table is None:  # this rank had no rows: an empty table still takes part
                 table = gpu.table_pool().get(1024, vdtype, op, self.device)
             acc, fps = self._take_fingerprint(head.name.inv_index)
+            acc = self._tag_exchange(acc, head)
             # order the exchange stream after the producers' combine kernels
             after = torch.cuda.Event()
             after.record(torch.cuda.default_stream(self.device))
@@ -646,14 +664,15 @@ class SpmdExecutor(LocalExecutor):
             pend = None
             first_err = None
             first_run = not all(h is not None for h in hints)
+            # destination tables that do not fit in L2 are combined region by region
+            # (rows are bucketed by region at the source); the region count decides the
+            # landing layout, so it must be the same on every rank whichever path each
+            # takes: it only ever changes at a board vote (below), from the table sizes
+            # all ranks posted there
+            regions = int(self.card_hints.get(self._hint_key(head, "regions"), 1))
             with torch.cuda.stream(rx.stream):
                 if all(h is not None for h in hints):
                     dests = []
-                    # destination tables that do not fit in L2 are combined region by
-                    # region (rows are bucketed by region at the source); the region count
-                    # must be the same on every rank: every rank derives it from the
-                    # largest shard's hint, which the report of the last run carried
-                    regions = int(self.card_hints.get(self._hint_key(head, "regions"), 1))
                     for j, h, dk in zip(locals_, hints, dkeys):
                         # The destination table and the output buffers are tied to the
                         # slice (not pooled): the same pointers every step, so the
@@ -678,12 +697,13 @@ class SpmdExecutor(LocalExecutor):
                     # arrives, then everything is sized exactly
                     with span("xchg/first_run_sync"):
                         probe = rx.exchange_probe(table, nparts, vote=(1 if bad else 0, acc),
-                                                  keymode=lay.mode)
+                                                  keymode=lay.mode, regions=regions)
                         rep = probe.resolve()
                     dests = []
                     if rep.error == 0:
                         for j in locals_:
                             rows = int(rep.recv_rows[j])
+                            # (quantised capacities are multiples of 64: they split into regions)
                             dt = gpu.table_pool().get(gpu.table_capacity(rows + 1024), vdtype, op,
                                                       self.device, warm=0)
                             cap = rows + 16
@@ -695,7 +715,7 @@ class SpmdExecutor(LocalExecutor):
                         self._learner(head, lkey, dkeys, nparts)(rep)
                     pend = rx.exchange_finish(table, nparts, dests,
                                               on_report=None if first_err else
-                                              self._learner(head, lkey, dkeys, nparts))
+                                              self._learner(head, lkey, dkeys, nparts), regions=regions)
                 done = pend.event
             table.ready = done  # the next user's stream waits for the scatter on the device
             gpu.table_pool().put(table, clean=True)

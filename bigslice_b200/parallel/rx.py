@@ -331,17 +331,22 @@ class ReduceExchange:
         self._chk(lib.bs_rx_end(ctypes.byref(pe), st, c_int(n), stp, caps, bits, self.xring.ptr,
                                 c_int(NSLOTS), c_int(1), s), "rx_end")
 
-    def exchange_probe(self, table, nparts: int, vote: Tuple[int, int] = (0, 0), keymode: int = 0) -> Pending:
+    def exchange_probe(self, table, nparts: int, vote: Tuple[int, int] = (0, 0), keymode: int = 0,
+                       regions: int = 1) -> Pending:
         """First half of an exchange whose destination sizes are unknown (first
         run of a slice): scatter + wait, then publish how many rows arrived for
         every local shard.  Call on the exchange stream; follow with
-        :meth:`exchange_finish` after sizing the destination tables."""
-        pe = self._peers_for(nparts, 1)
+        :meth:`exchange_finish` after sizing the destination tables.  ``regions``
+        must be what the peers use for this exchange (the landing layout depends on
+        it), whichever half-path each of them takes."""
+        if nparts * regions > MAXP:
+            raise RuntimeError("reduce exchange supports at most %d (shards x regions)" % MAXP)
+        pe = self._peers_for(nparts, regions)
         lib, st = self.lib, c_void_p(self.state.data_ptr())
         s = gpu._stream()
         self._chk(lib.bs_rx_set_vote(st, c_ull(vote[0]), c_ull(vote[1]), s), "rx_set_vote")
         self._enqueue_send(pe, table, nparts, keymode)
-        pl = pe.shards_per_rank
+        pl = pe.shards_per_rank // regions
         stp, caps = (c_void_p * pl)(), (c_ll * pl)()
         self._chk(lib.bs_rx_end(ctypes.byref(pe), st, c_int(pl), stp, caps, c_ull(0), self.xring.ptr,
                                 c_int(NSLOTS), c_int(0), s), "rx_end(probe)")
@@ -350,9 +355,11 @@ class ReduceExchange:
         self.stats["direct"] += 1
         return Pending(self, self.xring, self.epoch + 1, ev)
 
-    def exchange_finish(self, table, nparts: int, dests: Sequence[tuple], on_report=None) -> Pending:
-        """Second half: combine on arrival, compaction, acknowledgement."""
-        pe = self._peers_for(nparts, 1)
+    def exchange_finish(self, table, nparts: int, dests: Sequence[tuple], on_report=None,
+                        regions: int = 1) -> Pending:
+        """Second half: combine on arrival, compaction, acknowledgement and the
+        closing agreement (every rank reports the same verdict)."""
+        pe = self._peers_for(nparts, regions)
         self._enqueue_recv(pe, table, nparts, dests, int(pe.region_rows) * self.world)
         ev = torch.cuda.Event()
         ev.record()

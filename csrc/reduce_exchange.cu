@@ -52,13 +52,14 @@ enum RxError {
   RX_PRODUCER_FAILED = 3,   // a rank reported failed producers
   RX_FINGERPRINT = 4,       // ranks issued different invocations
   RX_TIMEOUT = 5,           // a peer did not show up (or aborted)
-  RX_DEST_OVERFLOW = 6,     // destination table / output buffer too small (local)
+  RX_DEST_OVERFLOW = 6,     // destination table / output buffer too small on some rank
 };
 
 // Symmetric control block: one per rank, mapped by every peer (CUDA IPC).
 struct RxCtrl {
   unsigned long long data_flag[RX_MAXW];  // [src] last epoch whose rows from src are complete here
   unsigned long long ack[RX_MAXW];        // [dst] last epoch dst has finished reading (written by dst)
+  unsigned long long fin[RX_MAXW];        // [src] (epoch << 8) | src's outcome of that epoch (see rx_end)
   unsigned long long abort_flag;
   unsigned long long pad[7];
   long long cnt[2][RX_MAXW][RX_MAXP];      // [parity][src][shard] rows written
@@ -488,8 +489,15 @@ struct RxEndArgs {
   unsigned long long clear_bits; // identity bit pattern: the tables were compacted-and-cleared
 };
 
+// Everything a rank can only find out after combining (destination table or output
+// buffer too small) is rank-local knowledge; a rank that retried on its own would
+// pair its repeated exchange with the peers' *next* one.  So the exchange ends with
+// a second, tiny agreement: every rank stores its outcome into every peer's `fin`
+// slot and reads the others' — the report carries the same verdict on every rank
+// and a lost exchange is retried by all of them together.
 __global__ void __launch_bounds__(64) rx_end_kernel(RxPeers pe, RxState* st, int nlocal, RxEndArgs a,
                                                     RxReport* ring, int nslots, int ack) {
+  __shared__ int verdict;
   const int tid = threadIdx.x;
   const unsigned long long epoch = st->epoch;
   RxReport* rep = ring + (epoch % (unsigned long long)nslots);
@@ -514,7 +522,35 @@ __global__ void __launch_bounds__(64) rx_end_kernel(RxPeers pe, RxState* st, int
         d->out_count = 0;
       }
     }
-    rep->error = err;
+    verdict = (int)err;
+  }
+  __syncthreads();
+  const int mine = verdict;
+  __syncthreads();
+  if (ack) {  // (the probe half of a first-run exchange ends without acknowledging: no agreement yet)
+    if (tid < pe.world)
+      bs_st_release_sys(&pe.ctrl[tid]->fin[pe.rank], (epoch << 8) | (unsigned long long)(mine & 0xff));
+    if (tid < pe.world && mine != RX_TIMEOUT) {
+      const unsigned long long* f = &pe.ctrl[pe.rank]->fin[tid];
+      const unsigned long long t0 = bs_globaltimer_ns();
+      unsigned long long v;
+      bool ok = true;
+      while (((v = bs_ld_acquire_sys(f)) >> 8) < epoch) {
+        if (bs_ld_relaxed_sys(&pe.ctrl[pe.rank]->abort_flag) != 0 || bs_globaltimer_ns() - t0 > st->timeout_ns) {
+          ok = false;
+          break;
+        }
+        __nanosleep(100);
+      }
+      if (!ok) atomicMax(&verdict, RX_TIMEOUT);
+      else if ((v >> 8) == epoch && (v & 0xffULL) != 0) atomicMax(&verdict, (int)(v & 0xffULL));
+    }
+    __syncthreads();
+  }
+  if (tid == 0) {
+    if (ack && verdict == RX_TIMEOUT && mine != RX_TIMEOUT)
+      for (int p = 0; p < pe.world; ++p) bs_st_release_sys(&pe.ctrl[p]->abort_flag, 1ULL);
+    rep->error = (long long)verdict;
     rep->need_rows = (long long)st->need_rows;
     rep->sent_rows = st->sent_rows;
     __threadfence_system();

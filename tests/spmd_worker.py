@@ -361,6 +361,34 @@ def async_table_checks(sess, ex, world, rank):
         dist.all_reduce(tot, group=ex.ctrl_group)
         out["overflow_recovered_ok"] = int(tot[0]) == n * world * S and ex.rx.arena_bytes > before
         res.discard()
+    # (d) a destination overflow on ONE rank only: partition 1 (owned by rank 1 % world)
+    # receives three times the distinct keys the hints of this call site promise.  The
+    # exchange's closing agreement gives every rank the same verdict, all of them repeat
+    # the exchange (exactly sized this time) — nobody retries on its own.
+    if ex.rx is not None:
+        from bigslice_b200.ops import gpu
+        P = world * S
+        ex._want_arena = 0
+        ex.rx.reset(ex.rx.bytes_for(P, 4 * n))     # landing regions are not the limit here
+        cand = torch.arange(0, 8 * n * P, device=dev) * 3 + 1000003
+        cand = cand[(gpu.hash_column(cand) % P) == 1][:3 * n]
+        assert cand.numel() == 3 * n
+        mine = cand[rank::world].contiguous()
+        shards = [(mine, torch.ones(mine.numel(), dtype=torch.int64, device=dev)) if s == rank else empty
+                  for s in range(P)]
+        wc.register_source("skew", wc.DeviceRows(shards))
+        before = len(ex.exchange_log)
+        res = sess.run(wc.wordcount, "skew")
+        f = res.to_frame()
+        tot = torch.tensor([len(f), int(f.col(1).sum()) if len(f) else 0], dtype=torch.int64)
+        dist.all_reduce(tot, group=ex.ctrl_group)
+        attempts = torch.tensor([len(ex.exchange_log) - before], dtype=torch.int64)
+        lo, hi = attempts.clone(), attempts.clone()
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN, group=ex.ctrl_group)
+        dist.all_reduce(hi, op=dist.ReduceOp.MAX, group=ex.ctrl_group)
+        out["dest_overflow_attempts"] = [int(lo[0]), int(hi[0])]
+        out["dest_overflow_recovered_ok"] = tot.tolist() == [3 * n, 3 * n] and int(lo[0]) == int(hi[0]) == 2
+        res.discard()
     return out
 
 

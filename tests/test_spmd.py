@@ -45,7 +45,8 @@ def check(outs, world):
             assert o[k], (k, o)
     for o in outs:
         for k in ("exchange_content_ok", "table_exchange_ok", "exchange_vote_ok", "bigcount_ok",
-                  "sentinel_ok", "distinct_ok", "hints_ok", "overflow_recovered_ok", "recovery_ok"):
+                  "sentinel_ok", "distinct_ok", "hints_ok", "overflow_recovered_ok", "dest_overflow_recovered_ok",
+                  "recovery_ok"):
             if k in o:
                 assert o[k], (k, o["rank"])
     if world > 1:

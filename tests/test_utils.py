@@ -46,3 +46,65 @@ def test_topology_binding_is_safe_without_nvml():
         del os.environ["BIGSLICE_NO_NUMA_BIND"]
         if before is not None:
             os.sched_setaffinity(0, before)
+
+
+def test_status_board_vote_and_diverged_exchange_sequences():
+    """Two 'ranks' (threads) vote through the shared-memory board.  Equal exchange
+    tags agree and return every rank's integer; a rank that repeats an exchange on
+    its own (attempt 2 against the peer's attempt 1 of the next group) makes the
+    vote fail on BOTH sides instead of pairing two different exchanges."""
+    import pytest
+    from bigslice_b200 import errors
+    from bigslice_b200.exec.spmd import SpmdExecutor
+    from bigslice_b200.utils.shmboard import Board
+
+    class Name:
+        def __init__(self, inv, s):
+            self.inv_index, self.s = inv, s
+
+        def __str__(self):
+            return self.s
+
+    class Head:
+        def __init__(self, inv, s):
+            self.name = Name(inv, s)
+
+    name = "bigslice-test-board-%d" % os.getpid()
+    exs = []
+    for r in range(2):
+        ex = SpmdExecutor(device=None)
+        ex.rank, ex.world, ex.exchange_timeout = r, 2, 5.0
+        ex.board = Board(name, 2, r, create=(r == 0))
+        exs.append(ex)
+    try:
+        G, H = Head(3, "inv3_reduce_0"), Head(3, "inv3_reduce_1")
+        assert exs[0]._tag_exchange(7, G) == exs[1]._tag_exchange(7, G)     # same exchange, same tag
+        assert exs[0]._tag_exchange(7, G) != exs[1]._tag_exchange(7, H)     # attempt 2 of G vs attempt 1 of H
+        assert exs[0]._tag_exchange(7, H) != exs[1]._tag_exchange(7, G)     # (both ranks have now issued G, G, H)
+
+        def vote(ex, acc, head, extra, out):
+            try:
+                out.append(ex._board_vote(0, acc, [], head, extra=extra))
+            except errors.Error as e:
+                out.append(e)
+        # in step: both at attempt 3 of G
+        outs = [[], []]
+        accs = [ex._tag_exchange(0, G) for ex in exs]
+        ts = [threading.Thread(target=vote, args=(exs[r], accs[r], G, 100 + r, outs[r])) for r in range(2)]
+        [t.start() for t in ts]
+        [t.join() for t in ts]
+        assert outs[0] == outs[1] == [[100, 101]]
+        # diverged: rank 1 repeats G on its own while rank 0 moved on to H
+        outs = [[], []]
+        accs = [exs[0]._tag_exchange(0, H), exs[1]._tag_exchange(0, G)]
+        heads = [H, G]
+        ts = [threading.Thread(target=vote, args=(exs[r], accs[r], heads[r], 0, outs[r])) for r in range(2)]
+        [t.start() for t in ts]
+        [t.join() for t in ts]
+        for o in outs:
+            assert isinstance(o[0], errors.Error) and "diverged" in str(o[0])
+            with pytest.raises(errors.Error):
+                raise o[0]
+    finally:
+        for r in (1, 0):
+            exs[r].board.close(unlink=(r == 0))
