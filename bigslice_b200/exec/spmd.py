@@ -561,8 +561,15 @@ class SpmdExecutor(LocalExecutor):
             return
         self.xseq += 1
         self.board.post(self.xseq, 0, -1)
-        if self.board.wait_all(self.xseq, self.exchange_timeout) is None:
+        votes = self.board.wait_all(self.xseq, self.exchange_timeout)
+        if votes is None:
             raise errors.TaskLostError("spmd: rank(s) %s unreachable" % self.board.missing(self.xseq))
+        others = [r for r, v in enumerate(votes) if v[1] != -1]
+        if others:
+            # they are voting on an ordinary exchange: entering the collective reset now
+            # would leave this rank in a barrier nobody else joins
+            raise errors.fatal("spmd: exchange sequences diverged: rank %d re-establishes the exchange after a "
+                               "lost one while rank(s) %s carry on with the next" % (self.rank, others))
 
     def _board_vote(self, bad: int, acc: int, fps, head: Task, extra: int = 0) -> List[int]:
         """Host-side agreement for one exchange: post my status + fingerprint (and
@@ -967,26 +974,40 @@ class SpmdExecutor(LocalExecutor):
         return out
 
     def _shuffle_objects(self, f: Frame, ids: torch.Tensor, nparts: int):
-        """Any column type: codec-encoded per-shard frames over the control
-        plane (all_gather_object)."""
+        """Any column type (host strings, lists, python objects): codec-encoded
+        per-shard frames, each sent **only to the rank that owns the shard** — one
+        all-to-all of byte counts and one of the bytes over the control-plane group
+        (round 1 all-gathered every rank's whole send set to every rank)."""
         parts = split_by_partition(f, ids, nparts) if len(f) else []
-        mine = {}
+        per_rank: List[Dict[int, bytes]] = [dict() for _ in range(self.world)]
         for p, g in enumerate(parts):
             if len(g) and self.owner(p) != self.rank:
-                mine[p] = encode_frame(g.to("cpu") if g.device.type != "cpu" else g)
-        allsends: List = [None] * self.world
+                per_rank[self.owner(p)][p] = encode_frame(g.to("cpu") if g.device.type != "cpu" else g)
+        received: List[Dict[int, bytes]] = []
         if self.world > 1:
-            dist.all_gather_object(allsends, mine, group=self.ctrl_group)
+            blobs = [pickle.dumps(d, protocol=pickle.HIGHEST_PROTOCOL) if d else b"" for d in per_rank]
+            send_counts = torch.tensor([len(b) for b in blobs], dtype=torch.int64)
+            recv_counts = torch.empty_like(send_counts)
+            dist.all_to_all_single(recv_counts, send_counts, group=self.ctrl_group)
+            payload = b"".join(blobs)
+            send = torch.frombuffer(bytearray(payload), dtype=torch.uint8) if payload \
+                else torch.empty(0, dtype=torch.uint8)
+            recv = torch.empty(int(recv_counts.sum()), dtype=torch.uint8)
+            dist.all_to_all_single(recv, send, recv_counts.tolist(), send_counts.tolist(), group=self.ctrl_group)
+            raw = recv.numpy().tobytes()
+            at = 0
+            for n in recv_counts.tolist():
+                received.append(pickle.loads(raw[at:at + n]) if n else {})
+                at += n
         out: Dict[int, List[Frame]] = {}
         for p in range(self.rank, nparts, self.world):
             frs = []
             if parts and len(parts[p]):
                 frs.append(parts[p])
-            for r, sends in enumerate(allsends):
-                if r == self.rank or not sends or p not in sends:
+            for r, sends in enumerate(received):
+                if r == self.rank or p not in sends:
                     continue
-                b = sends[p]
-                frs.append(_decode_one(b, f.typ, self.device))
+                frs.append(_decode_one(sends[p], f.typ, self.device))
             out[p] = frs
         return out
 
