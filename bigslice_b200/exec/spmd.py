@@ -137,6 +137,7 @@ class SpmdExecutor(LocalExecutor):
         self._out_sets: Dict[tuple, list] = {}       # hint key -> [(keys, vals, weakref to the frame)]
         self.group_cancel: Dict[int, threading.Event] = {}
         self._attempts: Dict[tuple, int] = {}        # (invocation, group name) -> exchanges issued
+        self._group_pend: Dict[int, Any] = {}        # gid -> outcome handle of the exchange in place
         self.fault_hook = None                       # tests: called as hook(stage, group_name)
 
     def name(self) -> str:
@@ -637,6 +638,8 @@ class SpmdExecutor(LocalExecutor):
                     else:
                         self.card_hints[key] = 4 * max(self.card_hints.get(key, 0), int(rep.out_rows[0]), 1 << 14)
                 pend = rx.publish(table.status, cap, on_report=learned)
+                with self._glock:
+                    self._group_pend[gid] = pend
                 gpu.table_pool().put(table, clean=True)
                 out[0] = [DeferredFrame([ok, ov], typ, self._resolver(pend, gid, head, 0), finalize=fin)]
             mode = "table-local"
@@ -724,6 +727,8 @@ class SpmdExecutor(LocalExecutor):
                                               on_report=None if first_err else
                                               self._learner(head, lkey, dkeys, nparts), regions=regions)
                 done = pend.event
+            with self._glock:
+                self._group_pend[gid] = pend
             table.ready = done  # the next user's stream waits for the scatter on the device
             gpu.table_pool().put(table, clean=True)
             if first_run:
@@ -810,19 +815,25 @@ class SpmdExecutor(LocalExecutor):
                 return pend.rows(j)
             except ExchangeFailed as e:
                 if e.retriable:
-                    self._mark_group_lost(gid, head)
+                    self._mark_group_lost(gid, head, pend)
                     raise errors.TaskLostError("spmd: exchange of %s was lost (%s); recomputing"
                                                % (head.name, e)) from e
                 raise errors.fatal("spmd: exchange of %s failed: %s" % (head.name, e)) from e
         return resolve
 
-    def _mark_group_lost(self, gid: int, head: Task) -> None:
+    def _mark_group_lost(self, gid: int, head: Task, pend=None) -> None:
         """The group's exchange did not deliver: forget it and mark the producers
         LOST so that the evaluator re-runs them (and, through ``_ensure_group``,
-        the exchange)."""
+        the exchange).  ``pend`` names the attempt that failed: a consumer that
+        still holds a frame of an *earlier* attempt finds a newer exchange in place
+        and only re-runs itself — one failed attempt is repeated exactly once, on
+        every rank (the ranks must issue the same number of exchanges)."""
         with self._glock:
             if gid not in self.group_done:
                 return  # already handled by another consumer
+            if pend is not None and self._group_pend.get(gid) is not pend:
+                return  # superseded: the repeated exchange is already queued or done
+            self._group_pend.pop(gid, None)
             self.group_done.pop(gid, None)
             self.group_err.pop(gid, None)
             for k in [k for k in self.exchanged if k[0] == gid]:
@@ -1141,6 +1152,7 @@ class SpmdExecutor(LocalExecutor):
                     del self.exchanged[k]
                 self.group_done.pop(gid, None)
                 self.group_err.pop(gid, None)
+                self._group_pend.pop(gid, None)
 
     # -- results -------------------------------------------------------------------
     def result_reader(self, result) -> Reader:

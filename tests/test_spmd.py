@@ -29,6 +29,19 @@ def launch(nproc, tmp_path, device="cpu", shuffle="auto", timeout=600, extra_env
            "--nproc-per-node=%d" % nproc, "--master-addr", "127.0.0.1",
            "--master-port", str(free_port()), os.path.join(HERE, "spmd_worker.py")]
     r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=timeout)
+    dump = os.environ.get("BS_TEST_DUMP")   # keep what the workers said (debugging on a remote GPU box)
+    if dump:
+        os.makedirs(dump, exist_ok=True)
+        tag = "%s_w%d_%s" % (device, nproc, os.path.basename(str(tmp_path)))
+        with open(os.path.join(dump, tag + ".stderr"), "w") as fh:
+            fh.write(r.stderr[-20000:])
+        for i in range(nproc):
+            if os.path.exists(out + ".%d" % i):
+                with open(out + ".%d" % i) as src, open(os.path.join(dump, "%s.%d.json" % (tag, i)), "w") as dst:
+                    o = json.load(src)
+                    o.pop("scan_local", None)
+                    o.pop("wordcount_local_keys", None)
+                    json.dump(o, dst)
     assert r.returncode == 0, r.stderr[-4000:]
     return [json.load(open(out + ".%d" % i)) for i in range(nproc)]
 

@@ -108,3 +108,46 @@ def test_status_board_vote_and_diverged_exchange_sequences():
     finally:
         for r in (1, 0):
             exs[r].board.close(unlink=(r == 0))
+
+
+def test_a_failed_exchange_attempt_is_repeated_once_however_many_consumers_hold_its_frames():
+    import threading as th
+    from bigslice_b200.exec.spmd import SpmdExecutor
+    from bigslice_b200.exec.task import TaskState
+
+    class T:
+        def __init__(self):
+            self.st, self.group = TaskState.OK, None
+
+        def state(self):
+            return self.st
+
+        def set(self, s):
+            self.st = s
+
+    ex = SpmdExecutor(device=None)
+    prods = [T(), T()]
+    for p in prods:
+        p.group = prods
+    gid = id(prods[0])
+    attempt1, attempt2 = object(), object()
+    ex.group_done[gid] = th.Event()
+    ex._group_pend[gid] = attempt1
+    ex.exchanged[(gid, 0)] = ["frames of attempt 1"]
+    # first consumer of the failed attempt: the group is forgotten, producers are LOST
+    ex._mark_group_lost(gid, prods[0], attempt1)
+    assert gid not in ex.group_done and (gid, 0) not in ex.exchanged
+    assert all(p.state() == TaskState.LOST for p in prods)
+    # the evaluator re-runs the producers; the repeated exchange is queued, then in place
+    for p in prods:
+        p.set(TaskState.OK)
+    ex.group_done[gid] = th.Event()
+    ex._mark_group_lost(gid, prods[0], attempt1)           # stale frame while the retry is queued
+    assert gid in ex.group_done and all(p.state() == TaskState.OK for p in prods)
+    ex._group_pend[gid] = attempt2
+    ex.exchanged[(gid, 0)] = ["frames of attempt 2"]
+    ex._mark_group_lost(gid, prods[0], attempt1)           # stale frame after the retry completed
+    assert ex.exchanged[(gid, 0)] == ["frames of attempt 2"] and all(p.state() == TaskState.OK for p in prods)
+    # the new attempt failing is a new loss
+    ex._mark_group_lost(gid, prods[0], attempt2)
+    assert gid not in ex.group_done and all(p.state() == TaskState.LOST for p in prods)
