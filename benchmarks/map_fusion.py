@@ -5,7 +5,7 @@ The same three lambdas are evaluated over one resident tile (2^26 rows, two
 columns — inputs 4× the 126 MB L2) through the framework's chain reader:
 
   * ``fused``  — the functions are traced (``ops/trace.py``) and the whole chain is one
-    NVRTC-compiled sm_100a kernel + one compaction;
+    NVRTC-compiled count kernel + one write kernel that emits only the kept rows;
   * ``eager``  — ``BIGSLICE_TRACE=0``: every operator of every lambda is its own PyTorch
     kernel with its own temporary (what round 1 did).
 

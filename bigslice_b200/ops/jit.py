@@ -86,17 +86,15 @@ def check_types(dts: Sequence[DType]) -> None:
             raise TypeError("expression stages support scalar numeric/bool columns, not %s" % d)
 
 
-def generate_ex(in_types: Sequence[DType], stages: Sequence[Stage]
-                ) -> Tuple[str, List[DType], bool, List[Optional[int]]]:
-    """CUDA source of the fused kernel, its output dtypes, whether it has a
-    predicate, and for every output the input column it merely passes through
-    (such outputs get no kernel parameter: the caller reuses the input column)."""
+def _definitions(in_types: Sequence[DType], stages: Sequence[Stage], index: str):
+    """The chain as C definitions over row ``index``: (lines, output value names,
+    output dtypes, predicate names, number of leading load lines)."""
     check_types(in_types)
     cur = list(in_types)
     body = []
     names = ["v0_%d" % j for j in range(len(cur))]
     for j, t in enumerate(cur):
-        body.append("    const %s v0_%d = in%d[i];" % (CTYPE[t.name], j, j))
+        body.append("    const %s v0_%d = in%d[%s];" % (CTYPE[t.name], j, j, index))
     preds = []
     for s, st in enumerate(stages, 1):
         def sub(expr, names=names):
@@ -120,10 +118,22 @@ def generate_ex(in_types: Sequence[DType], stages: Sequence[Stage]
                 body.append("    const %s v%d_%d = (%s)(%s);" % (CTYPE[t.name], s, j, CTYPE[t.name], sub(e)))
                 new.append("v%d_%d" % (s, j))
             names, cur = new, list(st.out)
+    return body, names, cur, preds, len(in_types)
+
+
+def _drop_unused_loads(body: List[str], nloads: int, extra: Sequence[str]) -> List[str]:
+    used = set(int(m.group(1)) for m in re.finditer(r"\bv0_(\d+)\b", "\n".join(body[nloads:] + list(extra))))
+    return [ln for j, ln in enumerate(body) if j >= nloads or j in used]
+
+
+def generate_ex(in_types: Sequence[DType], stages: Sequence[Stage]
+                ) -> Tuple[str, List[DType], bool, List[Optional[int]]]:
+    """CUDA source of the fused kernel, its output dtypes, whether it has a
+    predicate, and for every output the input column it merely passes through
+    (such outputs get no kernel parameter: the caller reuses the input column)."""
+    body, names, cur, preds, nloads = _definitions(in_types, stages, "i")
     alias: List[Optional[int]] = [int(nm[3:]) if nm.startswith("v0_") else None for nm in names]
-    used = set(int(m.group(1)) for m in re.finditer(r"\bv0_(\d+)\b", "\n".join(
-        body[len(in_types):] + [nm for nm, a in zip(names, alias) if a is None])))
-    body = [ln for j, ln in enumerate(body) if j >= len(in_types) or j in used]
+    body = _drop_unused_loads(body, nloads, [nm for nm, a in zip(names, alias) if a is None])
     params = ["long long n"]
     params += ["const %s* __restrict__ in%d" % (CTYPE[t.name], j) for j, t in enumerate(in_types)]
     params += ["%s* __restrict__ out%d" % (CTYPE[t.name], j) for j, t in enumerate(cur) if alias[j] is None]
@@ -139,6 +149,87 @@ def generate_ex(in_types: Sequence[DType], stages: Sequence[Stage]
            "       i += (long long)gridDim.x * blockDim.x) {\n%s\n  }\n}\n"
            % (", ".join(params), "\n".join(body)))
     return src, cur, bool(preds), alias
+
+
+#: rows per CTA of the compacting kernels: COMPACT_ITEMS iterations of 256 consecutive rows
+COMPACT_ITEMS = 8
+COMPACT_CHUNK = 256 * COMPACT_ITEMS
+
+
+def generate_compact(in_types: Sequence[DType], stages: Sequence[Stage]) -> Tuple[str, List[DType]]:
+    """Source of the two kernels that evaluate a chain **with predicates** and
+    write only the kept rows, in row order, without materialising the unfiltered
+    outputs or a mask:
+
+    * ``bs_fused_count``  one CTA per chunk of %d rows: the number of rows the chunk keeps;
+    * ``bs_fused_write``  given the exclusive prefix sum of those counts, the chain is
+      evaluated again and every kept row is written straight to its final position
+      (rank inside the CTA from warp ballots + a shared-memory scan of the 8 warp counts).
+
+    Rows past ``n`` re-read row ``n-1`` (all threads stay converged for the ballots)
+    and are never kept.""" % COMPACT_CHUNK
+    body, names, cur, preds, nloads = _definitions(in_types, stages, "ii")
+    if not preds:
+        raise ValueError("generate_compact needs at least one predicate stage")
+    keep = "(i < n) && (%s)" % " && ".join(preds)
+    ins = ["const %s* __restrict__ in%d" % (CTYPE[t.name], j) for j, t in enumerate(in_types)]
+    head = ("    const long long i = base + (long long)it * 256 + tid;\n"
+            "    const long long ii = i < n ? i : n - 1;\n")
+    count_body = "\n".join(_drop_unused_loads(body, nloads, []))
+    write_body = "\n".join(_drop_unused_loads(body, nloads, names))
+    stores = "\n".join("      out%d[o] = %s;" % (j, nm) for j, nm in enumerate(names))
+    outs = ["%s* __restrict__ out%d" % (CTYPE[t.name], j) for j, t in enumerate(cur)]
+    src = PRELUDE + (
+        "#define BS_ITEMS %d\n"
+        "extern \"C\" __global__ void __launch_bounds__(256) bs_fused_count(%s) {\n"
+        "  __shared__ int wsum[8];\n"
+        "  const int tid = threadIdx.x;\n"
+        "  const long long base = (long long)blockIdx.x * (256 * BS_ITEMS);\n"
+        "  int kept = 0;\n"
+        "#pragma unroll\n"
+        "  for (int it = 0; it < BS_ITEMS; ++it) {\n%s%s\n"
+        "    const bool keep = %s;\n"
+        "    kept += __popc(__ballot_sync(0xffffffffu, keep));\n"
+        "  }\n"
+        "  if ((tid & 31) == 0) wsum[tid >> 5] = kept;\n"
+        "  __syncthreads();\n"
+        "  if (tid == 0) {\n"
+        "    int t = 0;\n"
+        "    for (int w = 0; w < 8; ++w) t += wsum[w];\n"
+        "    counts[blockIdx.x] = t;\n"
+        "  }\n"
+        "}\n"
+        "extern \"C\" __global__ void __launch_bounds__(256) bs_fused_write(%s) {\n"
+        "  __shared__ int wcnt[8];\n"
+        "  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;\n"
+        "  const long long base = (long long)blockIdx.x * (256 * BS_ITEMS);\n"
+        "  const long long pos0 = offs[blockIdx.x];\n"
+        "  int run = 0;\n"
+        "#pragma unroll\n"
+        "  for (int it = 0; it < BS_ITEMS; ++it) {\n%s%s\n"
+        "    const bool keep = %s;\n"
+        "    const unsigned b = __ballot_sync(0xffffffffu, keep);\n"
+        "    if (lane == 0) wcnt[warp] = __popc(b);\n"
+        "    __syncthreads();\n"
+        "    int before = 0, tot = 0;\n"
+        "#pragma unroll\n"
+        "    for (int w = 0; w < 8; ++w) {\n"
+        "      const int c = wcnt[w];\n"
+        "      if (w < warp) before += c;\n"
+        "      tot += c;\n"
+        "    }\n"
+        "    if (keep) {\n"
+        "      const long long o = pos0 + run + before + __popc(b & ((1u << lane) - 1u));\n%s\n"
+        "    }\n"
+        "    run += tot;\n"
+        "    __syncthreads();\n"
+        "  }\n"
+        "}\n"
+        % (COMPACT_ITEMS,
+           ", ".join(["long long n"] + ins + ["int* __restrict__ counts"]), head, count_body, keep,
+           ", ".join(["long long n"] + ins + ["const long long* __restrict__ offs"] + outs), head, write_body,
+           keep, stores))
+    return src, cur
 
 
 def generate(in_types: Sequence[DType], stages: Sequence[Stage]) -> Tuple[str, List[DType], bool]:
@@ -210,9 +301,9 @@ def _driver():
     return _cuda
 
 
-def _function(src: str) -> ctypes.c_void_p:
+def _function(src: str, entry: str = "bs_fused") -> ctypes.c_void_p:
     dev = torch.cuda.current_device()
-    key = (dev, hashlib.sha1(src.encode()).hexdigest())
+    key = (dev, hashlib.sha1(src.encode()).hexdigest() + ":" + entry)
     with _lock:
         if key in _funcs:
             return _funcs[key]
@@ -224,7 +315,7 @@ def _function(src: str) -> ctypes.c_void_p:
     if rc != 0:
         raise RuntimeError("cuModuleLoadData failed: %d" % rc)
     fn = ctypes.c_void_p()
-    rc = cu.cuModuleGetFunction(ctypes.byref(fn), mod, b"bs_fused")
+    rc = cu.cuModuleGetFunction(ctypes.byref(fn), mod, entry.encode())
     if rc != 0:
         raise RuntimeError("cuModuleGetFunction failed: %d" % rc)
     with _lock:
@@ -261,6 +352,45 @@ def run_fused(cols: Sequence[torch.Tensor], in_types: Sequence[DType], stages: S
         raise RuntimeError("cuLaunchKernel failed: %d" % rc)
     launch_count += 1
     return outs, mask
+
+
+def _launch(fn, blocks: int, threads: int, args) -> None:
+    global launch_count
+    argv = (ctypes.c_void_p * len(args))(*[ctypes.cast(ctypes.pointer(a), ctypes.c_void_p) for a in args])
+    rc = _driver().cuLaunchKernel(fn, blocks, 1, 1, threads, 1, 1, 0,
+                                  ctypes.c_void_p(torch.cuda.current_stream().cuda_stream), argv, None)
+    if rc != 0:
+        raise RuntimeError("cuLaunchKernel failed: %d" % rc)
+    launch_count += 1
+
+
+def run_fused_compact(cols: Sequence[torch.Tensor], in_types: Sequence[DType], stages: Sequence[Stage]
+                      ) -> List[torch.Tensor]:
+    """Evaluate a chain that contains Filters and return only the kept rows, in
+    row order: count kernel -> prefix sum of the per-CTA counts -> write kernel
+    (``generate_compact``).  One host read (the number of kept rows, to size the
+    outputs); no mask, no full-size temporaries, no gathers."""
+    src, out_types = generate_compact(in_types, stages)
+    n = int(cols[0].shape[0]) if cols else 0
+    dev = cols[0].device
+    if n == 0:
+        return [torch.empty(0, dtype=t.torch_dtype, device=dev) for t in out_types]
+    cols = [c.contiguous() for c in cols]
+    nblocks = (n + COMPACT_CHUNK - 1) // COMPACT_CHUNK
+    counts = torch.empty(nblocks, dtype=torch.int32, device=dev)
+    ins = [ctypes.c_void_p(c.data_ptr()) for c in cols]
+    _launch(_function(src, "bs_fused_count"), nblocks, 256,
+            [ctypes.c_longlong(n)] + ins + [ctypes.c_void_p(counts.data_ptr())])
+    incl = torch.cumsum(counts, 0, dtype=torch.int64)
+    total = int(incl[-1])
+    outs = [torch.empty(total, dtype=t.torch_dtype, device=dev) for t in out_types]
+    if total == 0:
+        return outs
+    offs = (incl - counts).contiguous()
+    _launch(_function(src, "bs_fused_write"), nblocks, 256,
+            [ctypes.c_longlong(n)] + ins + [ctypes.c_void_p(offs.data_ptr())] +
+            [ctypes.c_void_p(o.data_ptr()) for o in outs])
+    return outs
 
 
 # ---------------------------------------------------------------------------

@@ -1131,9 +1131,14 @@ class _ExprReader(Reader):
         return cur
 
     def _device(self, cols, n, device):
-        from .ops import gpu, jit, trace
+        from .ops import jit, trace
+        filtered = any(st.pred is not None for st in self.stages)
         try:
-            outs, mask = jit.run_fused(cols, self.in_typ.cols, self.stages)
+            if filtered:
+                # count -> prefix sum -> write: only the kept rows are ever written
+                outs = jit.run_fused_compact(cols, self.in_typ.cols, self.stages)
+            else:
+                outs, _ = jit.run_fused(cols, self.in_typ.cols, self.stages)
         except RuntimeError as e:
             traced = [st for st in self.stages if st.fn is not None]
             if not traced or "does not compile" not in str(e):
@@ -1145,9 +1150,6 @@ class _ExprReader(Reader):
                         ", ".join(_fn_name(st.fn) for st in traced), str(e).splitlines()[0])
             self.eager_only = True
             return self._host(cols, n, device)
-        if mask is not None:
-            idx = gpu.compact_indices(mask.view(torch.bool))
-            outs = [gpu.gather_rows(o, idx) if o.dtype != torch.bool else o[idx] for o in outs]
         unchecked = [st for st in self.stages if st.fn is not None and not trace.verified(st.fn)]
         if unchecked:
             # first tile of a traced python function: its fused result must equal what the
@@ -1155,10 +1157,7 @@ class _ExprReader(Reader):
             # mis-traced function; it then runs eagerly from here on)
             m = min(n, 4096)
             ref = self._host([c[:m] for c in cols], m, device)
-            if mask is not None:
-                k = int(mask[:m].sum())
-            else:
-                k = m
+            k = int(ref[0].shape[0]) if filtered else m   # kept rows among the first m
             if _same_columns(ref, [o[:k] for o in outs]):
                 for st in unchecked:
                     trace.mark_verified(st.fn)

@@ -94,6 +94,10 @@ def test_every_traced_kernel_compiles_for_sm_100a():
         pred = trace.trace_filter(slicefunc.Func(lambda *c: c[0] != 0), _types(dts))
         src = jit.generate(_types(dts), [st, pred])[0]
         assert jit.compile_cubin(src)[:4] == b"\x7fELF"
+        # and as the count/write pair that emits only the kept rows
+        csrc, couts = jit.generate_compact(_types(dts), [st, pred])
+        assert "bs_fused_count" in csrc and "bs_fused_write" in csrc and len(couts) == len(outs)
+        assert jit.compile_cubin(csrc)[:4] == b"\x7fELF"
 
 
 def test_what_is_not_traceable_runs_eagerly():
@@ -254,7 +258,8 @@ def test_traced_python_pipeline_runs_as_one_kernel_on_gpu():
     wk, wv = chain_reference(k, v)
     assert [a for a, _ in rows] == wk.tolist()
     assert [b for _, b in rows] == pytest.approx(wv.tolist(), rel=1e-5)
-    assert jit.launch_count == before + 2   # one fused launch per shard for the three python stages
+    # per shard: count kernel + write kernel for the three python stages together
+    assert jit.launch_count == before + 4
 
 
 @pytest.mark.gpu
