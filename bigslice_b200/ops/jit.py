@@ -7,8 +7,10 @@ compiler pipelines into one task are **fused into a single sm_100a kernel**:
 the chain is composed symbolically, compiled once with NVRTC
 (``--gpu-architecture=sm_100a``) into a cubin, cached by source, loaded through
 the driver API and launched on the current stream.  One pass over the tile
-evaluates every stage; a Filter anywhere in the chain makes the kernel emit a
-keep-mask that feeds the stream-compaction kernel.
+evaluates every stage.  A chain with Filters compiles to a *count* kernel and a
+*write* kernel (``generate_compact``): per-CTA kept-row counts, a prefix sum,
+then every kept row is written straight to its final position — in row order,
+with no mask, no full-size temporaries and no gathers.
 
 On executors without a GPU the same expressions are evaluated with torch ops
 under C semantics (truncating integer division/modulo), so results agree.
