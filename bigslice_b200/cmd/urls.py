@@ -18,7 +18,6 @@ from __future__ import annotations
 
 import argparse
 import sys
-import threading
 from typing import Dict
 from urllib.parse import urlparse
 

@@ -19,7 +19,6 @@ import random
 import threading
 from typing import Optional
 
-from .. import errors
 from .local import LocalExecutor
 from .task import Task, TaskState
 

@@ -31,7 +31,7 @@ for rank-consistent cache decisions (``exec/compile.go:133-184``).
 """
 from __future__ import annotations
 
-from typing import Any, Callable, Dict, List, Optional, Sequence, Tuple
+from typing import Callable, Dict, List, Optional, Tuple
 
 from .. import errors
 from ..internal import slicecache

@@ -22,13 +22,13 @@ import os
 import threading
 import time
 import traceback
-from typing import Callable, Dict, List, Optional, Sequence
+from typing import Dict, List, Optional
 
 import torch
 
 from .. import context as _context
-from .. import errors, metrics, slicefunc
-from ..frame import Frame, concat
+from .. import errors, slicefunc
+from ..frame import Frame
 from ..sliceio import EmptyReader, FrameReader, MultiReader, Reader
 from .combiner import Combiner
 from ..utils.spans import span

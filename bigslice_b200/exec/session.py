@@ -18,16 +18,16 @@ import logging
 import threading
 import time
 from concurrent.futures import ThreadPoolExecutor
-from typing import Any, Callable, Dict, List, Optional, Sequence
+from typing import Callable, Dict, List, Optional
 
 from .. import errors, metrics, typecheck
 from ..frame import Frame, concat
 from ..func import FuncValue, Invocation
 from ..utils.spans import span
-from ..sliceio import MultiReader, Reader, Scanner, read_all
+from ..sliceio import MultiReader, Reader, Scanner
 from ..slices import Slice, make_name
 from ..status import Status
-from .compile import CompileEnv, ExecInvocation, compile_slice
+from .compile import ExecInvocation, compile_slice
 from .eval import Executor, evaluate
 from .local import LocalExecutor
 from .task import Task, TaskState, iter_tasks

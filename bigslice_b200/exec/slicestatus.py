@@ -12,7 +12,6 @@ from __future__ import annotations
 
 import logging
 import threading
-import time
 from typing import Dict, List, Optional, Sequence
 
 from ..status import Group, Status

@@ -9,7 +9,7 @@ helper ``exec/topn.go:39-57``.
 from __future__ import annotations
 
 import heapq
-from typing import List, Sequence
+from typing import List
 
 import torch
 

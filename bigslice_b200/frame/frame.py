@@ -14,7 +14,7 @@ of per-row calls.
 from __future__ import annotations
 
 import io
-from typing import Any, Iterable, List, Optional, Sequence
+from typing import Any, List, Optional, Sequence
 
 import numpy as np
 import torch

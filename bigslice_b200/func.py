@@ -18,9 +18,9 @@ import inspect
 import itertools
 import threading
 import typing
-from typing import Any, Callable, List, Optional, Sequence
+from typing import Any, Callable, List, Sequence
 
-from . import slicetype, typecheck
+from . import typecheck
 from .slices import Slice
 
 _funcs: List["FuncValue"] = []

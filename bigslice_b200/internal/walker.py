@@ -7,7 +7,7 @@ errors sticky.
 from __future__ import annotations
 
 import os
-from typing import List, Optional, Tuple
+from typing import List, Optional
 
 
 class Walker:

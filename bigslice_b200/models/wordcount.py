@@ -8,7 +8,7 @@ registered ``Func`` the benchmark runs through ``Session.run``.
 """
 from __future__ import annotations
 
-from typing import List, Optional, Tuple
+from typing import List, Tuple
 
 import torch
 

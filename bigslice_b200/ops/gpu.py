@@ -17,7 +17,7 @@ from __future__ import annotations
 import ctypes
 import os
 import threading
-from typing import List, Optional, Sequence, Tuple
+from typing import List, Optional, Tuple
 
 import torch
 

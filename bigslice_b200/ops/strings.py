@@ -27,7 +27,7 @@ CPU tensors run the same operations through numpy/torch (tests, small data).
 from __future__ import annotations
 
 import ctypes
-from typing import List, Optional, Sequence, Tuple
+from typing import Optional, Sequence, Tuple
 
 import numpy as np
 import torch

@@ -32,7 +32,7 @@ from __future__ import annotations
 
 import math
 import os
-from typing import Callable, List, Optional, Sequence, Tuple
+from typing import Callable, List, Optional, Sequence
 
 import numpy as np
 import torch

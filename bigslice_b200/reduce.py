@@ -20,7 +20,7 @@ from typing import Callable, List
 from . import context as _context
 from . import slicefunc, slicetype, sortio, typecheck
 from .frame import ops as frame_ops
-from .sliceio import FuncReader, MultiReader, Reader
+from .sliceio import Reader
 from .slices import Dep, Slice, _check_slice, _fn_name, make_name
 from .slicetype import Type
 

@@ -21,7 +21,6 @@ import torch
 
 from . import context as _context
 from . import slicefunc, slicetype, typecheck
-from .reduce import can_make_combining_frame
 from .frame import Frame
 from .frame import ops as frame_ops
 from .sliceio import MultiReader, Reader

@@ -18,7 +18,6 @@ from .internal import defaultsize
 from .sliceio import FuncReader
 from .slices import Slice, make_name
 from .slicetype import Type
-from . import context as _context
 
 
 class _ScanReader(Slice):

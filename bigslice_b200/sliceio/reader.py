@@ -13,7 +13,6 @@ ReaderWithCloseFunc, ClosingReader, EmptyReader, PprofReader).
 """
 from __future__ import annotations
 
-import contextlib
 import threading
 from typing import Callable, Iterable, List, Optional, Sequence
 

@@ -9,7 +9,7 @@ Close; arity misuse is a typecheck error).
 """
 from __future__ import annotations
 
-from typing import Iterator, List, Optional, Tuple
+from typing import Iterator, List, Optional
 
 from .. import typecheck
 from ..frame import Frame

@@ -21,19 +21,18 @@ from __future__ import annotations
 import logging
 import threading
 import types as _pytypes
-from typing import Any, Callable, List, Optional, Sequence
+from typing import Callable, List, Optional, Sequence
 
 import numpy as np
 import torch
 
 from . import context as _context
 from . import errors, slicefunc, slicetype, typecheck
-from .frame import Frame, concat
+from .frame import Frame
 from .frame import columns as C
 from .internal import defaultsize
 from .ops.segmented import group_starts, segmented_fold
-from .sliceio import (EOF, EmptyReader, FrameReader, FuncReader, Reader, Scanner,
-                      read_all)
+from .sliceio import EOF, FrameReader, FuncReader, Reader, Scanner, read_all
 from .slicetype import DType, Type
 
 log = logging.getLogger("bigslice")

@@ -12,7 +12,7 @@ descriptors that map to torch/numpy storage rather than ``reflect.Type``.
 from __future__ import annotations
 
 from dataclasses import dataclass
-from typing import Iterable, Optional, Sequence, Tuple
+from typing import Iterable, Optional, Tuple
 
 import numpy as np
 import torch

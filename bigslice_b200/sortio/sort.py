@@ -23,8 +23,7 @@ import torch
 from ..frame import Frame, concat
 from ..frame import columns as C
 from ..internal import defaultsize
-from ..sliceio import (ClosingReader, EmptyReader, FrameReader, Reader, Rebatch,
-                       Spiller, read_full)
+from ..sliceio import EmptyReader, FrameReader, Reader, Rebatch, Spiller, read_full
 from ..slicetype import Type
 
 

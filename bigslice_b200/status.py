@@ -9,7 +9,7 @@ from __future__ import annotations
 import io
 import threading
 import time
-from typing import Dict, List, Optional
+from typing import List, Optional
 
 
 class StatusTask:

@@ -13,7 +13,6 @@ from __future__ import annotations
 import os
 import threading
 import time
-from contextlib import contextmanager
 from typing import Dict, List, Tuple
 
 _enabled = os.environ.get("BIGSLICE_SPANS", "") not in ("", "0")
