@@ -38,6 +38,7 @@ from .ops import functors as ops
 from . import exec  # noqa: A004 - mirrors the reference package name
 from . import slicetest, sliceio, sortio, frame  # noqa: F401,E402
 from .exec import (Local, LocalDevice, MachineCombiners, MaxLoad, Parallelism, Result, StoreOpt, Journal,
-                   Session, Spmd, TracePath, start, Start)
+                   Session, Spmd, TracePath, start, Start, StatusOpt, EventerOpt, Bigmachine)
+from . import sliceconfig, text  # noqa: F401,E402
 
 __version__ = "0.1.0"
