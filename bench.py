@@ -274,7 +274,8 @@ def cpu_proxy(args, rows=1 << 21):
             sess.run(job).discard()
             dt = _t.perf_counter() - t0
         return {"rows": rows, "rows_per_s": rows / dt, "seconds": dt,
-                "what": "bigslice_b200 Local executor on CPU (8 shards, 8 procs), labelled proxy - not the Go reference"}
+                "what": "bigslice_b200 Local executor on CPU (8 shards, 8 procs), labelled proxy - "
+                        "not the Go reference"}
     except Exception as e:  # the proxy must never break the benchmark
         return {"error": str(e)[:200]}
 

@@ -80,7 +80,8 @@ def main():
     ms = sorted(times)[len(times) // 2]
     tot = torch.tensor([nkeys], device=dev)
     dist.all_reduce(tot)
-    out = {"metric": "BroadcastJoin rows/s" if a.broadcast else "Cogroup join rows/s", "world": world, "rows_large_per_gpu": a.large,
+    out = {"metric": "BroadcastJoin rows/s" if a.broadcast else "Cogroup join rows/s", "world": world,
+           "rows_large_per_gpu": a.large,
            "rows_small_per_gpu": a.small, "ms_per_step": ms,
            "rows_per_s": (a.large + a.small) * world / (ms / 1e3), "distinct_keys": int(tot[0]),
            "modes": sorted(set(x["mode"] for x in sess.executor.exchange_log))}

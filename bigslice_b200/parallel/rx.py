@@ -395,8 +395,9 @@ class ReduceExchange:
             self._chk(lib.bs_rx_set_vote(c_void_p(self.state.data_ptr()), c_ull(vote[0]), c_ull(vote[1]), s),
                       "rx_set_vote")
             key = (table.slots.data_ptr(), table.total, table.status.data_ptr(), nparts, rows, table.vdtype,
-                   table.op, keymode, regions) + tuple((j, dt.slots.data_ptr(), dt.total, dt.status.data_ptr(), ok.data_ptr(),
-                                      ov.data_ptr(), cap) for j, dt, ok, ov, cap in dests)
+                   table.op, keymode, regions) + tuple(
+                (j, dt.slots.data_ptr(), dt.total, dt.status.data_ptr(), ok.data_ptr(), ov.data_ptr(), cap)
+                for j, dt, ok, ov, cap in dests)
             g = self.graphs.get(key) if self.use_graphs else None
             if g is not None:
                 self._chk(lib.bs_graph_launch(c_void_p(g.exec), c_ll(g.nodes), s), "graph_launch")
