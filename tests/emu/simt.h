@@ -1,0 +1,223 @@
+// A small SIMT emulator for running bigslice_b200's CUDA kernels on the CPU in tests.
+//
+// Every CUDA thread of a CTA is a ucontext fiber; CTAs run one after the other.
+// Fibers switch only at synchronisation points (__syncthreads, warp collectives), so
+// between two such points a thread runs alone — data races cannot be observed, but
+// everything else can: indexing, barriers, ballots/shuffles, shared memory, atomics,
+// grid-stride loops, tail handling.  Built with -fsanitize=address the same run is a
+// memcheck of the device code.  `kernel<<<grid, block, smem, stream>>>(args)` is
+// rewritten (tests/emu/__init__.py) into `bs_emu_launch(grid, block, [=]{ kernel(args); })`.
+#pragma once
+#include <ucontext.h>
+
+#include <cmath>
+#include <cstdint>
+#include <cstdlib>
+#include <cstring>
+#include <string.h>
+#include <functional>
+#include <vector>
+
+#define __device__
+#define __global__
+#define __host__
+#define __forceinline__ inline
+#define __restrict__
+#define __launch_bounds__(...)
+#define __shared__ static
+#define __constant__ static
+#define __align__(x) __attribute__((aligned(x)))
+
+typedef void* cudaStream_t;
+typedef int cudaError_t;
+enum { cudaSuccess = 0, cudaDevAttrMultiProcessorCount = 16 };
+enum cudaMemcpyKind { cudaMemcpyHostToHost, cudaMemcpyHostToDevice, cudaMemcpyDeviceToHost, cudaMemcpyDeviceToDevice,
+                      cudaMemcpyDefault };
+static inline cudaError_t cudaGetLastError() { return cudaSuccess; }
+static inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }
+static inline cudaError_t cudaMemsetAsync(void* p, int v, size_t n, cudaStream_t) { memset(p, v, n); return cudaSuccess; }
+static inline cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, cudaMemcpyKind, cudaStream_t) {
+  memcpy(d, s, n);
+  return cudaSuccess;
+}
+#define cudaMemcpyToSymbol(sym, src, n) (memcpy((void*)&(sym), (src), (n)), cudaSuccess)
+static inline cudaError_t cudaGetDevice(int* d) { *d = 0; return cudaSuccess; }
+static inline cudaError_t cudaDeviceGetAttribute(int* v, int, int) { *v = 2; return cudaSuccess; }  // "2 SMs"
+
+struct int4 { int x, y, z, w; };
+struct bs_dim3 { unsigned x, y, z; };
+static bs_dim3 threadIdx{0, 0, 0}, blockIdx{0, 0, 0}, blockDim{1, 1, 1}, gridDim{1, 1, 1};
+
+// ---- fibers -------------------------------------------------------------------
+static ucontext_t bs_sched;
+static std::vector<ucontext_t> bs_fib;
+static std::vector<char> bs_done;
+static int bs_cur, bs_live, bs_nthreads;
+static std::function<void()> bs_kernel;
+static inline void bs_yield() { swapcontext(&bs_fib[bs_cur], &bs_sched); }
+
+static int bs_bar_gen, bs_bar_count;
+static inline void bs_bar_check() {
+  if (bs_live > 0 && bs_bar_count == bs_live) { bs_bar_count = 0; ++bs_bar_gen; }
+}
+static inline void __syncthreads() {
+  const int gen = bs_bar_gen;
+  ++bs_bar_count;
+  bs_bar_check();
+  while (bs_bar_gen == gen) bs_yield();
+}
+static inline void __syncwarp(unsigned = 0xffffffffu) {}
+static inline void __threadfence() {}
+static inline void __threadfence_block() {}
+static inline void __threadfence_system() {}
+static inline void __nanosleep(unsigned) { bs_yield(); }
+
+// ---- warp collectives: every live lane of the warp deposits, the last arrival publishes ----
+struct bs_warp_t {
+  unsigned bits, result_bits;
+  unsigned long long val[32], result_val[32];
+  int count, gen, lanes, width;  // lanes: still running; width: lanes the warp started with
+};
+static std::vector<bs_warp_t> bs_warps;
+static inline bs_warp_t& bs_warp() { return bs_warps[bs_cur >> 5]; }
+static inline int bs_lane() { return bs_cur & 31; }
+static inline void bs_warp_arrive(bs_warp_t& w) {
+  const int gen = w.gen;
+  if (++w.count == w.lanes) {
+    w.result_bits = w.bits;
+    std::memcpy(w.result_val, w.val, sizeof(w.val));
+    w.bits = 0;
+    w.count = 0;
+    ++w.gen;
+  }
+  while (w.gen == gen) bs_yield();
+}
+static inline unsigned __ballot_sync(unsigned, int p) {
+  bs_warp_t& w = bs_warp();
+  if (p) w.bits |= 1u << bs_lane();
+  bs_warp_arrive(w);
+  return w.result_bits;
+}
+static inline unsigned __activemask() { return 0xffffffffu; }
+template <class T> static inline unsigned long long bs_bits(T v) {
+  unsigned long long b = 0;
+  std::memcpy(&b, &v, sizeof(T));
+  return b;
+}
+template <class T> static inline T bs_unbits(unsigned long long b) {
+  T v;
+  std::memcpy(&v, &b, sizeof(T));
+  return v;
+}
+template <class T> static inline T bs_exchange(T v, int src_lane) {
+  bs_warp_t& w = bs_warp();
+  w.val[bs_lane()] = bs_bits(v);
+  bs_warp_arrive(w);
+  if (src_lane < 0 || src_lane >= w.width) return v;
+  return bs_unbits<T>(w.result_val[src_lane]);
+}
+template <class T> static inline T __shfl_sync(unsigned, T v, int src, int width = 32) {
+  return bs_exchange(v, (bs_lane() / width) * width + (src % width));
+}
+template <class T> static inline T __shfl_down_sync(unsigned, T v, unsigned d, int width = 32) {
+  const int l = bs_lane(), s = l + (int)d;
+  return bs_exchange(v, (s / width == l / width) ? s : l);
+}
+template <class T> static inline T __shfl_up_sync(unsigned, T v, unsigned d, int width = 32) {
+  const int l = bs_lane(), s = l - (int)d;
+  return bs_exchange(v, (s >= 0 && s / width == l / width) ? s : l);
+}
+template <class T> static inline T __shfl_xor_sync(unsigned, T v, int m, int width = 32) {
+  return bs_exchange(v, bs_lane() ^ m);
+}
+template <class T> static inline unsigned __match_any_sync(unsigned, T v) {
+  bs_warp_t& w = bs_warp();
+  w.val[bs_lane()] = bs_bits(v);
+  bs_warp_arrive(w);
+  unsigned m = 0;
+  for (int l = 0; l < w.width; ++l)
+    if (w.result_val[l] == bs_bits(v)) m |= 1u << l;
+  return m;
+}
+
+// ---- scalar intrinsics ------------------------------------------------------------
+static inline int __popc(unsigned x) { return __builtin_popcount(x); }
+static inline int __popcll(unsigned long long x) { return __builtin_popcountll(x); }
+static inline int __ffs(int x) { return __builtin_ffs(x); }
+static inline int __clz(int x) { return x ? __builtin_clz((unsigned)x) : 32; }
+static inline unsigned __funnelshift_l(unsigned lo, unsigned hi, unsigned s) {
+  s &= 31;
+  return s ? (hi << s) | (lo >> (32 - s)) : hi;
+}
+static inline float __int_as_float(int v) { return bs_unbits<float>((unsigned)v); }
+static inline int __float_as_int(float v) { return (int)bs_bits(v); }
+template <class T> static inline T __ldg(const T* p) { return *p; }
+
+// atomics: a thread runs alone between synchronisation points
+template <class T, class U> static inline T atomicAdd(T* p, U v) { T o = *p; *p = (T)(o + (T)v); return o; }
+template <class T, class U> static inline T atomicSub(T* p, U v) { T o = *p; *p = (T)(o - (T)v); return o; }
+template <class T, class U> static inline T atomicMax(T* p, U v) { T o = *p; if ((T)v > o) *p = (T)v; return o; }
+template <class T, class U> static inline T atomicMin(T* p, U v) { T o = *p; if ((T)v < o) *p = (T)v; return o; }
+template <class T, class U> static inline T atomicOr(T* p, U v) { T o = *p; *p = (T)(o | (T)v); return o; }
+template <class T, class U> static inline T atomicAnd(T* p, U v) { T o = *p; *p = (T)(o & (T)v); return o; }
+template <class T, class U> static inline T atomicExch(T* p, U v) { T o = *p; *p = (T)v; return o; }
+template <class T, class U, class V> static inline T atomicCAS(T* p, U cmp, V v) {
+  T o = *p;
+  if (o == (T)cmp) *p = (T)v;
+  return o;
+}
+
+// ---- launch -----------------------------------------------------------------------
+static void bs_trampoline() {
+  bs_kernel();
+  bs_done[bs_cur] = 1;
+  --bs_live;
+  bs_warp_t& w = bs_warp();
+  --w.lanes;  // a lane that has exited no longer takes part in collectives
+  if (w.lanes > 0 && w.count == w.lanes) {
+    w.result_bits = w.bits;
+    std::memcpy(w.result_val, w.val, sizeof(w.val));
+    w.bits = 0;
+    w.count = 0;
+    ++w.gen;
+  }
+  bs_bar_check();
+  swapcontext(&bs_fib[bs_cur], &bs_sched);
+}
+
+static void bs_emu_launch(long long grid, long long block, std::function<void()> k) {
+  static std::vector<std::vector<char>> stacks;
+  if ((long long)stacks.size() < block) stacks.resize(block, std::vector<char>(1 << 17));
+  bs_kernel = k;
+  gridDim = bs_dim3{(unsigned)grid, 1, 1};
+  blockDim = bs_dim3{(unsigned)block, 1, 1};
+  bs_nthreads = (int)block;
+  for (long long b = 0; b < grid; ++b) {
+    blockIdx = bs_dim3{(unsigned)b, 0, 0};
+    bs_bar_gen = bs_bar_count = 0;
+    bs_live = bs_nthreads;
+    bs_warps.assign((bs_nthreads + 31) / 32, bs_warp_t());
+    for (size_t w = 0; w < bs_warps.size(); ++w) {
+      const int left = bs_nthreads - (int)w * 32;
+      bs_warps[w].lanes = bs_warps[w].width = left < 32 ? left : 32;
+    }
+    bs_fib.assign(bs_nthreads, ucontext_t());
+    bs_done.assign(bs_nthreads, 0);
+    for (int t = 0; t < bs_nthreads; ++t) {
+      getcontext(&bs_fib[t]);
+      bs_fib[t].uc_stack.ss_sp = stacks[t].data();
+      bs_fib[t].uc_stack.ss_size = stacks[t].size();
+      bs_fib[t].uc_link = &bs_sched;
+      makecontext(&bs_fib[t], bs_trampoline, 0);
+    }
+    int ndone = 0;
+    while (ndone < bs_nthreads)
+      for (int t = 0; t < bs_nthreads; ++t) {
+        if (bs_done[t]) continue;
+        bs_cur = t;
+        threadIdx = bs_dim3{(unsigned)t, 0, 0};
+        swapcontext(&bs_sched, &bs_fib[t]);
+        if (bs_done[t]) ++ndone;
+      }
+  }
+}

@@ -1,0 +1,156 @@
+"""Hand-written CUDA kernels, run on the CPU through the SIMT emulator (tests/emu).
+
+``csrc/{strings,merge,cogroup,misc}.cu`` are compiled *unmodified* (kernels and
+host wrappers; launches rewritten, inline PTX dropped) against ``tests/emu/simt.h``
+and loaded in place of the CUDA library, so the framework's own python wrappers
+(``ops/gpu.py``, ``ops/strings.py``) drive the real kernels over CPU tensors:
+indexing, tails, shared memory, ballots/shuffles, atomics and the host-side glue
+between launches are all exercised by the CPU test suite.  A second pass runs the
+same calls with AddressSanitizer: a memcheck of the device code without a GPU.
+(The GPU suite compares the same kernels with PyTorch references on a B200.)
+"""
+import ctypes
+import os
+import shutil
+import subprocess
+import sys
+import zlib
+
+import numpy as np
+import pytest
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+import emu  # noqa: E402
+
+from bigslice_b200.frame import hashing  # noqa: E402
+from bigslice_b200.ops import gpu, strings  # noqa: E402
+
+pytestmark = pytest.mark.skipif(shutil.which("g++") is None, reason="needs g++")
+FILES = ["strings", "merge", "cogroup", "misc"]
+
+
+class EmuLib:
+    """Looks a ``bs_*`` symbol up in whichever emulated object exports it."""
+
+    def __init__(self, asan=False):
+        self.libs = [ctypes.CDLL(emu.build(f, asan=asan)) for f in FILES]
+
+    def __getattr__(self, name):
+        for lib in self.libs:
+            try:
+                return getattr(lib, name)
+            except AttributeError:
+                continue
+        raise AttributeError(name)
+
+
+@pytest.fixture
+def emulated(monkeypatch):
+    lib = EmuLib(asan=bool(os.environ.get("BS_EMU_ASAN")))
+    monkeypatch.setattr(gpu, "require", lambda: lib)
+    monkeypatch.setattr(gpu, "_stream", lambda: ctypes.c_void_p(0))
+    monkeypatch.setattr(strings, "_cuda", lambda col: True)
+    return lib
+
+
+G = torch.Generator().manual_seed(3)
+
+
+def test_compaction_segmented_reduce_and_expand(emulated):
+    for n in (1, 31, 2049, 10007):
+        mask = torch.rand(n, generator=G) < 0.37
+        assert torch.equal(gpu.compact_indices(mask), torch.nonzero(mask).flatten())
+    assert gpu.compact_indices(torch.zeros(5000, dtype=torch.bool)).numel() == 0
+    # segmented reduce: every op, integer and float values, segments that straddle warps and CTAs
+    n = 6000
+    starts = torch.rand(n, generator=G) < 0.02
+    starts[0] = True
+    seg = torch.cumsum(starts.to(torch.int64), 0) - 1
+    nseg = int(seg[-1]) + 1
+    for dt in (torch.int64, torch.int32, torch.float32, torch.float64):
+        vals = torch.randint(-50, 50, (n,), generator=G).to(dt)
+        for op, red in (("add", "sum"), ("min", "amin"), ("max", "amax")):
+            want = torch.zeros(nseg, dtype=dt).scatter_reduce_(0, seg, vals, red, include_self=False)
+            assert torch.equal(gpu.segmented_reduce(vals, starts, nseg, op), want), (dt, op)
+    counts = torch.randint(0, 5, (777,), generator=G)
+    offs = torch.cat([torch.zeros(1, dtype=torch.int64), torch.cumsum(counts, 0)])
+    assert torch.equal(gpu.expand_indices(offs), torch.repeat_interleave(torch.arange(777), counts))
+
+
+def test_topk_and_crc32(emulated):
+    for dt in (torch.int64, torch.float32, torch.int32):
+        v = torch.randint(-1000, 1000, (5003,), generator=G).to(dt)
+        for k in (1, 10, 300):
+            vals, idx = gpu.topk(v, k)
+            assert torch.equal(vals, torch.topk(v, k).values) and torch.equal(v[idx], vals)
+    data = torch.randint(0, 256, (100003,), generator=G).to(torch.uint8)
+    assert gpu.crc32(data) == zlib.crc32(data.numpy().tobytes())
+
+
+def test_merge_path_is_a_stable_merge(emulated):
+    for na, nb in ((0, 5), (7, 0), (100, 3), (2048, 2048), (5000, 3001)):
+        a = torch.sort(torch.randint(0, 200, (na,), generator=G)).values
+        b = torch.sort(torch.randint(0, 200, (nb,), generator=G)).values
+        keys, src = gpu.merge_sorted_i64(a, b)
+        both = torch.cat([a, b])
+        want = torch.sort(both, stable=True)      # a-rows first among equal keys == stable sort of [a | b]
+        assert torch.equal(keys, want.values) and torch.equal(src, want.indices)
+
+
+def test_cogroup_union_kernels(emulated):
+    a = torch.sort(torch.randint(0, 300, (4000,), generator=G)).values
+    b = torch.sort(torch.randint(100, 500, (1500,), generator=G)).values
+    sa, sb = gpu.run_starts(a), gpu.run_starts(b)
+    ua, ca = torch.unique_consecutive(a, return_counts=True)
+    ub, cb = torch.unique_consecutive(b, return_counts=True)
+    assert torch.equal(a[sa], ua) and torch.equal(b[sb], ub)
+    r, m = gpu.cogroup_search(ua, ub)
+    assert torch.equal(r, torch.searchsorted(ub, ua)) and torch.equal(m.bool(), torch.isin(ua, ub))
+    uk, za, zb = gpu.cogroup_union2(ua, sa, a.numel(), ub, sb, b.numel())
+    want = torch.unique(torch.cat([ua, ub]))
+    assert torch.equal(uk, want)
+    da, db = dict(zip(ua.tolist(), ca.tolist())), dict(zip(ub.tolist(), cb.tolist()))
+    assert za.tolist() == [da.get(k, 0) for k in want.tolist()]
+    assert zb.tolist() == [db.get(k, 0) for k in want.tolist()]
+
+
+def test_string_kernels(emulated):
+    words = ["", "a", "hello", "naïve café", "x" * 37, "The quick  brown\tfox", "https://User@Example.COM:8080/a?b#c",
+             "b.org/y z", "ftp://HOST", "no-host-here?", "tail "] * 9
+    col = strings.from_objects(words)
+    for seed in (0, 0x9747b28c):
+        assert torch.equal(strings.hash32(col, seed),
+                           hashing.hash_objects(np.array(words, dtype=object), seed))
+    ids = strings.key64(col)
+    lo, hi = strings.hash32(col, 0), strings.hash32(col, 0x9747b28c)
+    assert torch.equal(ids, (lo | (hi << 32)).to(torch.int64))      # (wraps to the signed image)
+    toks, parent = strings.split(col)
+    want_t, want_p = [], []
+    for i, w in enumerate(words):
+        for t in w.split():
+            want_t.append(t)
+            want_p.append(i)
+    assert toks.tolist() == want_t and parent.tolist() == want_p
+    assert strings.url_domain(col).tolist()[:11] == ["", "a", "hello", "naïve café", "x" * 37, "the quick  brown\tfox",
+                                                     "example.com:8080", "b.org", "host", "no-host-here", "tail "]
+    idx = torch.tensor([10, 2, 2, 0, 6])
+    assert strings.take(col, idx).tolist() == [words[i] for i in idx.tolist()]
+    d_ids, d_strs = strings.dictionary(col, ids)
+    assert strings.verify_dictionary(col, ids, d_ids, d_strs)
+    forged = ids.clone()
+    forged[1] = ids[2]                                               # "a" claims the id of "hello"
+    assert not strings.verify_dictionary(col, forged, d_ids, d_strs)
+
+
+@pytest.mark.skipif(not os.path.exists(emu.asan_preload().split(":")[0]), reason="needs libasan")
+def test_the_same_calls_are_clean_under_address_sanitizer():
+    """Every kernel above once more, in a subprocess with the emulated objects built
+    with -fsanitize=address: an out-of-bounds load or store anywhere in the device code
+    (or in the host glue that sizes the buffers) aborts the run."""
+    env = dict(os.environ, BS_EMU_ASAN="1", LD_PRELOAD=emu.asan_preload(),
+               ASAN_OPTIONS="detect_leaks=0:abort_on_error=1:detect_stack_use_after_return=0")
+    r = subprocess.run([sys.executable, "-m", "pytest", "-q", "-x", "-p", "no:cacheprovider", __file__,
+                        "-k", "not address_sanitizer"], env=env, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, (r.stdout[-3000:], r.stderr[-3000:])
+    assert "passed" in r.stdout and "AddressSanitizer" not in r.stderr
