@@ -9,7 +9,8 @@ file, with
 * inline ``asm volatile(...)`` statements dropped (kernels that depend on them —
   TMA, multicast stores — are not runnable, the rest of the file still is);
 * every ``kernel<<<grid, block, smem, stream>>>(args);`` rewritten to
-  ``bs_emu_launch(grid, block, [=] { kernel(args); });``.
+  ``bs_emu_launch(grid, block, smem, [=] { kernel(args); });`` and ``extern __shared__``
+  arrays pointed at the emulator's dynamic shared-memory buffer.
 
 ``asan=True`` compiles with AddressSanitizer; run such a library in a subprocess
 with ``LD_PRELOAD`` set to ``asan_preload()``: every out-of-bounds access of the
@@ -131,14 +132,23 @@ def rewrite_launches(text: str) -> str:
         end = _match(text, p, "(", ")")
         args = text[p + 1:end - 1]
         semi = text.index(";", end)
-        call = "bs_emu_launch((long long)(%s), (long long)(%s), [=] { %s(%s); })" % (cfg[0], cfg[1], name, args)
+        smem = cfg[2] if len(cfg) > 2 else "0"
+        call = "bs_emu_launch((long long)(%s), (long long)(%s), (long long)(%s), [=] { %s(%s); })" % (
+            cfg[0], cfg[1], smem, name, args)
         text = text[:start] + call + text[semi:]
+
+
+def rewrite_dynamic_smem(text: str) -> str:
+    """``extern __shared__ T name[];`` -> a pointer into the emulator's dynamic
+    shared-memory buffer (sized by the launch's third configuration argument)."""
+    return re.sub(r"extern\s+__shared__\s+(?:__align__\(\d+\)\s*)?([\w ]+?)\s+(\w+)\[\];",
+                  r"\1* \2 = (\1*)bs_dyn_smem;", text)
 
 
 def source_for(name: str) -> str:
     text = open(os.path.join(CSRC, name + ".cu")).read()
     text = text.replace('#include "common.cuh"', '#include "simt.h"\n' + portable_common())
-    text = rewrite_launches(strip_asm(text))
+    text = rewrite_launches(strip_asm(rewrite_dynamic_smem(text)))
     if not re.search(r"^long long bs_launch_counter", text, re.M):
         text += '\nextern "C" { long long bs_launch_counter = 0; }\n'
     return text

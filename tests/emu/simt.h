@@ -6,7 +6,7 @@
 // everything else can: indexing, barriers, ballots/shuffles, shared memory, atomics,
 // grid-stride loops, tail handling.  Built with -fsanitize=address the same run is a
 // memcheck of the device code.  `kernel<<<grid, block, smem, stream>>>(args)` is
-// rewritten (tests/emu/__init__.py) into `bs_emu_launch(grid, block, [=]{ kernel(args); })`.
+// rewritten (tests/emu/__init__.py) into `bs_emu_launch(grid, block, smem, [=]{ kernel(args); })`.
 #pragma once
 #include <ucontext.h>
 
@@ -30,7 +30,8 @@
 
 typedef void* cudaStream_t;
 typedef int cudaError_t;
-enum { cudaSuccess = 0, cudaDevAttrMultiProcessorCount = 16 };
+enum { cudaSuccess = 0, cudaDevAttrMultiProcessorCount = 16, cudaFuncAttributeMaxDynamicSharedMemorySize = 8 };
+template <class F> static inline cudaError_t cudaFuncSetAttribute(F, int, int) { return cudaSuccess; }
 enum cudaMemcpyKind { cudaMemcpyHostToHost, cudaMemcpyHostToDevice, cudaMemcpyDeviceToHost, cudaMemcpyDeviceToDevice,
                       cudaMemcpyDefault };
 static inline cudaError_t cudaGetLastError() { return cudaSuccess; }
@@ -66,7 +67,6 @@ static inline void __syncthreads() {
   bs_bar_check();
   while (bs_bar_gen == gen) bs_yield();
 }
-static inline void __syncwarp(unsigned = 0xffffffffu) {}
 static inline void __threadfence() {}
 static inline void __threadfence_block() {}
 static inline void __threadfence_system() {}
@@ -98,6 +98,7 @@ static inline unsigned __ballot_sync(unsigned, int p) {
   bs_warp_arrive(w);
   return w.result_bits;
 }
+static inline void __syncwarp(unsigned = 0xffffffffu) { bs_warp_arrive(bs_warp()); }  // a real warp barrier
 static inline unsigned __activemask() { return 0xffffffffu; }
 template <class T> static inline unsigned long long bs_bits(T v) {
   unsigned long long b = 0;
@@ -185,8 +186,11 @@ static void bs_trampoline() {
   swapcontext(&bs_fib[bs_cur], &bs_sched);
 }
 
-static void bs_emu_launch(long long grid, long long block, std::function<void()> k) {
+alignas(128) static unsigned char bs_dyn_smem[256 << 10];  // dynamic shared memory of the running CTA
+
+static void bs_emu_launch(long long grid, long long block, long long smem_bytes, std::function<void()> k) {
   static std::vector<std::vector<char>> stacks;
+  if (smem_bytes > (long long)sizeof(bs_dyn_smem)) abort();
   if ((long long)stacks.size() < block) stacks.resize(block, std::vector<char>(1 << 17));
   bs_kernel = k;
   gridDim = bs_dim3{(unsigned)grid, 1, 1};

@@ -1,6 +1,6 @@
 """Hand-written CUDA kernels, run on the CPU through the SIMT emulator (tests/emu).
 
-``csrc/{strings,merge,cogroup,misc}.cu`` are compiled *unmodified* (kernels and
+``csrc/{strings,merge,cogroup,misc,hash_partition,sort}.cu`` are compiled *unmodified* (kernels and
 host wrappers; launches rewritten, inline PTX dropped) against ``tests/emu/simt.h``
 and loaded in place of the CUDA library, so the framework's own python wrappers
 (``ops/gpu.py``, ``ops/strings.py``) drive the real kernels over CPU tensors:
@@ -27,7 +27,7 @@ from bigslice_b200.frame import hashing  # noqa: E402
 from bigslice_b200.ops import gpu, strings  # noqa: E402
 
 pytestmark = pytest.mark.skipif(shutil.which("g++") is None, reason="needs g++")
-FILES = ["strings", "merge", "cogroup", "misc"]
+FILES = ["strings", "merge", "cogroup", "misc", "hash_partition", "sort"]
 
 
 class EmuLib:
@@ -76,6 +76,39 @@ def test_compaction_segmented_reduce_and_expand(emulated):
     counts = torch.randint(0, 5, (777,), generator=G)
     offs = torch.cat([torch.zeros(1, dtype=torch.int64), torch.cumsum(counts, 0)])
     assert torch.equal(gpu.expand_indices(offs), torch.repeat_interleave(torch.arange(777), counts))
+
+
+def test_hashing_partitioning_gather_and_radix_sort(emulated):
+    # bit-exact murmur3 of every key width, seeds, XOR accumulation across key columns
+    for dt in (torch.int64, torch.int32, torch.int16, torch.int8, torch.uint8, torch.float32, torch.float64):
+        c = torch.randint(-100, 100, (3001,), generator=G).to(dt)
+        for seed in (0, 77):
+            assert torch.equal(gpu.hash_column(c, seed), hashing.hash_tensor(c, seed)), (dt, seed)
+    a, b = torch.randint(-9, 9, (500,), generator=G), torch.randint(0, 5, (500,), generator=G).to(torch.int32)
+    h = gpu.hash_column(a)
+    gpu.hash_column(b, out=h, xor_into=True)
+    assert torch.equal(h, hashing.hash_tensor(a, 0) ^ hashing.hash_tensor(b, 0))
+    # partition permutation: keys hashed in the kernel, and explicit ids
+    keys = torch.randint(-1000, 1000, (9001,), generator=G)
+    for npart in (1, 7, 64):
+        dest = hashing.hash_tensor(keys, 0) % npart
+        for ids, ks in ((None, keys), (dest, None)):
+            perm, counts = gpu.partition_perm(ids, ks, keys.numel(), npart)
+            assert torch.equal(counts, torch.bincount(dest, minlength=npart))
+            assert torch.equal(torch.sort(perm).values, torch.arange(keys.numel()))   # a permutation
+            grouped = dest[perm]
+            assert torch.equal(grouped, torch.sort(grouped).values)                      # grouped by destination
+    # gather of wide and narrow rows
+    wide = torch.randn(700, 4, generator=G)
+    idx = torch.randint(0, 700, (1234,), generator=G)
+    assert torch.equal(gpu.gather_rows(wide, idx), wide[idx])
+    assert torch.equal(gpu.gather_rows(keys, idx), keys[idx])
+    # stable LSD radix sort of (key, payload) pairs
+    for n in (2, 300, 5000):
+        k = torch.randint(-50, 50, (n,), generator=G) * (1 << 33) + torch.randint(0, 3, (n,), generator=G)
+        sk, perm = gpu.sort_pairs_i64(k, None)
+        want = torch.sort(k, stable=True)
+        assert torch.equal(sk, want.values) and torch.equal(perm, want.indices)
 
 
 def test_topk_and_crc32(emulated):
