@@ -147,7 +147,10 @@ def rewrite_dynamic_smem(text: str) -> str:
 
 def source_for(name: str) -> str:
     text = open(os.path.join(CSRC, name + ".cu")).read()
-    text = text.replace('#include "common.cuh"', '#include "simt.h"\n' + portable_common())
+    if '#include "table.cuh"' in text:   # the table header is part of the translation unit
+        table = open(os.path.join(CSRC, "table.cuh")).read().replace("#pragma once", "")
+        text = text.replace('#include "table.cuh"', table)
+    text = text.replace('#include "common.cuh"', '#include "simt.h"\n' + portable_common() + '\n#include "ptx_emu.h"\n')
     text = rewrite_launches(strip_asm(rewrite_dynamic_smem(text)))
     if not re.search(r"^long long bs_launch_counter", text, re.M):
         text += '\nextern "C" { long long bs_launch_counter = 0; }\n'

@@ -100,6 +100,8 @@ static inline unsigned __ballot_sync(unsigned, int p) {
 }
 static inline void __syncwarp(unsigned = 0xffffffffu) { bs_warp_arrive(bs_warp()); }  // a real warp barrier
 static inline unsigned __activemask() { return 0xffffffffu; }
+static inline int __any_sync(unsigned m, int p) { return __ballot_sync(m, p) != 0; }
+static inline int __all_sync(unsigned m, int p) { return __ballot_sync(m, !p) == 0; }
 template <class T> static inline unsigned long long bs_bits(T v) {
   unsigned long long b = 0;
   std::memcpy(&b, &v, sizeof(T));
@@ -153,6 +155,9 @@ static inline unsigned __funnelshift_l(unsigned lo, unsigned hi, unsigned s) {
 static inline float __int_as_float(int v) { return bs_unbits<float>((unsigned)v); }
 static inline int __float_as_int(float v) { return (int)bs_bits(v); }
 template <class T> static inline T __ldg(const T* p) { return *p; }
+template <class T> static inline T __ldcg(const T* p) { return *p; }
+static inline double __longlong_as_double(long long v) { return bs_unbits<double>((unsigned long long)v); }
+static inline long long __double_as_longlong(double v) { return (long long)bs_bits(v); }
 
 // atomics: a thread runs alone between synchronisation points
 template <class T, class U> static inline T atomicAdd(T* p, U v) { T o = *p; *p = (T)(o + (T)v); return o; }

@@ -1,6 +1,6 @@
 """Hand-written CUDA kernels, run on the CPU through the SIMT emulator (tests/emu).
 
-``csrc/{strings,merge,cogroup,misc,hash_partition,sort}.cu`` are compiled *unmodified* (kernels and
+``csrc/{strings,merge,cogroup,misc,hash_partition,sort,hash_combine}.cu`` are compiled *unmodified* (kernels and
 host wrappers; launches rewritten, inline PTX dropped) against ``tests/emu/simt.h``
 and loaded in place of the CUDA library, so the framework's own python wrappers
 (``ops/gpu.py``, ``ops/strings.py``) drive the real kernels over CPU tensors:
@@ -27,7 +27,7 @@ from bigslice_b200.frame import hashing  # noqa: E402
 from bigslice_b200.ops import gpu, strings  # noqa: E402
 
 pytestmark = pytest.mark.skipif(shutil.which("g++") is None, reason="needs g++")
-FILES = ["strings", "merge", "cogroup", "misc", "hash_partition", "sort"]
+FILES = ["strings", "merge", "cogroup", "misc", "hash_partition", "sort", "hash_combine"]
 
 
 class EmuLib:
@@ -49,6 +49,8 @@ class EmuLib:
 def emulated(monkeypatch):
     lib = EmuLib(asan=bool(os.environ.get("BS_EMU_ASAN")))
     monkeypatch.setattr(gpu, "require", lambda: lib)
+    monkeypatch.setattr(gpu, "_lib", lib)
+    monkeypatch.setattr(gpu, "_pool", gpu.TablePool())
     monkeypatch.setattr(gpu, "_stream", lambda: ctypes.c_void_p(0))
     monkeypatch.setattr(strings, "_cuda", lambda col: True)
     return lib
@@ -109,6 +111,54 @@ def test_hashing_partitioning_gather_and_radix_sort(emulated):
         sk, perm = gpu.sort_pairs_i64(k, None)
         want = torch.sort(k, stable=True)
         assert torch.equal(sk, want.values) and torch.equal(perm, want.indices)
+
+
+def _reduce_reference(k, v, op):
+    uk, inv = torch.unique(k, return_inverse=True)
+    red = {"add": "sum", "min": "amin", "max": "amax"}[op]
+    return uk, torch.zeros(uk.numel(), dtype=v.dtype).scatter_reduce_(0, inv, v, red, include_self=False)
+
+
+def test_flagship_hash_combine_kernel_with_its_tma_pipeline(emulated):
+    """``hash_combine_tma_kernel``: the producer warp's TMA loads and the mbarrier
+    full/empty pipeline run under the emulator's mbarrier model (tests/emu/ptx_emu.h);
+    shared-memory hot table, warm level, main level, the ragged tail kernel, the
+    reserved EMPTY key, destination counting and overflow reporting."""
+    n = 40000                                    # > 4 tiles: the TMA kernel takes the aligned part
+    k = (torch.randint(0, 3000, (n,), generator=G) ** 2) * 7919 - 12345
+    k[::97] = -(1 << 63)                         # the table's EMPTY marker as a real key
+    for dt in (torch.int64, torch.int32, torch.float32, torch.float64):
+        v = torch.randint(-9, 9, (n,), generator=G).to(dt)
+        for op in ("add", "min", "max"):
+            uk, acc = gpu.hash_combine(k, v, op)
+            wk, wv = _reduce_reference(k, v, op)
+            o = torch.sort(uk).indices
+            assert torch.equal(uk[o], wk) and torch.equal(acc[o], wv), (dt, op)
+    # a table with a warm (L2) level in front, fed tile by tile, then scan-and-clear
+    v = torch.ones(n, dtype=torch.int64)
+    t = gpu.HashTable(8192, torch.int64, "add", "cpu", warm=1024)
+    t.track(8)                                   # count first-time insertions per destination shard
+    for part in torch.chunk(torch.arange(n), 3):
+        t.combine(k[part], v[part])
+    uk, acc = t.compact(clear=True)
+    wk, wv = _reduce_reference(k, v, "add")
+    o = torch.sort(uk).indices
+    assert torch.equal(uk[o], wk) and torch.equal(acc[o], wv)
+    dest = hashing.hash_tensor(wk[wk != -(1 << 63)], 0) % 8        # the EMPTY key is routed out of band
+    assert torch.equal(t.dest_counts[:8], torch.bincount(dest, minlength=8))
+    assert int((t.slots[:, 0] != -(1 << 63)).sum()) == 0           # the table is empty again
+    # overflow is reported, not silent: 3000 distinct keys cannot fit 1024 + 256 slots
+    small = gpu.HashTable(1024, torch.int64, "add", "cpu", warm=256)
+    small.combine(k, v)
+    assert small.failed() > 0
+    with pytest.raises(gpu.TableFull):
+        small.compact()
+    # compaction into a buffer that is too small keeps writing inside it and reports the need
+    t2 = gpu.HashTable(8192, torch.int64, "add", "cpu", warm=0)
+    t2.combine(k, v)
+    ok, ov = torch.full((100,), -1), torch.full((100,), -1)
+    t2.compact_into(ok, ov, clear=False)
+    assert int(t2.status[3]) == wk.numel() and int((ok != -1).sum()) == 100
 
 
 def test_topk_and_crc32(emulated):
