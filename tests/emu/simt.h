@@ -4,7 +4,9 @@
 // Fibers switch only at synchronisation points (__syncthreads, warp collectives), so
 // between two such points a thread runs alone — data races cannot be observed, but
 // everything else can: indexing, barriers, ballots/shuffles, shared memory, atomics,
-// grid-stride loops, tail handling.  Built with -fsanitize=address the same run is a
+// grid-stride loops, tail handling.  All emulator state is thread_local: every host thread
+// is its own "device", so several ranks of a multi-GPU protocol can run concurrently in one
+// process (their kernels spin on each other's flags through ordinary memory).  Built with -fsanitize=address the same run is a
 // memcheck of the device code.  `kernel<<<grid, block, smem, stream>>>(args)` is
 // rewritten (tests/emu/__init__.py) into `bs_emu_launch(grid, block, smem, [=]{ kernel(args); })`.
 #pragma once
@@ -24,7 +26,7 @@
 #define __forceinline__ inline
 #define __restrict__
 #define __launch_bounds__(...)
-#define __shared__ static
+#define __shared__ static thread_local   // one copy per emulated device (= per host thread)
 #define __constant__ static
 #define __align__(x) __attribute__((aligned(x)))
 
@@ -32,6 +34,24 @@ typedef void* cudaStream_t;
 typedef int cudaError_t;
 enum { cudaSuccess = 0, cudaDevAttrMultiProcessorCount = 16, cudaFuncAttributeMaxDynamicSharedMemorySize = 8 };
 template <class F> static inline cudaError_t cudaFuncSetAttribute(F, int, int) { return cudaSuccess; }
+// graphs are not emulated (callers fall back to direct launches); pinned memory is ordinary memory
+typedef void* cudaGraph_t;
+typedef void* cudaGraphExec_t;
+typedef void* cudaGraphNode_t;
+enum { cudaStreamCaptureModeThreadLocal = 1, cudaHostAllocPortable = 1, cudaHostAllocMapped = 2,
+       cudaErrorNotSupported = 801 };
+static inline cudaError_t cudaStreamBeginCapture(cudaStream_t, int) { return cudaErrorNotSupported; }
+static inline cudaError_t cudaStreamEndCapture(cudaStream_t, cudaGraph_t* g) { *g = nullptr; return cudaErrorNotSupported; }
+static inline cudaError_t cudaGraphGetNodes(cudaGraph_t, cudaGraphNode_t*, size_t* n) { *n = 0; return cudaSuccess; }
+static inline cudaError_t cudaGraphInstantiate(cudaGraphExec_t* e, cudaGraph_t, unsigned long long) { *e = nullptr; return cudaErrorNotSupported; }
+static inline cudaError_t cudaGraphLaunch(cudaGraphExec_t, cudaStream_t) { return cudaErrorNotSupported; }
+static inline cudaError_t cudaGraphExecDestroy(cudaGraphExec_t) { return cudaSuccess; }
+static inline cudaError_t cudaGraphDestroy(cudaGraph_t) { return cudaSuccess; }
+static inline cudaError_t cudaHostAlloc(void** p, size_t n, unsigned) {
+  *p = aligned_alloc(64, (n + 63) & ~(size_t)63);
+  return *p ? cudaSuccess : 2;
+}
+static inline cudaError_t cudaFreeHost(void* p) { free(p); return cudaSuccess; }
 enum cudaMemcpyKind { cudaMemcpyHostToHost, cudaMemcpyHostToDevice, cudaMemcpyDeviceToHost, cudaMemcpyDeviceToDevice,
                       cudaMemcpyDefault };
 static inline cudaError_t cudaGetLastError() { return cudaSuccess; }
@@ -45,19 +65,20 @@ static inline cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, cuda
 static inline cudaError_t cudaGetDevice(int* d) { *d = 0; return cudaSuccess; }
 static inline cudaError_t cudaDeviceGetAttribute(int* v, int, int) { *v = 2; return cudaSuccess; }  // "2 SMs"
 
-struct int4 { int x, y, z, w; };
+struct alignas(16) int4 { int x, y, z, w; };
+static inline int4 make_int4(int x, int y, int z, int w) { return int4{x, y, z, w}; }
 struct bs_dim3 { unsigned x, y, z; };
-static bs_dim3 threadIdx{0, 0, 0}, blockIdx{0, 0, 0}, blockDim{1, 1, 1}, gridDim{1, 1, 1};
+static thread_local bs_dim3 threadIdx{0, 0, 0}, blockIdx{0, 0, 0}, blockDim{1, 1, 1}, gridDim{1, 1, 1};
 
 // ---- fibers -------------------------------------------------------------------
-static ucontext_t bs_sched;
-static std::vector<ucontext_t> bs_fib;
-static std::vector<char> bs_done;
-static int bs_cur, bs_live, bs_nthreads;
-static std::function<void()> bs_kernel;
+static thread_local ucontext_t bs_sched;
+static thread_local std::vector<ucontext_t> bs_fib;
+static thread_local std::vector<char> bs_done;
+static thread_local int bs_cur, bs_live, bs_nthreads;
+static thread_local std::function<void()> bs_kernel;
 static inline void bs_yield() { swapcontext(&bs_fib[bs_cur], &bs_sched); }
 
-static int bs_bar_gen, bs_bar_count;
+static thread_local int bs_bar_gen, bs_bar_count;
 static inline void bs_bar_check() {
   if (bs_live > 0 && bs_bar_count == bs_live) { bs_bar_count = 0; ++bs_bar_gen; }
 }
@@ -78,7 +99,7 @@ struct bs_warp_t {
   unsigned long long val[32], result_val[32];
   int count, gen, lanes, width;  // lanes: still running; width: lanes the warp started with
 };
-static std::vector<bs_warp_t> bs_warps;
+static thread_local std::vector<bs_warp_t> bs_warps;
 static inline bs_warp_t& bs_warp() { return bs_warps[bs_cur >> 5]; }
 static inline int bs_lane() { return bs_cur & 31; }
 static inline void bs_warp_arrive(bs_warp_t& w) {
@@ -191,10 +212,10 @@ static void bs_trampoline() {
   swapcontext(&bs_fib[bs_cur], &bs_sched);
 }
 
-alignas(128) static unsigned char bs_dyn_smem[256 << 10];  // dynamic shared memory of the running CTA
+alignas(128) static thread_local unsigned char bs_dyn_smem[256 << 10];  // dynamic shared memory of the running CTA
 
 static void bs_emu_launch(long long grid, long long block, long long smem_bytes, std::function<void()> k) {
-  static std::vector<std::vector<char>> stacks;
+  static thread_local std::vector<std::vector<char>> stacks;
   if (smem_bytes > (long long)sizeof(bs_dyn_smem)) abort();
   if ((long long)stacks.size() < block) stacks.resize(block, std::vector<char>(1 << 17));
   bs_kernel = k;

@@ -1,0 +1,286 @@
+"""The multi-rank Reduce exchange protocol, run on the CPU.
+
+``csrc/reduce_exchange.cu`` and ``csrc/hash_combine.cu`` are compiled unmodified
+against the SIMT emulator (tests/emu).  The emulator's state is thread-local, so
+every *host thread is one GPU*: two (or three) ranks run their kernels
+concurrently in one process, with each other's control blocks and landing arenas
+mapped as ordinary memory — the same pointers a rank gets from CUDA IPC on a real
+box.  ``rx_begin / rx_scatter / rx_wait / rx_combine / table_compact / rx_end``
+then exchange data and flags exactly as they do over NVLink:
+
+* rows arrive at the right rank, in the right shard (and table region), combined;
+* parity halves and acknowledgements carry several epochs;
+* every device-detected failure is the *same verdict on every rank* — a landing
+  overflow, a vote mismatch, a failed producer, and in particular a destination
+  overflow that only one rank can see (the closing agreement of ``rx_end``);
+* a rank that never shows up is a bounded timeout on the others, not a hang.
+"""
+import ctypes
+import os
+import shutil
+import subprocess
+import sys
+import threading
+
+import pytest
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+import emu  # noqa: E402
+
+from bigslice_b200.frame import hashing  # noqa: E402
+from bigslice_b200.ops import gpu  # noqa: E402
+from bigslice_b200.parallel import rx  # noqa: E402
+
+pytestmark = pytest.mark.skipif(shutil.which("g++") is None, reason="needs g++")
+c_void_p, c_int, c_ll, c_ull = ctypes.c_void_p, ctypes.c_int, ctypes.c_longlong, ctypes.c_ulonglong
+EMPTY = -(1 << 63)
+
+
+class Lib:
+    def __init__(self):
+        asan = bool(os.environ.get("BS_EMU_ASAN"))
+        self.libs = [ctypes.CDLL(emu.build(f, asan=asan)) for f in ("reduce_exchange", "hash_combine")]
+
+    def __getattr__(self, name):
+        for lib in self.libs:
+            try:
+                return getattr(lib, name)
+            except AttributeError:
+                continue
+        raise AttributeError(name)
+
+
+@pytest.fixture
+def lib(monkeypatch):
+    lib = Lib()
+    monkeypatch.setattr(gpu, "require", lambda: lib)
+    monkeypatch.setattr(gpu, "_lib", lib)
+    monkeypatch.setattr(gpu, "_stream", lambda: c_void_p(0))
+    return lib
+
+
+def ptr(t):
+    return c_void_p(t.data_ptr())
+
+
+class Rank:
+    """One emulated GPU: control block, landing arena, device state, report ring."""
+
+    def __init__(self, lib, world, rank, arena_bytes, timeout_s=20.0):
+        self.lib, self.world, self.rank = lib, world, rank
+        sizes = [c_int() for _ in range(4)]
+        lib.bs_rx_sizes(*[ctypes.byref(s) for s in sizes])
+        self.ctrl_bytes, self.state_bytes, self.report_bytes, peers_b = [s.value for s in sizes]
+        assert peers_b == ctypes.sizeof(rx.RxPeers)
+        offs = [c_ll() for _ in range(3)]
+        lib.bs_rx_report_offsets(*[ctypes.byref(o) for o in offs])
+        self.report_offs = tuple(o.value for o in offs)
+        self.ctrl = torch.zeros(self.ctrl_bytes, dtype=torch.uint8)
+        self.arena = torch.zeros(arena_bytes, dtype=torch.uint8)
+        self.state = torch.zeros(self.state_bytes, dtype=torch.uint8)
+        self.ring = torch.zeros(self.report_bytes * rx.NSLOTS // 8, dtype=torch.int64)
+        self.arena_bytes = arena_bytes
+        self.timeout_ns = int(timeout_s * 1e9)
+        self.epoch = 0
+        self.peers = None
+
+    def connect(self, ranks):
+        p = rx.RxPeers()
+        p.world, p.rank = self.world, self.rank
+        for r, other in enumerate(ranks):
+            p.ctrl[r], p.arena[r] = other.ctrl.data_ptr(), other.arena.data_ptr()
+        self.peers = p
+        assert self.lib.bs_rx_state_init(ptr(self.state), c_ull(self.timeout_ns), c_void_p(0)) == 0
+
+    def geometry(self, nparts, regions):
+        pl = (nparts + self.world - 1) // self.world
+        half = (self.arena_bytes // 2) & ~0xFF
+        p = self.peers
+        p.shards_per_rank, p.regions = pl * regions, regions
+        p.region_rows = half // (pl * regions * self.world * 16)
+        p.half_bytes = half
+        return pl
+
+    def exchange(self, keys, vals, nparts, op="add", regions=1, vote=(0, 0), dest_cap=None, out_cap=None):
+        """One full exchange of this rank's rows; returns (report, {shard: (keys, vals)})."""
+        lib, pe = self.lib, self.peers
+        pl = self.geometry(nparts, regions)
+        vdt = vals.dtype
+        vt, opc = c_int(gpu.VTYPE[vdt]), c_int(gpu.OPS[op])
+        table = gpu.HashTable(max(2048, 4 * keys.numel()), vdt, op, "cpu", warm=0)
+        if keys.numel():
+            table.combine(keys, vals)
+        bits = c_ull(table.identity_bits())
+        st = ptr(self.state)
+        assert lib.bs_rx_set_vote(st, c_ull(vote[0]), c_ull(vote[1]), c_void_p(0)) == 0
+        assert lib.bs_rx_scatter(ctypes.byref(pe), st, ptr(table.slots), c_ll(table.total), c_int(nparts), c_int(1),
+                                 bits, ptr(table.status), c_int(0), c_void_p(0)) == 0
+        assert lib.bs_rx_wait(ctypes.byref(pe), st, c_int(nparts), c_void_p(0)) == 0
+        locals_ = [j for j in range(pl) if self.rank + j * self.world < nparts]
+        stp, caps = (c_void_p * max(len(locals_), 1))(), (c_ll * max(len(locals_), 1))()
+        dests = []
+        max_rows = int(pe.region_rows) * self.world
+        for i, j in enumerate(locals_):
+            dt = gpu.HashTable(dest_cap or 8192, vdt, op, "cpu", warm=0)
+            cap = out_cap or dt.total
+            ok, ov = torch.full((cap,), EMPTY), torch.zeros(cap, dtype=vdt)
+            rcap = dt.total // regions
+            for r in range(regions):
+                assert lib.bs_rx_combine(ctypes.byref(pe), st, c_int(j * regions + r), vt, opc,
+                                         c_void_p(dt.slots.data_ptr() + r * rcap * 16), c_ll(rcap), ptr(dt.status),
+                                         c_ll(max_rows), c_void_p(0)) == 0
+            assert lib.bs_table_compact(ptr(dt.slots), c_ll(dt.total), vt, ptr(ok), ptr(ov), ptr(dt.status), c_int(1),
+                                        bits, c_ll(cap), c_void_p(0)) == 0
+            stp[i], caps[i] = dt.status.data_ptr(), cap
+            dests.append((j, dt, ok, ov))
+        assert lib.bs_rx_end(ctypes.byref(pe), st, c_int(len(locals_)), stp, caps, bits, ptr(self.ring),
+                             c_int(rx.NSLOTS), c_int(1), c_void_p(0)) == 0
+        self.epoch += 1
+        words = self.ring.numpy().reshape(rx.NSLOTS, self.report_bytes // 8)[self.epoch % rx.NSLOTS].copy()
+        rep = rx.Report(words, self.report_offs)
+        assert rep.ticket == self.epoch
+        out = {}
+        for i, (j, dt, ok, ov) in enumerate(dests):
+            n = rep.out_rows[i]
+            out[self.rank + j * self.world] = (ok[:n].clone(), ov[:n].clone())
+        return rep, out
+
+
+def run_ranks(world, fn, arena_bytes=1 << 20, timeout_s=20.0, lib=None, absent=()):
+    """Run ``fn(rank_object)`` on one thread per rank; returns the per-rank results."""
+    ranks = [Rank(lib, world, r, arena_bytes, timeout_s) for r in range(world)]
+    for r in ranks:
+        r.connect(ranks)
+    res, errs = [None] * world, []
+
+    def body(r):
+        try:
+            res[r.rank] = fn(r)
+        except BaseException as e:  # noqa: BLE001
+            errs.append((r.rank, e))
+    ts = [threading.Thread(target=body, args=(r,)) for r in ranks if r.rank not in absent]
+    [t.start() for t in ts]
+    [t.join(timeout=120) for t in ts]
+    assert not any(t.is_alive() for t in ts), "an emulated rank hangs"
+    assert not errs, errs
+    return res
+
+
+def rows_of(rank, world, n=6000, seed=0):
+    g = torch.Generator().manual_seed(100 * seed + rank)
+    k = torch.randint(0, 900, (n,), generator=g) * 104729 - 77
+    k[::131] = EMPTY
+    v = torch.randint(1, 5, (n,), generator=g)
+    return k, v
+
+
+def reference(world, nparts, op="add", seed=0, n=6000):
+    ks, vs = zip(*[rows_of(r, world, n, seed) for r in range(world)])
+    k, v = torch.cat(ks), torch.cat(vs)
+    uk, inv = torch.unique(k, return_inverse=True)
+    red = {"add": "sum", "min": "amin", "max": "amax"}[op]
+    acc = torch.zeros(uk.numel(), dtype=v.dtype).scatter_reduce_(0, inv, v, red, include_self=False)
+    dest = hashing.hash_tensor(uk, 0) % nparts
+    return {p: dict(zip(uk[dest == p].tolist(), acc[dest == p].tolist())) for p in range(nparts)}
+
+
+@pytest.mark.parametrize("world,nparts,regions", [(1, 3, 1), (2, 4, 1), (2, 2, 2), (3, 5, 1)])
+def test_rows_reach_their_shard_combined_over_several_epochs(lib, world, nparts, regions):
+    steps = 4   # parity halves alternate; from the third epoch on rx_begin waits for acknowledgements
+
+    def body(r):
+        got = []
+        for s in range(steps):
+            k, v = rows_of(r.rank, world, seed=s)
+            rep, out = r.exchange(k, v, nparts, regions=regions)
+            assert rep.error == 0, rep.error
+            got.append(out)
+        return got
+    res = run_ranks(world, body, lib=lib)
+    for s in range(steps):
+        want = reference(world, nparts, seed=s)
+        seen = {}
+        for r in range(world):
+            for p, (k, v) in res[r][s].items():
+                assert p % world == r                      # shard p lives on rank p % world
+                seen[p] = dict(zip(k.tolist(), v.tolist()))
+        assert seen == want
+
+
+def test_min_and_float_values(lib):
+    def body(r):
+        k, v = rows_of(r.rank, 2)
+        return r.exchange(k, v.to(torch.float32) * 0.5, 2, op="min")
+    res = run_ranks(2, body, lib=lib)
+    ks, vs = zip(*[rows_of(r, 2) for r in range(2)])
+    k, v = torch.cat(ks), torch.cat(vs).to(torch.float32) * 0.5
+    uk, inv = torch.unique(k, return_inverse=True)
+    acc = torch.zeros(uk.numel()).scatter_reduce_(0, inv, v, "amin", include_self=False)
+    want = dict(zip(uk.tolist(), acc.tolist()))
+    got = {}
+    for rep, out in res:
+        assert rep.error == 0
+        for p, (kk, vv) in out.items():
+            got.update(zip(kk.tolist(), vv.tolist()))
+    assert got == want
+
+
+def test_every_rank_reports_the_same_verdict(lib):
+    # (a) a destination overflow only rank 1 can see: its result buffer holds 16 rows,
+    # rank 0's own destination is fine — without rx_end's closing agreement rank 0
+    # would report success and the two ranks would part ways
+    def dest_overflow(r):
+        k, v = rows_of(r.rank, 2)
+        rep, _ = r.exchange(k, v, 2, out_cap=16 if r.rank == 1 else None)
+        return rep.error
+    assert run_ranks(2, dest_overflow, lib=lib) == [rx.DEST_OVERFLOW, rx.DEST_OVERFLOW]
+    # (b) the ranks disagree about which invocation this is
+    def fingerprints(r):
+        k, v = rows_of(r.rank, 2)
+        return r.exchange(k, v, 2, vote=(0, 1000 + r.rank))[0].error
+    assert run_ranks(2, fingerprints, lib=lib) == [rx.FINGERPRINT, rx.FINGERPRINT]
+    # (c) one rank's producers failed
+    def producer_failed(r):
+        k, v = rows_of(r.rank, 3)
+        return r.exchange(k, v, 3, vote=(1 if r.rank == 2 else 0, 7))[0].error
+    assert run_ranks(3, producer_failed, lib=lib) == [rx.PRODUCER_FAILED] * 3
+    # (d) landing regions too small: everybody learns how many rows would have been needed
+    def landing(r):
+        k, v = rows_of(r.rank, 2)
+        rep, _ = r.exchange(k, v, 2)
+        return rep.error, rep.need_rows
+    res = run_ranks(2, landing, arena_bytes=16 << 10, lib=lib)    # 128 rows per region
+    assert [e for e, _ in res] == [rx.LANDING_OVERFLOW] * 2
+    assert res[0][1] == res[1][1] and res[0][1] > 128
+    # ... and the exchange after a failed one works (flags, parity and tables were left consistent)
+    def fail_then_succeed(r):
+        k, v = rows_of(r.rank, 2)
+        first, _ = r.exchange(k, v, 2, vote=(0, r.rank))          # fingerprint mismatch
+        second, out = r.exchange(k, v, 2, vote=(0, 5))
+        return first.error, second.error, out
+    res = run_ranks(2, fail_then_succeed, lib=lib)
+    assert [(a, b) for a, b, _ in res] == [(rx.FINGERPRINT, 0)] * 2
+    want = reference(2, 2)
+    assert {p: dict(zip(k.tolist(), v.tolist())) for _, _, out in res for p, (k, v) in out.items()} == want
+
+
+def test_a_rank_that_never_arrives_is_a_bounded_timeout(lib):
+    def body(r):
+        k, v = rows_of(r.rank, 2)
+        return r.exchange(k, v, 2)[0].error
+    res = run_ranks(2, body, timeout_s=0.5, lib=lib, absent=(1,))
+    assert res[0] == rx.TIMEOUT
+
+
+@pytest.mark.skipif(not os.path.exists(emu.asan_preload().split(":")[0]), reason="needs libasan")
+def test_the_protocol_is_clean_under_address_sanitizer():
+    """The data-path scenarios once more with the kernels built with -fsanitize=address:
+    landing regions, staging buffers, tables and reports are never accessed out of bounds."""
+    env = dict(os.environ, BS_EMU_ASAN="1", LD_PRELOAD=emu.asan_preload(),
+               ASAN_OPTIONS="detect_leaks=0:abort_on_error=1:detect_stack_use_after_return=0")
+    r = subprocess.run([sys.executable, "-m", "pytest", "-q", "-x", "-p", "no:cacheprovider", __file__,
+                        "-k", "several_epochs or same_verdict"], env=env, capture_output=True, text=True,
+                       timeout=900)
+    assert r.returncode == 0, (r.stdout[-3000:], r.stderr[-3000:])
+    assert "passed" in r.stdout and "AddressSanitizer" not in r.stderr
