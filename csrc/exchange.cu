@@ -121,8 +121,14 @@ __global__ void __launch_bounds__(256) xchg_plan_kernel(XcPeers pe, XcSpec sp, X
   const int W = pe.world, me = pe.rank, P = sp.nparts;
   const int par = (int)(epoch & 1);
   const int tid = threadIdx.x;
-  __shared__ int bad;
-  if (tid == 0) bad = 0;
+  // two verdicts, each written in one phase and read only after the barrier that ends it
+  // (one variable for both let a thread that was already voting overwrite what a slower
+  // thread was still reading as the flag-wait verdict — found by the CPU emulator)
+  __shared__ int bad, vote_bad;
+  if (tid == 0) {
+    bad = 0;
+    vote_bad = 0;
+  }
   // 1. publish my counts row and arena base to every peer (P2P stores)
   for (int x = tid; x < W * P; x += blockDim.x) {
     int p = x / P, d = x - p * P;
@@ -162,12 +168,12 @@ __global__ void __launch_bounds__(256) xchg_plan_kernel(XcPeers pe, XcSpec sp, X
   //     and fingerprint, so all of them fail (or proceed) together — no host
   //     collective before the exchange.
   if (tid < W) {
-    if (mine->vote[par][tid][0] != 0) atomicMax(&bad, 3);
-    else if (mine->vote[par][tid][1] != my_fp) atomicMax(&bad, 4);
+    if (mine->vote[par][tid][0] != 0) atomicMax(&vote_bad, 3);
+    else if (mine->vote[par][tid][1] != my_fp) atomicMax(&vote_bad, 4);
   }
   __syncthreads();
-  if (bad) {
-    if (tid == 0) plan->error = bad;
+  if (vote_bad) {
+    if (tid == 0) plan->error = vote_bad;
     return;
   }
   // 4. layout: shards of rank p are packed in increasing d, each (d, c) region

@@ -52,6 +52,23 @@ static inline cudaError_t cudaHostAlloc(void** p, size_t n, unsigned) {
   return *p ? cudaSuccess : 2;
 }
 static inline cudaError_t cudaFreeHost(void* p) { free(p); return cudaSuccess; }
+// device memory is host memory; IPC handles carry the pointer itself (one process)
+enum { cudaErrorPeerAccessAlreadyEnabled = 704, cudaIpcMemLazyEnablePeerAccess = 1 };
+struct cudaIpcMemHandle_t { char reserved[64]; };
+static inline cudaError_t cudaMalloc(void** p, size_t n) { return cudaHostAlloc(p, n ? n : 64, 0); }
+static inline cudaError_t cudaFree(void* p) { free(p); return cudaSuccess; }
+static inline cudaError_t cudaMemset(void* p, int v, size_t n) { memset(p, v, n); return cudaSuccess; }
+static inline cudaError_t cudaDeviceEnablePeerAccess(int, unsigned) { return cudaSuccess; }
+static inline cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t* h, void* p) {
+  memset(h, 0, sizeof(*h));
+  memcpy(h->reserved, &p, sizeof(p));
+  return cudaSuccess;
+}
+static inline cudaError_t cudaIpcOpenMemHandle(void** p, cudaIpcMemHandle_t h, unsigned) {
+  memcpy(p, h.reserved, sizeof(*p));
+  return cudaSuccess;
+}
+static inline cudaError_t cudaIpcCloseMemHandle(void*) { return cudaSuccess; }
 enum cudaMemcpyKind { cudaMemcpyHostToHost, cudaMemcpyHostToDevice, cudaMemcpyDeviceToHost, cudaMemcpyDeviceToDevice,
                       cudaMemcpyDefault };
 static inline cudaError_t cudaGetLastError() { return cudaSuccess; }
@@ -88,6 +105,25 @@ static inline void __syncthreads() {
   bs_bar_check();
   while (bs_bar_gen == gen) bs_yield();
 }
+// barrier + block-wide reduction of a predicate.  Every thread counts its own reduction
+// rounds; round r accumulates in slot r % 4, initialised by its first arrival — a slot is
+// reused four rounds later, when every thread has long read the old result.
+struct bs_red_t { long long round; int any, all, count; };
+static thread_local bs_red_t bs_red[4];
+static thread_local std::vector<long long> bs_red_round;   // per CUDA thread
+static inline int bs_sync_reduce(int p, int what) {
+  const long long r = ++bs_red_round[bs_cur];
+  bs_red_t& a = bs_red[r & 3];
+  if (a.round != r) a = bs_red_t{r, 0, 1, 0};
+  a.any |= (p != 0);
+  a.all &= (p != 0);
+  a.count += (p != 0);
+  __syncthreads();
+  return what == 0 ? a.any : what == 1 ? a.all : a.count;
+}
+static inline int __syncthreads_or(int p) { return bs_sync_reduce(p, 0); }
+static inline int __syncthreads_and(int p) { return bs_sync_reduce(p, 1); }
+static inline int __syncthreads_count(int p) { return bs_sync_reduce(p, 2); }
 static inline void __threadfence() {}
 static inline void __threadfence_block() {}
 static inline void __threadfence_system() {}
@@ -225,6 +261,8 @@ static void bs_emu_launch(long long grid, long long block, long long smem_bytes,
   for (long long b = 0; b < grid; ++b) {
     blockIdx = bs_dim3{(unsigned)b, 0, 0};
     bs_bar_gen = bs_bar_count = 0;
+    bs_red_round.assign(bs_nthreads, 0);
+    for (auto& a : bs_red) a = bs_red_t{0, 0, 1, 0};
     bs_live = bs_nthreads;
     bs_warps.assign((bs_nthreads + 31) / 32, bs_warp_t());
     for (size_t w = 0; w < bs_warps.size(); ++w) {

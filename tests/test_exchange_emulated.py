@@ -284,3 +284,138 @@ def test_the_protocol_is_clean_under_address_sanitizer():
                        timeout=900)
     assert r.returncode == 0, (r.stdout[-3000:], r.stderr[-3000:])
     assert "passed" in r.stdout and "AddressSanitizer" not in r.stderr
+
+
+# ---------------------------------------------------------------------------
+# the generic (any columns) exchange of csrc/exchange.cu, through parallel/peer.py
+
+def _peer_groups(xlib, world, arena_bytes, monkeypatch):
+    """PeerGroup objects wired to each other without CUDA IPC / torch.distributed:
+    what ``PeerGroup.__init__`` sets up, over ordinary memory."""
+    from bigslice_b200.parallel import peer
+    monkeypatch.setattr(gpu, "require", lambda: xlib)
+    monkeypatch.setattr(gpu, "_stream", lambda: c_void_p(0))
+    sizes = [c_int() for _ in range(4)]
+    xlib.bs_xc_sizes(*[ctypes.byref(s) for s in sizes])
+    ctrl_bytes, plan_bytes, peers_b, spec_b = [s.value for s in sizes]
+    assert peers_b == ctypes.sizeof(peer.XcPeers) and spec_b == ctypes.sizeof(peer.XcSpec)
+    offs = [c_ll() for _ in range(5)]
+    xlib.bs_xc_plan_offsets(*[ctypes.byref(o) for o in offs])
+    ctrls = [torch.zeros(ctrl_bytes, dtype=torch.uint8) for _ in range(world)]
+    arenas = [torch.zeros(arena_bytes, dtype=torch.uint8) for _ in range(world)]
+    groups = []
+    for r in range(world):
+        pg = object.__new__(peer.PeerGroup)
+        pg.lib, pg.group, pg.world, pg.rank, pg.device = xlib, None, world, r, torch.device("cpu")
+        pg.ctrl_bytes, pg.plan_bytes = ctrl_bytes, plan_bytes
+        (pg.off_recv_total, pg.off_recv_off, pg.off_arena_end, pg.off_send_count, pg.off_error) = [o.value for o in offs]
+        pg.arena_bytes = arena_bytes
+        pg._ctrl, pg._arena = c_void_p(ctrls[r].data_ptr()), c_void_p(arenas[r].data_ptr())
+        pg.peers = peer.XcPeers()
+        pg.peers.world, pg.peers.rank, pg.peers.arena_bytes = world, r, arena_bytes
+        for q in range(world):
+            pg.peers.ctrl[q], pg.peers.arena[q] = ctrls[q].data_ptr(), arenas[q].data_ptr()
+        pg._opened, pg.epoch, pg.last_sent, pg.barrier_epoch = [], 0, 0, 0
+        pg.plan = torch.zeros(plan_bytes, dtype=torch.uint8)
+        pg.err = torch.zeros(2, dtype=torch.int32)
+        pg.arena_view = arenas[r]
+        pg.stats = {"exchanges": 0, "bytes_sent": 0, "rows_sent": 0}
+        pg._keep = (ctrls, arenas)
+        groups.append(pg)
+    return groups
+
+
+def _threads(world, fn):
+    res, errs = [None] * world, []
+
+    def body(r):
+        try:
+            res[r] = fn(r)
+        except BaseException as e:  # noqa: BLE001
+            errs.append((r, repr(e)))
+    ts = [threading.Thread(target=body, args=(r,)) for r in range(world)]
+    [t.start() for t in ts]
+    [t.join(timeout=120) for t in ts]
+    assert not any(t.is_alive() for t in ts), "an emulated rank hangs"
+    assert not errs, errs
+    return res
+
+
+@pytest.mark.parametrize("world,nparts", [(1, 3), (2, 5), (3, 3)])
+def test_generic_exchange_moves_every_row_to_the_owner_of_its_shard(world, nparts, monkeypatch):
+    """Reshard/Reshuffle/Cogroup shuffles: hash -> count -> plan (count all-gather by
+    peer stores) -> scatter -> wait, for a frame of mixed-width columns keyed on two
+    columns, then with explicit destination ids; two epochs each."""
+    xlib = ctypes.CDLL(emu.build("exchange", asan=bool(os.environ.get("BS_EMU_ASAN"))))
+    groups = _peer_groups(xlib, world, 1 << 20, monkeypatch)
+
+    def cols_of(r, seed):
+        g = torch.Generator().manual_seed(1000 * seed + r)
+        n = 3000 + 17 * r
+        return [torch.randint(-50, 50, (n,), generator=g),                       # int64 key
+                torch.randint(0, 9, (n,), generator=g).to(torch.int32),          # int32 key
+                torch.randn(n, generator=g),                                     # float32 payload
+                torch.randn(n, 3, generator=g, dtype=torch.float64)]             # 24-byte rows
+
+    def body(r):
+        out = []
+        for seed in range(2):
+            cols = cols_of(r, seed)
+            out.append(groups[r].exchange(cols, nparts, nkeys=2))
+        ids = (torch.arange(cols[0].numel()) * 7 + r) % nparts
+        out.append(groups[r].exchange(cols, nparts, nkeys=2, ids=ids))
+        return out
+    res = _threads(world, body)
+
+    def rows(cols):
+        return sorted(zip(cols[0].tolist(), cols[1].tolist(), cols[2].tolist(), map(tuple, cols[3].tolist())))
+    for step in range(3):
+        seed = min(step, 1)
+        every = [cols_of(r, seed) for r in range(world)]
+        for p in range(nparts):
+            want = []
+            for r, cols in enumerate(every):
+                if step < 2:
+                    dest = (hashing.hash_tensor(cols[0], 0) ^ hashing.hash_tensor(cols[1], 0)) % nparts
+                else:
+                    dest = (torch.arange(cols[0].numel()) * 7 + r) % nparts
+                sel = dest == p
+                want += rows([c[sel] for c in cols])
+            got = res[p % world][step][p]
+            assert got[3].shape[1:] == (3,) and got[1].dtype == torch.int32
+            assert rows(got) == sorted(want), (step, p)
+    # no other shard shows up on a rank
+    for r in range(world):
+        assert set(res[r][0]) == set(range(r, nparts, world))
+
+
+def test_generic_exchange_vote_and_arena_overflow_fail_on_every_rank(monkeypatch):
+    from bigslice_b200.parallel import peer
+    xlib = ctypes.CDLL(emu.build("exchange"))
+    groups = _peer_groups(xlib, 2, 64 << 10, monkeypatch)
+    k = torch.arange(1000)
+
+    def voted(r):
+        desc = [(k.data_ptr(), 8, 8, torch.int64, ())]
+        kinds = []
+        # a failed producer, twice in a row, then different fingerprints, then a clean exchange:
+        # a failed vote must leave nothing behind (in particular no abort flag — the plan
+        # kernel once set it by reading the vote verdict as the flag-wait verdict)
+        for vote in ((1 if r == 1 else 0, 5), (1 if r == 1 else 0, 5), (0, 100 + r), (0, 9)):
+            try:
+                got = groups[r].exchange_raw(desc, 1000, 2, vote=vote)
+                kinds.append(sum(int(c[0].numel()) for c in got.values()))
+            except peer.ExchangeVoteError as e:
+                kinds.append(-e.kind)
+        return kinds
+    res = _threads(2, voted)
+    assert [x[:3] for x in res] == [[-3, -3, -4]] * 2
+    assert res[0][3] + res[1][3] == 2000          # every row of both ranks arrived somewhere
+
+    def too_big(r):
+        big = torch.arange(20000)
+        try:
+            groups[r].exchange([big, big.clone()], 2)
+        except peer.ExchangeError as e:
+            return "overflow" in str(e)
+    assert _threads(2, too_big) == [True, True]
