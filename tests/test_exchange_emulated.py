@@ -102,8 +102,12 @@ class Rank:
         p.half_bytes = half
         return pl
 
-    def exchange(self, keys, vals, nparts, op="add", regions=1, vote=(0, 0), dest_cap=None, out_cap=None):
-        """One full exchange of this rank's rows; returns (report, {shard: (keys, vals)})."""
+    def exchange(self, keys, vals, nparts, op="add", regions=1, vote=(0, 0), dest_cap=None, out_cap=None,
+                 two_part=False):
+        """One full exchange of this rank's rows; returns (report, {shard: (keys, vals)}).
+        ``two_part``: the first-run shape of the host code — scatter + wait, a report
+        without acknowledgement (the host sizes the destinations from it), then combine,
+        compaction and the closing ``rx_end``."""
         lib, pe = self.lib, self.peers
         pl = self.geometry(nparts, regions)
         vdt = vals.dtype
@@ -118,6 +122,14 @@ class Rank:
                                  bits, ptr(table.status), c_int(0), c_void_p(0)) == 0
         assert lib.bs_rx_wait(ctypes.byref(pe), st, c_int(nparts), c_void_p(0)) == 0
         locals_ = [j for j in range(pl) if self.rank + j * self.world < nparts]
+        if two_part:
+            none, zero = (c_void_p * pl)(), (c_ll * pl)()
+            assert lib.bs_rx_end(ctypes.byref(pe), st, c_int(pl), none, zero, c_ull(0), ptr(self.ring),
+                                 c_int(rx.NSLOTS), c_int(0), c_void_p(0)) == 0
+            words = self.ring.numpy().reshape(rx.NSLOTS, self.report_bytes // 8)[(self.epoch + 1) % rx.NSLOTS].copy()
+            probe = rx.Report(words, self.report_offs)
+            assert probe.ticket == self.epoch + 1
+            self.probe_rows = probe.recv_rows[:pl]
         stp, caps = (c_void_p * max(len(locals_), 1))(), (c_ll * max(len(locals_), 1))()
         dests = []
         max_rows = int(pe.region_rows) * self.world
@@ -205,6 +217,27 @@ def test_rows_reach_their_shard_combined_over_several_epochs(lib, world, nparts,
             for p, (k, v) in res[r][s].items():
                 assert p % world == r                      # shard p lives on rank p % world
                 seen[p] = dict(zip(k.tolist(), v.tolist()))
+        assert seen == want
+
+
+def test_first_run_and_steady_state_paths_interoperate(lib):
+    """One rank takes the two-part first-run path (probe report, then combine) while the
+    other runs the whole sequence at once, with the destination tables split into two
+    regions: both see the same epochs, flags and landing layout."""
+    def body(r):
+        got = []
+        for s in range(3):
+            k, v = rows_of(r.rank, 2, seed=s)
+            rep, out = r.exchange(k, v, 4, regions=2, two_part=(r.rank + s) % 2 == 0)
+            assert rep.error == 0
+            if (r.rank + s) % 2 == 0:   # the probe said how many rows arrived for every local shard
+                assert r.probe_rows[:2] == rep.recv_rows[:2] and sum(r.probe_rows) > 0
+            got.append(out)
+        return got
+    res = run_ranks(2, body, lib=lib)
+    for s in range(3):
+        want = reference(2, 4, seed=s)
+        seen = {p: dict(zip(k.tolist(), v.tolist())) for r in range(2) for p, (k, v) in res[r][s].items()}
         assert seen == want
 
 
