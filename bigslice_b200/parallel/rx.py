@@ -280,7 +280,8 @@ class ReduceExchange:
 
     def bytes_for(self, nparts: int, region_rows: int, regions: int = 1) -> int:
         pl = (nparts + self.world - 1) // self.world
-        return 2 * (pl * regions * self.world * 16 * int(region_rows) + 256)
+        # (_map rounds the arena down to 4 KiB: round up here so the regions really hold region_rows)
+        return (2 * (pl * regions * self.world * 16 * int(region_rows) + 256) + 0xFFF) & ~0xFFF
 
     @staticmethod
     def regions_for(table_bytes: int, nparts: int, l2_part: int = 48 << 20) -> int:

@@ -452,3 +452,142 @@ def test_generic_exchange_vote_and_arena_overflow_fail_on_every_rank(monkeypatch
         except peer.ExchangeError as e:
             return "overflow" in str(e)
     assert _threads(2, too_big) == [True, True]
+
+
+# ---------------------------------------------------------------------------
+# parallel/rx.py (the host side of the Reduce exchange) over the emulated library
+
+class _FakeEvent:
+    def __init__(self, *a, **k):
+        pass
+
+    def record(self, *a):
+        pass
+
+    def synchronize(self):
+        pass
+
+    def query(self):
+        return True
+
+
+class _FakeStream:
+    def __init__(self, *a, **k):
+        self.cuda_stream = 0
+
+    def wait_event(self, ev):
+        pass
+
+
+class _Null:
+    def __init__(self, *a):
+        pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        return False
+
+
+def test_reduce_exchange_host_object_single_rank(monkeypatch):
+    """``ReduceExchange`` itself — allocation through the IPC entry points, the
+    direct-launch path, first-run probe/finish, reports through the pinned ring,
+    purely local publishes, overflow verdicts, a collective reset that grows the
+    arena — with the CUDA stream/event objects stubbed and the kernels emulated."""
+    class Lib3(Lib):
+        def __init__(self):
+            self.libs = [ctypes.CDLL(emu.build(f)) for f in ("reduce_exchange", "hash_combine", "exchange")]
+    lib = Lib3()
+    monkeypatch.setattr(gpu, "require", lambda: lib)
+    monkeypatch.setattr(gpu, "_lib", lib)
+    monkeypatch.setattr(gpu, "_stream", lambda: c_void_p(0))
+    monkeypatch.setattr(gpu, "_pool", gpu.TablePool())
+    monkeypatch.setenv("BIGSLICE_NO_GRAPHS", "1")
+    for name, fake in (("Stream", _FakeStream), ("Event", _FakeEvent), ("stream", _Null)):
+        monkeypatch.setattr(torch.cuda, name, fake)
+    monkeypatch.setattr(torch.cuda, "synchronize", lambda *a: None)
+    monkeypatch.setattr(torch.cuda, "current_device", lambda: 0)
+
+    ex = rx.ReduceExchange(None, 1 << 20, "cpu", timeout_s=5.0)
+    try:
+        assert ex.world == 1 and ex.arena_bytes == 1 << 20
+        nparts = 3
+        k, v = rows_of(0, 1, n=5000)
+        want = reference(1, nparts, n=5000)
+
+        def table():
+            t = gpu.HashTable(16384, torch.int64, "add", "cpu", warm=0)
+            t.combine(k, v)
+            return t
+
+        def dests(cap_rows):
+            out = []
+            for j in range(nparts):
+                dt = gpu.HashTable(gpu.table_capacity(cap_rows), torch.int64, "add", "cpu", warm=0)
+                out.append((j, dt, torch.empty(cap_rows, dtype=torch.int64), torch.empty(cap_rows, dtype=torch.int64),
+                            cap_rows))
+            return out
+
+        def check(pend, ds):
+            got = {}
+            for j, dt, ok, ov, cap in ds:
+                n = pend.rows(j)
+                got[j] = dict(zip(ok[:n].tolist(), ov[:n].tolist()))
+            assert got == want
+        # first run: probe (rows per shard) -> exactly sized destinations -> finish
+        t = table()
+        probe = ex.exchange_probe(t, nparts, vote=(0, 7))
+        rep = probe.resolve()
+        assert rep.error == 0 and rep.recv_rows[:nparts] == [len(want[p]) for p in range(nparts)]
+        ds = dests(max(rep.recv_rows[:nparts]) + 16)
+        seen = []
+        check(ex.exchange_finish(t, nparts, ds, on_report=seen.append), ds)
+        assert len(seen) == 1 and seen[0].sent_rows == sum(len(w) for w in want.values())
+        # steady state: the whole sequence in one call, several epochs, reports harvested
+        for _ in range(3):
+            ds = dests(1024)
+            check(ex.exchange(table(), nparts, ds, vote=(0, 7)), ds)
+        ex.harvest()
+        assert not ex.pending and ex.stats["exchanges"] == 4
+        # destination buffers too small: a retriable verdict that says what happened
+        ds = dests(64)
+        pend = ex.exchange(table(), nparts, ds)
+        with pytest.raises(rx.ExchangeFailed) as ei:
+            pend.rows(0)
+        assert ei.value.code == rx.DEST_OVERFLOW and ei.value.retriable
+        # landing regions too small (1 MiB arena = 10922 rows per region; 50 000 distinct keys)
+        # -> need_rows -> grow the arena with the collective reset -> the same exchange works
+        bigk = torch.arange(50000) * 7919 + 13
+        bigv = torch.ones(50000, dtype=torch.int64)
+
+        def big_table():
+            t = gpu.HashTable(131072, torch.int64, "add", "cpu", warm=0)
+            t.combine(bigk, bigv)
+            return t
+        attempts = 0
+        while True:   # the executor's loop: lost -> grow by what the report asked for -> again
+            attempts += 1
+            ds = dests(32768)
+            pend = ex.exchange(big_table(), nparts, ds)
+            try:
+                assert sum(pend.rows(j) for j in range(nparts)) == 50000
+                break
+            except rx.ExchangeFailed as e:
+                # (need_rows is a lower bound: CTAs that start after the overflow was raised
+                # send — and count — nothing)
+                assert e.code == rx.LANDING_OVERFLOW and e.retriable and e.need_rows > ex.geometry(nparts)[1]
+                before = ex.arena_bytes
+                ex.reset(ex.bytes_for(nparts, e.need_rows + 8))
+                assert ex.epoch == 0 and ex.arena_bytes > before
+        assert 2 <= attempts <= 4
+        ds = dests(1024)
+        check(ex.exchange(table(), nparts, ds), ds)
+        # a purely local combine -> compact publishes its row count the same way
+        t = table()
+        ok, ov = torch.empty(4096, dtype=torch.int64), torch.empty(4096, dtype=torch.int64)
+        t.compact_into(ok, ov, clear=True)
+        pub = ex.publish(t.status, 4096)
+        assert pub.rows(0) == sum(len(w) for w in want.values())
+    finally:
+        ex.close()
