@@ -237,3 +237,46 @@ def test_the_same_calls_are_clean_under_address_sanitizer():
                         "-k", "not address_sanitizer"], env=env, capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, (r.stdout[-3000:], r.stderr[-3000:])
     assert "passed" in r.stdout and "AddressSanitizer" not in r.stderr
+
+
+def test_hash_combine_random_shapes(emulated):
+    """Randomised tables through the combine kernels: sizes around the TMA kernel's
+    tile threshold, warm levels, high load factors, colliding key patterns, the reserved
+    key, every op and value type.  Either the result is exact or the table says it
+    overflowed — never a silently wrong aggregate."""
+    import random
+    rnd = random.Random(2024)
+    patterns = ("uniform", "strided", "few", "negative")
+    for trial in range(40):
+        n = rnd.choice([1, 17, 511, 4096, 16384, 20001, 33000])
+        pat = rnd.choice(patterns)
+        nk = max(1, rnd.choice([1, 7, n // 50 + 1, n // 3 + 1, n]))
+        g = torch.Generator().manual_seed(trial)
+        base = torch.randint(0, nk, (n,), generator=g)
+        if pat == "strided":
+            k = base * 4096                        # many keys share low bits
+        elif pat == "few":
+            k = base % 5
+        elif pat == "negative":
+            k = -base * 7919 - 1
+        else:
+            k = base * 2654435761 % (1 << 40)
+        if rnd.random() < 0.3:
+            k[:: max(1, n // 9)] = -(1 << 63)
+        dt = rnd.choice([torch.int64, torch.int32, torch.float32, torch.float64])
+        op = rnd.choice(["add", "min", "max"])
+        v = torch.randint(-20, 20, (n,), generator=g).to(dt)
+        distinct = int(torch.unique(k).numel())
+        cap = max(1024, int(distinct * rnd.choice([0.5, 1.2, 2.0, 4.0])))
+        warm = rnd.choice([0, 0, 256, 1024])
+        t = gpu.HashTable(cap, dt, op, "cpu", warm=warm)
+        for part in torch.chunk(torch.arange(n), rnd.choice([1, 2, 5])):
+            if part.numel():
+                t.combine(k[part], v[part], force_simple=rnd.random() < 0.2)
+        wk, wv = _reduce_reference(k, v, op)
+        if t.failed():
+            assert distinct > 0.5 * t.total, (trial, distinct, t.total)   # only a really full table may give up
+            continue
+        uk, acc = t.compact()
+        o = torch.sort(uk).indices
+        assert torch.equal(uk[o], wk) and torch.equal(acc[o], wv), (trial, n, pat, nk, dt, op, cap, warm)
