@@ -17,6 +17,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string.h>
+#include <algorithm>
 #include <functional>
 #include <vector>
 
@@ -248,17 +249,35 @@ static void bs_trampoline() {
   swapcontext(&bs_fib[bs_cur], &bs_sched);
 }
 
-alignas(128) static thread_local unsigned char bs_dyn_smem[256 << 10];  // dynamic shared memory of the running CTA
+alignas(128) static thread_local unsigned char bs_dyn_smem[256 << 10];
+static thread_local unsigned long long bs_rng = 0;
+static thread_local long long bs_sched_seed = -1;   // -1: not read yet
+static inline unsigned bs_rand() {                  // xorshift64*
+  bs_rng ^= bs_rng >> 12;
+  bs_rng ^= bs_rng << 25;
+  bs_rng ^= bs_rng >> 27;
+  return (unsigned)((bs_rng * 2685821657736338717ULL) >> 33);
+}  // dynamic shared memory of the running CTA
 
 static void bs_emu_launch(long long grid, long long block, long long smem_bytes, std::function<void()> k) {
   static thread_local std::vector<std::vector<char>> stacks;
   if (smem_bytes > (long long)sizeof(bs_dyn_smem)) abort();
   if ((long long)stacks.size() < block) stacks.resize(block, std::vector<char>(1 << 17));
+  if (bs_sched_seed < 0) {
+    const char* e = getenv("BS_EMU_SCHED");
+    bs_sched_seed = e ? atoll(e) : 0;
+    bs_rng = 0x9E3779B97F4A7C15ULL ^ (unsigned long long)bs_sched_seed;
+  }
   bs_kernel = k;
   gridDim = bs_dim3{(unsigned)grid, 1, 1};
   blockDim = bs_dim3{(unsigned)block, 1, 1};
   bs_nthreads = (int)block;
-  for (long long b = 0; b < grid; ++b) {
+  std::vector<long long> cta_order(grid);
+  for (long long b = 0; b < grid; ++b) cta_order[b] = b;
+  if (bs_sched_seed)
+    for (long long b = grid - 1; b > 0; --b) std::swap(cta_order[b], cta_order[bs_rand() % (unsigned)(b + 1)]);
+  for (long long bi = 0; bi < grid; ++bi) {
+    const long long b = cta_order[bi];
     blockIdx = bs_dim3{(unsigned)b, 0, 0};
     bs_bar_gen = bs_bar_count = 0;
     bs_red_round.assign(bs_nthreads, 0);
@@ -278,14 +297,25 @@ static void bs_emu_launch(long long grid, long long block, long long smem_bytes,
       bs_fib[t].uc_link = &bs_sched;
       makecontext(&bs_fib[t], bs_trampoline, 0);
     }
+    // Scheduling order.  Default: round robin.  BS_EMU_SCHED=<seed> (non-zero): CTAs are
+    // visited in a random order and, on every pass, the runnable threads too — a schedule
+    // fuzzer: code that only works because threads happen to run in index order between
+    // barriers (an unsynchronised read of something a neighbour writes) gives wrong answers.
+    static thread_local std::vector<int> order;
+    order.resize(bs_nthreads);
+    for (int t = 0; t < bs_nthreads; ++t) order[t] = t;
     int ndone = 0;
-    while (ndone < bs_nthreads)
-      for (int t = 0; t < bs_nthreads; ++t) {
+    while (ndone < bs_nthreads) {
+      if (bs_sched_seed)
+        for (int t = bs_nthreads - 1; t > 0; --t) std::swap(order[t], order[bs_rand() % (unsigned)(t + 1)]);
+      for (int q = 0; q < bs_nthreads; ++q) {
+        const int t = order[q];
         if (bs_done[t]) continue;
         bs_cur = t;
         threadIdx = bs_dim3{(unsigned)t, 0, 0};
         swapcontext(&bs_sched, &bs_fib[t]);
         if (bs_done[t]) ++ndone;
       }
+    }
   }
 }

@@ -2,15 +2,16 @@
 
 ``bs_fused_count`` / ``bs_fused_write`` use warp ballots, a shared-memory scan and
 block barriers, so defining the CUDA keywords away is not enough to run them on the
-host.  This test compiles the *unmodified generated source* with g++ against a small
-SIMT emulator: every CUDA thread of a CTA is a ``ucontext`` fiber, ``__syncthreads``
-and ``__ballot_sync`` are cooperative barriers over the fibers of the block / warp,
-``__shared__`` variables are statics (CTAs run one after the other).  The kept rows
+host.  This test compiles the *unmodified generated source* with g++ against the SIMT
+emulator of ``tests/emu/simt.h``: every CUDA thread of a CTA is a ``ucontext`` fiber,
+``__syncthreads`` and ``__ballot_sync`` are cooperative barriers over the fibers of the
+block / warp, ``__shared__`` variables are statics (CTAs run one after the other).  The kept rows
 must come out exactly as the host evaluation of the same chain produces them — row
 order included — for chains with pass-through columns, type changes, bool outputs
 and row counts that are not a multiple of the CTA chunk.
 """
 import ctypes
+import os
 import shutil
 import subprocess
 
@@ -21,82 +22,9 @@ import torch
 import bigslice_b200 as bs
 from bigslice_b200.ops import jit
 
-EMULATOR = r"""
-#include <ucontext.h>
-#include <cmath>
-#include <cstdlib>
-#include <functional>
-#include <vector>
-using std::fabs; using std::floor; using std::ceil; using std::sqrt; using std::exp; using std::log;
-using std::pow; using std::fmod;
-#define __device__
-#define __global__
-#define __forceinline__ inline
-#define __restrict__
-#define __launch_bounds__(x)
-#define __shared__ static
-struct bs_dim3 { long long x; };
-static bs_dim3 blockIdx{0}, blockDim{256}, threadIdx{0}, gridDim{1};
+EMU_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "emu")
 
-static ucontext_t bs_sched;
-static std::vector<ucontext_t> bs_fib;
-static std::vector<char> bs_done;
-static int bs_cur;
-static std::function<void()> bs_kernel;
-static inline void bs_yield() { swapcontext(&bs_fib[bs_cur], &bs_sched); }
-
-static int bs_bar_gen, bs_bar_count;
-static inline void __syncthreads() {
-  const int gen = bs_bar_gen;
-  if (++bs_bar_count == 256) { bs_bar_count = 0; ++bs_bar_gen; }
-  while (bs_bar_gen == gen) bs_yield();
-}
-struct bs_warp { unsigned bits, result; int count, gen; };
-static bs_warp bs_warps[8];
-static inline unsigned __ballot_sync(unsigned, bool p) {
-  bs_warp& w = bs_warps[bs_cur >> 5];
-  const int gen = w.gen;
-  if (p) w.bits |= 1u << (bs_cur & 31);
-  if (++w.count == 32) { w.result = w.bits; w.bits = 0; w.count = 0; ++w.gen; }
-  while (w.gen == gen) bs_yield();
-  return w.result;
-}
-static inline int __popc(unsigned x) { return __builtin_popcount(x); }
-
-static void bs_trampoline() {
-  bs_kernel();
-  bs_done[bs_cur] = 1;
-  swapcontext(&bs_fib[bs_cur], &bs_sched);
-}
-static void bs_launch(long long nblocks, std::function<void()> k) {
-  bs_kernel = k;
-  gridDim.x = nblocks;
-  static std::vector<std::vector<char>> stacks(256, std::vector<char>(1 << 16));
-  for (long long b = 0; b < nblocks; ++b) {
-    blockIdx.x = b;
-    bs_bar_gen = bs_bar_count = 0;
-    for (auto& w : bs_warps) w = bs_warp{0, 0, 0, 0};
-    bs_fib.assign(256, ucontext_t());
-    bs_done.assign(256, 0);
-    for (int t = 0; t < 256; ++t) {
-      getcontext(&bs_fib[t]);
-      bs_fib[t].uc_stack.ss_sp = stacks[t].data();
-      bs_fib[t].uc_stack.ss_size = stacks[t].size();
-      bs_fib[t].uc_link = &bs_sched;
-      makecontext(&bs_fib[t], bs_trampoline, 0);
-    }
-    int ndone = 0;
-    while (ndone < 256)
-      for (int t = 0; t < 256; ++t) {
-        if (bs_done[t]) continue;
-        bs_cur = t;
-        threadIdx.x = t;
-        swapcontext(&bs_sched, &bs_fib[t]);
-        if (bs_done[t]) ++ndone;
-      }
-  }
-}
-"""
+EMULATOR = '#include "simt.h"\n'   # tests/emu/simt.h: fibers, warp collectives, shared memory
 
 NP = {"int64": np.int64, "int32": np.int32, "float32": np.float32, "float64": np.float64, "bool": np.bool_,
       "int16": np.int16, "int8": np.int8, "uint8": np.uint8}
@@ -110,14 +38,14 @@ def build(tmp_path, tag, in_types, stages):
     out_args = ", ".join("out%d" % j for j in range(len(out_types)))
     wrappers = (
         'extern "C" void run_count(long long nblocks, long long n, %s, int* counts) {\n'
-        "  bs_launch(nblocks, [=] { bs_fused_count(n, %s, counts); });\n}\n"
+        "  bs_emu_launch(nblocks, 256, 0, [=] { bs_fused_count(n, %s, counts); });\n}\n"
         'extern "C" void run_write(long long nblocks, long long n, %s, const long long* offs, %s) {\n'
-        "  bs_launch(nblocks, [=] { bs_fused_write(n, %s, offs, %s); });\n}\n"
+        "  bs_emu_launch(nblocks, 256, 0, [=] { bs_fused_write(n, %s, offs, %s); });\n}\n"
         % (ins, in_args, ins, outs, in_args, out_args))
     cpp, so = tmp_path / (tag + ".cpp"), tmp_path / (tag + ".so")
     cpp.write_text(EMULATOR + src + wrappers)
-    subprocess.run(["g++", "-O1", "-fwrapv", "-std=c++17", "-shared", "-fPIC", "-w", "-o", str(so), str(cpp)],
-                   check=True)
+    subprocess.run(["g++", "-O1", "-fwrapv", "-std=c++17", "-shared", "-fPIC", "-w", "-I", EMU_DIR, "-o", str(so),
+                    str(cpp)], check=True)
     return ctypes.CDLL(str(so)), out_types
 
 

@@ -280,3 +280,20 @@ def test_hash_combine_random_shapes(emulated):
         uk, acc = t.compact()
         o = torch.sort(uk).indices
         assert torch.equal(uk[o], wk) and torch.equal(acc[o], wv), (trial, n, pat, nk, dt, op, cap, warm)
+
+
+def test_kernels_do_not_depend_on_the_order_threads_run_in():
+    """Schedule fuzzing: the emulator visits CTAs and, on every pass, runnable threads in
+    a random order (``BS_EMU_SCHED=<seed>``).  A kernel that is only right because thread
+    i happens to run before thread i+1 between two barriers — how the shared verdict
+    variable of ``xchg_plan_kernel`` went wrong — fails here.  Kernels, generated kernels
+    and the multi-rank exchanges are all re-run under one fuzzed schedule."""
+    here = os.path.dirname(os.path.abspath(__file__))
+    env = dict(os.environ, BS_EMU_SCHED="20260921")
+    r = subprocess.run([sys.executable, "-m", "pytest", "-q", "-x", "-p", "no:cacheprovider",
+                        os.path.join(here, "test_kernels_emulated.py"), os.path.join(here, "test_exchange_emulated.py"),
+                        os.path.join(here, "test_jit_emulated.py"),
+                        "-k", "not address_sanitizer and not order_threads_run"],
+                       env=env, capture_output=True, text=True, timeout=1200)
+    assert r.returncode == 0, (r.stdout[-3000:], r.stderr[-3000:])
+    assert "passed" in r.stdout
