@@ -103,7 +103,7 @@ class Rank:
         return pl
 
     def exchange(self, keys, vals, nparts, op="add", regions=1, vote=(0, 0), dest_cap=None, out_cap=None,
-                 two_part=False):
+                 two_part=False, keymode=0):
         """One full exchange of this rank's rows; returns (report, {shard: (keys, vals)}).
         ``two_part``: the first-run shape of the host code — scatter + wait, a report
         without acknowledgement (the host sizes the destinations from it), then combine,
@@ -119,7 +119,7 @@ class Rank:
         st = ptr(self.state)
         assert lib.bs_rx_set_vote(st, c_ull(vote[0]), c_ull(vote[1]), c_void_p(0)) == 0
         assert lib.bs_rx_scatter(ctypes.byref(pe), st, ptr(table.slots), c_ll(table.total), c_int(nparts), c_int(1),
-                                 bits, ptr(table.status), c_int(0), c_void_p(0)) == 0
+                                 bits, ptr(table.status), c_int(keymode), c_void_p(0)) == 0
         assert lib.bs_rx_wait(ctypes.byref(pe), st, c_int(nparts), c_void_p(0)) == 0
         locals_ = [j for j in range(pl) if self.rank + j * self.world < nparts]
         if two_part:
@@ -239,6 +239,49 @@ def test_first_run_and_steady_state_paths_interoperate(lib):
         want = reference(2, 4, seed=s)
         seen = {p: dict(zip(k.tolist(), v.tolist())) for r in range(2) for p, (k, v) in res[r][s].items()}
         assert seen == want
+
+
+def test_packed_keys_are_placed_like_the_frame_hash_of_their_columns(lib):
+    """Narrow and two-column key prefixes ride the tables packed into one word
+    (ops/keypack.py); the scatter kernel's key modes must send every packed key to the
+    shard ``Frame.hash`` assigns to its *columns*."""
+    from bigslice_b200 import slicetype
+    from bigslice_b200.frame import Frame
+    from bigslice_b200.ops import keypack
+    g = torch.Generator().manual_seed(4)
+    n, nparts = 4000, 5
+    cases = {
+        "int32": [torch.randint(-500, 500, (n,), generator=g).to(torch.int32)],
+        "int16+uint8": [torch.randint(-300, 300, (n,), generator=g).to(torch.int16),
+                        torch.randint(0, 200, (n,), generator=g).to(torch.uint8)],
+        "float32+int32": [(torch.randint(-9, 9, (n,), generator=g).to(torch.float32) * 0.25),
+                          torch.randint(-9, 9, (n,), generator=g).to(torch.int32)],
+        "float64": [torch.randint(-99, 99, (n,), generator=g).to(torch.float64) * 0.5],
+    }
+    for name, cols in cases.items():
+        typ = slicetype.Type([slicetype.dtype_of(c.dtype) for c in cols] + [slicetype.int64], len(cols))
+        lay = keypack.layout_for(typ)
+        assert lay is not None, name
+        word = keypack.pack(cols, lay)
+        ones = torch.ones(n, dtype=torch.int64)
+        want_dest = Frame(cols + [ones], typ).hash(0) % nparts
+
+        def body(r, word=word, lay=lay):
+            return r.exchange(word[r.rank::2], ones[r.rank::2], nparts, keymode=lay.mode)
+        res = run_ranks(2, body, lib=lib)
+        got = {}
+        for rep, out in res:
+            assert rep.error == 0
+            for p, (k, v) in out.items():
+                for kk, vv in zip(k.tolist(), v.tolist()):
+                    got[kk] = (p, vv)
+        uw, inv = torch.unique(word, return_inverse=True)
+        cnt = torch.bincount(inv)
+        first = torch.zeros(uw.numel(), dtype=torch.int64).scatter_(0, inv, torch.arange(n))
+        assert got == {int(w): (int(want_dest[i]), int(c)) for w, i, c in zip(uw.tolist(), first.tolist(), cnt.tolist())}, name
+        # and the packed word unpacks to the original key columns
+        back = keypack.unpack(word, lay)
+        assert all(torch.equal(a, b) for a, b in zip(back, cols)), name
 
 
 def test_min_and_float_values(lib):
