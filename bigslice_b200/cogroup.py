@@ -70,6 +70,67 @@ def _device_join2(frames: Sequence[Frame], out_typ: Type, left: bool = False):
     return Frame(cols, out_typ)
 
 
+_INT_KEYS = (torch.int64, torch.int32, torch.int16, torch.int8, torch.uint8)
+
+
+def _on_device(t) -> bool:
+    """A key column the cogroup kernels can take (tests run the kernels under the CPU
+    emulator and replace this predicate)."""
+    from .ops import gpu
+    return isinstance(t, torch.Tensor) and t.is_cuda and gpu.available()
+
+
+def _device_join_n(frames: Sequence[Frame], out_typ: Type):
+    """Any number of inputs, one integer key column of any width: the same kernels as
+    :func:`_device_join2`, composed.  Every input is sorted and its runs detected; the
+    distinct-key lists are united pairwise (``cogroup_union2`` on keys only); each
+    input's CSR group sizes come from one binary-search pass of the union against its
+    distinct keys (``cogroup_search``).  Narrow integer keys are widened to int64 for the
+    kernels (order-preserving) and narrowed again in the output.  Returns None when the
+    shape is not covered."""
+    if not frames or out_typ.prefix() != 1:
+        return None
+    from .ops import gpu
+    for f in frames:
+        k = f.col(0) if f.num_out() else None
+        if not (_on_device(k) and k.dtype in _INT_KEYS and k.dim() == 1):
+            return None
+    dev = frames[0].device
+    i64 = dict(dtype=torch.int64, device=dev)
+    srt, uniq, starts = [], [], []
+    for f in frames:
+        g = f.prefixed(1).sorted() if len(f) > 1 else f.prefixed(1)
+        srt.append(g)
+        k = g.col(0).to(torch.int64).contiguous()
+        st = gpu.run_starts(k) if len(g) else torch.zeros(0, **i64)
+        starts.append(st)
+        uniq.append(k[st] if len(g) else k)
+    union = uniq[0]
+    for u in uniq[1:]:
+        if u.numel() == 0:
+            continue
+        if union.numel() == 0:
+            union = u
+            continue
+        union, _, _ = gpu.cogroup_union2(union, torch.arange(union.numel(), **i64), union.numel(),
+                                         u, torch.arange(u.numel(), **i64), u.numel())
+    if union.numel() == 0:
+        return Frame.empty(out_typ, dev)
+    cols: List = [union.to(out_typ.out(0).torch_dtype)]
+    for g, u, st in zip(srt, uniq, starts):
+        if u.numel():
+            rank, match = gpu.cogroup_search(union, u)
+            run = torch.diff(torch.cat([st, torch.tensor([len(g)], **i64)]))
+            sizes = torch.where(match.bool(), run[rank.clamp(max=u.numel() - 1)], torch.zeros_like(rank))
+        else:
+            sizes = torch.zeros(union.numel(), **i64)
+        offs = torch.zeros(union.numel() + 1, **i64)
+        torch.cumsum(sizes, 0, out=offs[1:])
+        for j in range(1, g.num_out()):
+            cols.append(ListColumn(offs, g.col(j), g.out(j)))   # the sorted input column, zero copy
+    return Frame(cols, out_typ)
+
+
 def _left_join(srt, uniq, starts, out_typ: Type, dev) -> Frame:
     """Rows for the distinct keys of input 0 only.  The large side's value columns
     are its sorted columns (zero copy, CSR offsets = its run starts); of the small
@@ -103,6 +164,8 @@ def cogroup_frames(frames: Sequence[Frame], nkeys: int, out_typ: Type) -> Frame:
     """Merge-join whole (unsorted) input shards into the cogrouped frame."""
     if nkeys == 1:
         out = _device_join2(frames, out_typ)
+        if out is None:
+            out = _device_join_n(frames, out_typ)   # n inputs / narrow integer keys: the same kernels, composed
         if out is not None:
             return out
     dev = None
