@@ -80,31 +80,55 @@ def _on_device(t) -> bool:
     return isinstance(t, torch.Tensor) and t.is_cuda and gpu.available()
 
 
-def _device_join_n(frames: Sequence[Frame], out_typ: Type):
-    """Any number of inputs, one integer key column of any width: the same kernels as
-    :func:`_device_join2`, composed.  Every input is sorted and its runs detected; the
+_NARROW_INT = (torch.int32, torch.int16, torch.int8, torch.uint8)
+
+
+def _key_word(f: Frame, nkeys: int):
+    """The key prefix of ``f`` as one int64 per row whose signed order is the
+    lexicographic order of the key columns: one integer column of any width, or two
+    integer columns of at most 32 bits (first column in the high half, second biased
+    into the low half).  None when the prefix is not covered or not on the device."""
+    ks = [f.col(i) for i in range(nkeys)] if f.num_out() >= nkeys else []
+    if len(ks) != nkeys or not all(_on_device(k) and k.dim() == 1 for k in ks):
+        return None
+    if nkeys == 1 and ks[0].dtype in _INT_KEYS:
+        return ks[0].to(torch.int64).contiguous()
+    if nkeys == 2 and all(k.dtype in _NARROW_INT for k in ks):
+        return ((ks[0].to(torch.int64) << 32) | ((ks[1].to(torch.int64) + (1 << 31)) & 0xFFFFFFFF)).contiguous()
+    return None
+
+
+def _key_columns(word: torch.Tensor, out_typ: Type, nkeys: int) -> List[torch.Tensor]:
+    if nkeys == 1:
+        return [word.to(out_typ.out(0).torch_dtype)]
+    return [(word >> 32).to(out_typ.out(0).torch_dtype),
+            ((word & 0xFFFFFFFF) - (1 << 31)).to(out_typ.out(1).torch_dtype)]
+
+
+def _device_join_n(frames: Sequence[Frame], out_typ: Type, nkeys: int = 1):
+    """Any number of inputs; a key prefix that maps to one order-preserving int64 word
+    (:func:`_key_word`): the same kernels as :func:`_device_join2`, composed.  Every
+    input is sorted by its key word (one radix sort) and its runs detected; the
     distinct-key lists are united pairwise (``cogroup_union2`` on keys only); each
     input's CSR group sizes come from one binary-search pass of the union against its
-    distinct keys (``cogroup_search``).  Narrow integer keys are widened to int64 for the
-    kernels (order-preserving) and narrowed again in the output.  Returns None when the
-    shape is not covered."""
-    if not frames or out_typ.prefix() != 1:
+    distinct keys (``cogroup_search``).  Returns None when the shape is not covered."""
+    if not frames or out_typ.prefix() != nkeys:
         return None
     from .ops import gpu
-    for f in frames:
-        k = f.col(0) if f.num_out() else None
-        if not (_on_device(k) and k.dtype in _INT_KEYS and k.dim() == 1):
-            return None
+    words = [_key_word(f, nkeys) for f in frames]
+    if any(w is None for w in words):
+        return None
     dev = frames[0].device
     i64 = dict(dtype=torch.int64, device=dev)
     srt, uniq, starts = [], [], []
-    for f in frames:
-        g = f.prefixed(1).sorted() if len(f) > 1 else f.prefixed(1)
-        srt.append(g)
-        k = g.col(0).to(torch.int64).contiguous()
-        st = gpu.run_starts(k) if len(g) else torch.zeros(0, **i64)
+    for f, w in zip(frames, words):
+        if len(f) > 1:
+            w, perm = torch.sort(w, stable=True)
+            f = Frame([C.col_take(c, perm) for c in f.cols()], f.typ)
+        srt.append(f)
+        st = gpu.run_starts(w) if len(f) else torch.zeros(0, **i64)
         starts.append(st)
-        uniq.append(k[st] if len(g) else k)
+        uniq.append(w[st] if len(f) else w)
     union = uniq[0]
     for u in uniq[1:]:
         if u.numel() == 0:
@@ -116,7 +140,7 @@ def _device_join_n(frames: Sequence[Frame], out_typ: Type):
                                          u, torch.arange(u.numel(), **i64), u.numel())
     if union.numel() == 0:
         return Frame.empty(out_typ, dev)
-    cols: List = [union.to(out_typ.out(0).torch_dtype)]
+    cols: List = _key_columns(union, out_typ, nkeys)
     for g, u, st in zip(srt, uniq, starts):
         if u.numel():
             rank, match = gpu.cogroup_search(union, u)
@@ -126,7 +150,7 @@ def _device_join_n(frames: Sequence[Frame], out_typ: Type):
             sizes = torch.zeros(union.numel(), **i64)
         offs = torch.zeros(union.numel() + 1, **i64)
         torch.cumsum(sizes, 0, out=offs[1:])
-        for j in range(1, g.num_out()):
+        for j in range(nkeys, g.num_out()):
             cols.append(ListColumn(offs, g.col(j), g.out(j)))   # the sorted input column, zero copy
     return Frame(cols, out_typ)
 
@@ -162,12 +186,12 @@ def _left_join(srt, uniq, starts, out_typ: Type, dev) -> Frame:
 
 def cogroup_frames(frames: Sequence[Frame], nkeys: int, out_typ: Type) -> Frame:
     """Merge-join whole (unsorted) input shards into the cogrouped frame."""
-    if nkeys == 1:
-        out = _device_join2(frames, out_typ)
-        if out is None:
-            out = _device_join_n(frames, out_typ)   # n inputs / narrow integer keys: the same kernels, composed
-        if out is not None:
-            return out
+    out = _device_join2(frames, out_typ) if nkeys == 1 else None
+    if out is None:
+        # n inputs / narrow or two-column integer keys: the same kernels, composed
+        out = _device_join_n(frames, out_typ, nkeys)
+    if out is not None:
+        return out
     dev = None
     for f in frames:
         if len(f) and f.device.type != "cpu":

@@ -334,7 +334,28 @@ def test_n_way_cogroup_composed_from_the_union_kernels(emulated, monkeypatch):
             assert got is not None and got.col(0).dtype == kdt
             assert rows(got) == rows(want), (kdt, n_inputs)
             assert torch.equal(got.col(0), torch.sort(got.col(0)).values)       # keys come out sorted
-    # not covered: two key columns, float keys -> the generic path
+    # a two-column key of narrow integers: packed into one order-preserving word
+    def frames2(n_inputs):
+        out = []
+        for i in range(n_inputs):
+            n = [500, 300, 77][i]
+            a = torch.randint(-6, 6, (n,), generator=G).to(torch.int32)
+            b = torch.randint(-3, 3, (n,), generator=G).to(torch.int16)
+            out.append(Frame([a, b, torch.randn(n, generator=G)], bs.Type([bs.int32, bs.int16, bs.float32], 2)))
+        return out
+    for n_inputs in (2, 3):
+        fs = frames2(n_inputs)
+        out_typ = bs.Type([bs.int32, bs.int16] + [bs.List(bs.float32)] * n_inputs, 2)
+        monkeypatch.setattr(cogroup, "_on_device", lambda t: False)
+        want = cogroup.cogroup_frames(fs, 2, out_typ)
+        monkeypatch.setattr(cogroup, "_on_device", lambda t: isinstance(t, torch.Tensor))
+        got = cogroup.cogroup_frames(fs, 2, out_typ)
+        key = lambda f: [(r[0], r[1], tuple(tuple(sorted(x)) for x in r[2:])) for r in f.rows()]   # noqa: E731
+        assert key(got) == key(want)                                 # same groups, same (lexicographic) order
+        assert got.col(0).dtype == torch.int32 and got.col(1).dtype == torch.int16
+    # not covered: float keys, a 64-bit column in a two-column key -> the generic path
     monkeypatch.setattr(cogroup, "_on_device", lambda t: isinstance(t, torch.Tensor))
     f = Frame([torch.rand(5), torch.rand(5)], bs.Type([bs.float32, bs.float32], 1))
     assert cogroup._device_join_n([f], bs.Type([bs.float32, bs.List(bs.float32)], 1)) is None
+    f = Frame([torch.arange(5), torch.arange(5).to(torch.int32), torch.rand(5)], bs.Type([bs.int64, bs.int32, bs.float32], 2))
+    assert cogroup._device_join_n([f], bs.Type([bs.int64, bs.int32, bs.List(bs.float32)], 2), 2) is None
