@@ -305,10 +305,16 @@ class TableFull(RuntimeError):
 
 
 def can_hash_combine(f: Frame, op: str) -> bool:
-    if op not in OPS or f.num_out() != 2 or f.prefix() != 1:
+    """``<key prefix, one value>`` frames whose key fits one 64-bit word (ops/keypack.py:
+    an int64/float64 column, a narrower scalar column, or two columns of <= 4 bytes)."""
+    npre = f.prefix()
+    if op not in OPS or f.num_out() != npre + 1:
         return False
-    k, v = f.col(0), f.col(1)
-    return (isinstance(k, torch.Tensor) and k.dtype == torch.int64 and k.dim() == 1
+    from . import keypack
+    if keypack.layout_for(f.typ) is None:
+        return False
+    v = f.col(npre)
+    return (all(isinstance(f.col(i), torch.Tensor) and f.col(i).dim() == 1 for i in range(npre))
             and isinstance(v, torch.Tensor) and v.dtype in VTYPE and v.dim() == 1)
 
 
@@ -444,8 +450,14 @@ def hash_combine(keys: torch.Tensor, vals: torch.Tensor, op: str,
 
 
 def hash_combine_frame(f: Frame, op: str) -> Frame:
-    k, v = hash_combine(f.col(0), f.col(1), op)
-    return Frame([k, v], f.typ)
+    from . import keypack
+    lay, npre = keypack.layout_for(f.typ), f.prefix()
+    if lay.plain_int64:
+        k, v = hash_combine(f.col(0), f.col(1), op)
+        return Frame([k, v], f.typ)
+    word = keypack.pack([f.col(i) for i in range(npre)], lay)
+    k, v = hash_combine(word, f.col(npre), op)
+    return Frame(keypack.unpack(k, lay) + [v], f.typ)
 
 
 # ---------------------------------------------------------------- sort

@@ -818,11 +818,14 @@ class _Fold(Slice):
         if (name in ("add", "min", "max") and len(vals) == 1 and dev.type == "cuda"
                 and isinstance(vals[0], torch.Tensor) and vals[0].dim() == 1
                 and vals[0].dtype == acc_t.torch_dtype):
-            from .ops import gpu
+            from .ops import gpu, keypack
             k = f.col(0)
-            if gpu.available() and isinstance(k, torch.Tensor) and k.dtype == torch.int64 \
+            lay = keypack.layout_for(Type([self.typ.out(0)], 1))   # any key that fits one 64-bit word
+            if gpu.available() and isinstance(k, torch.Tensor) and k.dim() == 1 and lay is not None \
                     and vals[0].dtype in gpu.VTYPE:
-                uk, acc = gpu.hash_combine(k, vals[0], name)
+                uk, acc = gpu.hash_combine(k if lay.plain_int64 else keypack.pack([k], lay), vals[0], name)
+                if not lay.plain_int64:
+                    uk = keypack.unpack(uk, lay)[0]
                 if name == "min":      # the accumulator starts at zero
                     acc = torch.clamp(acc, max=0)
                 elif name == "max":

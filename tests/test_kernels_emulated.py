@@ -359,3 +359,34 @@ def test_n_way_cogroup_composed_from_the_union_kernels(emulated, monkeypatch):
     assert cogroup._device_join_n([f], bs.Type([bs.float32, bs.List(bs.float32)], 1)) is None
     f = Frame([torch.arange(5), torch.arange(5).to(torch.int32), torch.rand(5)], bs.Type([bs.int64, bs.int32, bs.float32], 2))
     assert cogroup._device_join_n([f], bs.Type([bs.int64, bs.int32, bs.List(bs.float32)], 2), 2) is None
+
+
+def test_hash_combine_of_frames_with_packed_key_prefixes(emulated):
+    """``gpu.hash_combine_frame`` (the in-process GPU executor's Reduce): narrow, float
+    and two-column key prefixes are packed into the table's 64-bit key and unpacked."""
+    import bigslice_b200 as bs
+    from bigslice_b200.frame import Frame
+    n = 20000
+    cases = {
+        "int32": ([torch.randint(-300, 300, (n,), generator=G).to(torch.int32)], [bs.int32]),
+        "float64": ([torch.randint(-50, 50, (n,), generator=G).to(torch.float64) * 0.5], [bs.float64]),
+        "int16+uint8": ([torch.randint(-20, 20, (n,), generator=G).to(torch.int16),
+                         torch.randint(0, 9, (n,), generator=G).to(torch.uint8)], [bs.int16, bs.uint8]),
+        "float32+int32": ([torch.randint(-4, 4, (n,), generator=G).to(torch.float32) * 0.25,
+                           torch.randint(-9, 9, (n,), generator=G).to(torch.int32)], [bs.float32, bs.int32]),
+    }
+    v = torch.randint(1, 4, (n,), generator=G)
+    for name, (keys, kt) in cases.items():
+        f = Frame(keys + [v], bs.Type(kt + [bs.int64], len(keys)))
+        assert gpu.can_hash_combine(f, "add"), name
+        out = gpu.hash_combine_frame(f, "add")
+        want = {}
+        for row in zip(*[k.tolist() for k in keys], v.tolist()):
+            want[row[:-1]] = want.get(row[:-1], 0) + row[-1]
+        got = {tuple(r[:-1]): r[-1] for r in out.rows()}
+        assert got == want, name
+        assert [c.dtype for c in out.cols()[:-1]] == [k.dtype for k in keys]
+    # not packable: three key columns, a 64-bit column in a two-column key, a string key
+    k = torch.arange(4)
+    assert not gpu.can_hash_combine(Frame([k, k.to(torch.int32), v[:4]], bs.Type([bs.int64, bs.int32, bs.int64], 2)), "add")
+    assert not gpu.can_hash_combine(Frame([k, k, k, v[:4]], bs.Type([bs.int64] * 4, 3)), "add")
