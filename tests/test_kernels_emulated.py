@@ -234,7 +234,8 @@ def test_the_same_calls_are_clean_under_address_sanitizer():
     env = dict(os.environ, BS_EMU_ASAN="1", LD_PRELOAD=emu.asan_preload(),
                ASAN_OPTIONS="detect_leaks=0:abort_on_error=1:detect_stack_use_after_return=0")
     r = subprocess.run([sys.executable, "-m", "pytest", "-q", "-x", "-p", "no:cacheprovider", __file__,
-                        "-k", "not address_sanitizer"], env=env, capture_output=True, text=True, timeout=900)
+                        "-k", "not address_sanitizer and not order_threads_run and not random_shapes"],
+                       env=env, capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, (r.stdout[-3000:], r.stderr[-3000:])
     assert "passed" in r.stdout and "AddressSanitizer" not in r.stderr
 
