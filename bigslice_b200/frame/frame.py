@@ -46,6 +46,9 @@ def _grow_cap(need: int, cap: int) -> int:
     return max(newcap, need)
 
 
+_NARROW_INTS = (torch.int32, torch.int16, torch.int8, torch.uint8)
+
+
 class Frame:
     """N typed equal-length columns with a key prefix."""
 
@@ -303,6 +306,13 @@ class Frame:
                 if gpu.available():
                     return gpu.sort_pairs_i64(k0, None)[1]
             return torch.sort(k0, stable=True)[1]
+        if len(keys) == 2 and all(isinstance(c, torch.Tensor) and c.dim() == 1 and c.dtype in _NARROW_INTS
+                                  for c in keys) and keys[0].device == keys[1].device:
+            # two integer columns of <= 32 bits: ONE sort of an order-preserving 64-bit word
+            # (first column in the high half, second biased into the low half) instead of
+            # one stable sort + gather per column
+            word = (keys[0].to(torch.int64) << 32) | ((keys[1].to(torch.int64) + (1 << 31)) & 0xFFFFFFFF)
+            return torch.sort(word, stable=True)[1]
         perm = None
         for c in reversed(keys):
             if isinstance(c, torch.Tensor):

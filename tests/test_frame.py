@@ -250,3 +250,17 @@ def test_native_object_hash_and_group_match_reference():
             got = combine_frame(f, fn)
             want = _without_native(lambda: combine_frame(f, fn))
             assert list(got.col(0)) == list(want.col(0)) and torch.equal(got.col(1), want.col(1))
+
+
+def test_two_narrow_integer_key_columns_sort_with_one_packed_sort():
+    import bigslice_b200 as bs
+    g = torch.Generator().manual_seed(9)
+    for dts in ((torch.int32, torch.int32), (torch.int16, torch.uint8), (torch.int8, torch.int32), (torch.uint8, torch.int16)):
+        lo = [0 if d == torch.uint8 else -120 for d in dts]
+        a = torch.randint(lo[0], 120, (3000,), generator=g).to(dts[0])
+        b = torch.randint(lo[1], 120, (3000,), generator=g).to(dts[1])
+        f = Frame([a, b, torch.arange(3000)], bs.Type([bs.slicetype.dtype_of(d) for d in dts] + [bs.int64], 2))
+        want = sorted(range(3000), key=lambda i: (int(a[i]), int(b[i])))   # stable lexicographic order
+        assert f.sort_indices().tolist() == want
+        s = f.sorted()
+        assert s.col(2).tolist() == want
