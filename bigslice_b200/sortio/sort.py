@@ -101,6 +101,15 @@ class FrameBuffer:
     Fill = fill
 
 
+def _device_key(k) -> bool:
+    """A key column the merge-path kernel takes: int64, on a GPU with the kernel library
+    (tests run the kernel under the CPU emulator and replace this predicate)."""
+    if not (isinstance(k, torch.Tensor) and k.is_cuda and k.dtype == torch.int64 and k.dim() == 1):
+        return False
+    from ..ops import gpu
+    return gpu.available()
+
+
 class MergeReader(Reader):
     """Batched k-way merge of sorted streams."""
 
@@ -193,12 +202,9 @@ class MergeReader(Reader):
         if self.nkeys != 1:
             return None
         for b in live:
-            k = b.frame.col(0)
-            if not (isinstance(k, torch.Tensor) and k.is_cuda and k.dtype == torch.int64 and k.dim() == 1):
+            if not _device_key(b.frame.col(0)):
                 return None
         from ..ops import gpu
-        if not gpu.available():
-            return None
         lasts = torch.stack([b.frame.col(0)[-1] for b in live])
         bound = lasts.min()
         cuts = [int(torch.searchsorted(b.frame.col(0), bound, right=True)) for b in live]

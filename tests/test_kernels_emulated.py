@@ -391,3 +391,39 @@ def test_hash_combine_of_frames_with_packed_key_prefixes(emulated):
     k = torch.arange(4)
     assert not gpu.can_hash_combine(Frame([k, k.to(torch.int32), v[:4]], bs.Type([bs.int64, bs.int32, bs.int64], 2)), "add")
     assert not gpu.can_hash_combine(Frame([k, k, k, v[:4]], bs.Type([bs.int64] * 4, 3)), "add")
+
+
+def test_merge_reader_device_step_merges_sorted_streams_with_the_merge_path_kernel(emulated, monkeypatch):
+    """``sortio.MergeReader`` over several key-sorted streams: the device step (emit bound
+    and per-stream cuts by searchsorted, pairwise stable merges with ``csrc/merge.cu``)
+    yields the same rows, in the same stable order, as sorting everything at once."""
+    import bigslice_b200 as bs
+    from bigslice_b200 import sortio
+    from bigslice_b200.frame import Frame
+    from bigslice_b200.sliceio import FrameReader
+    from bigslice_b200.sortio import sort as sortmod
+    monkeypatch.setattr(sortmod, "_device_key", lambda k: isinstance(k, torch.Tensor) and k.dtype == torch.int64)
+    monkeypatch.setattr(sortmod.MergeReader, "EAGER_ROWS", 100)     # merge step by step, do not sort it all
+    typ = bs.Type([bs.int64, bs.int64, bs.float32], 1)
+    streams, allk, allid = [], [], []
+    base = 0
+    for s in range(5):
+        n = [4000, 1, 2500, 0, 3333][s]
+        k = torch.sort(torch.randint(0, 500, (n,), generator=G)).values
+        ident = torch.arange(base, base + n)
+        base += n
+        allk.append(k)
+        allid.append(ident)
+        streams.append(FrameReader(Frame([k, ident, torch.randn(n, generator=G)], typ)))
+    calls = []
+    real = gpu.merge_sorted_i64
+    monkeypatch.setattr(gpu, "merge_sorted_i64", lambda a, b: (calls.append(1), real(a, b))[1])
+    out = list(sortio.merge_reader(typ, streams, tile=1024))
+    assert calls, "the merge-path kernel was not used"
+    gk = torch.cat([f.col(0) for f in out])
+    gid = torch.cat([f.col(1) for f in out])
+    k, ident = torch.cat(allk), torch.cat(allid)
+    order = torch.sort(k, stable=True).indices                         # streams in order = stable across streams
+    assert torch.equal(gk, k[order])
+    assert torch.equal(torch.sort(gid).values, ident)                  # every row exactly once
+    assert torch.equal(k[gid], gk)                                     # payloads travelled with their keys
