@@ -427,3 +427,27 @@ def test_merge_reader_device_step_merges_sorted_streams_with_the_merge_path_kern
     assert torch.equal(gk, k[order])
     assert torch.equal(torch.sort(gid).values, ident)                  # every row exactly once
     assert torch.equal(k[gid], gk)                                     # payloads travelled with their keys
+
+
+def test_text_pipeline_runs_the_string_kernels(emulated):
+    """lines -> Tokenize -> StringIds -> Reduce(add) and urls -> UrlDomains: the text
+    combinators drive the tokeniser / id / URL-host / span kernels (emulated here) and
+    verify every batch's dictionary."""
+    import bigslice_b200 as bs
+    from bigslice_b200 import slicetest, text
+    words = ["alpha", "beta", "gamma", "δelta", "e"]
+    lines = np.array([" ".join(words[(i + j) % 5] for j in range(1 + i % 4)) for i in range(400)], dtype=object)
+    d = text.IdDictionary()
+    s = bs.Reduce(text.StringIds(text.Tokenize(bs.Const(3, lines)), d), bs.ops.add)
+    rows = slicetest.run(s).rows()
+    names = d.lookup([k for k, _ in rows])
+    want = {}
+    for ln in lines.tolist():
+        for w in ln.split():
+            want[w] = want.get(w, 0) + 1
+    assert {names[k]: v for k, v in rows} == want
+    urls = np.array(["https://A.example.com/x?y", "http://b.org", "mailto:nobody", "c.net/p", ""] * 30, dtype=object)
+    doms = [r[0] for r in slicetest.run(text.UrlDomains(bs.Const(2, urls))).rows()]
+    # (same answers as the host implementation: no scheme -> everything up to the first '/')
+    assert sorted(set(doms)) == ["a.example.com", "b.org", "c.net", "mailto:nobody"]
+    assert doms.count("b.org") == 30 and len(doms) == 120            # rows without a host are dropped
