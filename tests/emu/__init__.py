@@ -19,6 +19,7 @@ device code is then a hard failure (a memcheck of the kernels without a GPU).
 from __future__ import annotations
 
 import ctypes
+import hashlib
 import os
 import re
 import subprocess
@@ -169,20 +170,31 @@ _built = {}
 
 
 def build(name: str, asan: bool = False) -> str:
-    """Compile csrc/<name>.cu for the emulator; returns the path of the shared object."""
+    """Compile csrc/<name>.cu for the emulator; returns the path of the shared object.
+    Objects are cached by content (source after rewriting + emulator headers + flags), so
+    the sanitizer and schedule-fuzzing subprocesses of a test run reuse them."""
     key = (name, asan)
     if key in _built:
         return _built[key]
-    d = tempfile.mkdtemp(prefix="bsemu-")
-    cpp, so = os.path.join(d, name + "_emu.cpp"), os.path.join(d, name + "_emu.so")
-    with open(cpp, "w") as fh:
-        fh.write(source_for(name))
-    cmd = ["g++", "-O1", "-g", "-fwrapv", "-std=c++17", "-shared", "-fPIC", "-w", "-I", HERE, "-o", so, cpp]
+    src = source_for(name)
+    flags = ["-O1", "-g", "-fwrapv", "-std=c++17", "-shared", "-fPIC", "-w", "-I", HERE]
     if asan:
-        cmd[1:1] = ["-fsanitize=address", "-fno-omit-frame-pointer"]
-    r = subprocess.run(cmd, capture_output=True, text=True)
-    if r.returncode != 0:
-        raise RuntimeError("emulator build of %s.cu failed:\n%s" % (name, r.stderr[-3000:]))
+        flags = ["-fsanitize=address", "-fno-omit-frame-pointer"] + flags
+    h = hashlib.sha1()
+    for part in [src, " ".join(flags)] + [open(os.path.join(HERE, f)).read() for f in ("simt.h", "ptx_emu.h")]:
+        h.update(part.encode())
+    cache = os.path.join(tempfile.gettempdir(), "bsemu-cache-%d" % os.getuid())
+    os.makedirs(cache, exist_ok=True)
+    so = os.path.join(cache, "%s-%s.so" % (name, h.hexdigest()[:16]))
+    if not os.path.exists(so):
+        d = tempfile.mkdtemp(prefix="bsemu-")
+        cpp, tmp = os.path.join(d, name + "_emu.cpp"), os.path.join(d, name + "_emu.so")
+        with open(cpp, "w") as fh:
+            fh.write(src)
+        r = subprocess.run(["g++"] + flags + ["-o", tmp, cpp], capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError("emulator build of %s.cu failed:\n%s" % (name, r.stderr[-3000:]))
+        os.replace(tmp, so)   # atomic: concurrent test processes may build the same object
     _built[key] = so
     return so
 
