@@ -279,7 +279,10 @@ class PeerGroup:
         specialised table kernels: rows of shard ``murmur3(key) % nparts`` arrive
         as ``[keys, values]`` views of this rank's arena (zero copy; valid until
         the next exchange).  With ``clear`` the table is left empty — ready for
-        reuse after ``reset_status()`` — so no separate init pass is needed."""
+        reuse after ``reset_status()`` — so no separate init pass is needed.  The
+        table's reserved EMPTY key is *not* exchanged: its combined value stays in the
+        status block for the caller to route (the Reduce path proper uses
+        ``parallel/rx.py``, whose scatter kernel routes it like any other row)."""
         vb = torch.empty(0, dtype=table.vdtype).element_size()
         self.epoch += 1
         self._chk(self.lib.bs_xc_exchange_table(

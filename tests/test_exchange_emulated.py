@@ -657,3 +657,48 @@ def test_row_record_exchange_variant(world, nparts, monkeypatch):
             want += list(zip(c[0][sel].tolist(), c[1][sel].tolist(), map(tuple, c[2][sel].tolist())))
         got = res[p % world][1][p]
         assert sorted(zip(got[0].tolist(), got[1].tolist(), map(tuple, got[2].tolist()))) == sorted(want)
+
+
+def test_table_exchange_of_the_generic_path(monkeypatch):
+    """``PeerGroup.exchange_table`` (the in-place table shuffle of csrc/exchange.cu, kept as
+    the library-baseline's companion): rows by shard, scan-and-clear, votes, and a clean
+    exchange after failed votes — two ranks."""
+    from bigslice_b200.parallel import peer
+
+    class Both(Lib):
+        def __init__(self):
+            self.libs = [ctypes.CDLL(emu.build(f)) for f in ("exchange", "hash_combine")]
+    xlib = Both()
+    monkeypatch.setattr(gpu, "_lib", xlib)
+    groups = _peer_groups(xlib, 2, 1 << 20, monkeypatch)
+    nparts = 4
+
+    def body(r):
+        k, v = rows_of(r, 2)
+        kinds, out = [], None
+        for vote in ((1 if r == 1 else 0, 5), (0, 100 + r), (0, 9)):
+            t = gpu.HashTable(16384, torch.int64, "add", "cpu", warm=0)
+            t.track(nparts)
+            t.combine(k, v)
+            try:
+                got = groups[r].exchange_table(t, nparts, clear=True, vote=vote)
+                kinds.append(0)
+                out = {p: (c[0].clone(), c[1].clone()) for p, c in got.items()}
+                assert int((t.slots[:, 0] != EMPTY).sum()) == 0          # scanned and cleared
+                # the reserved key does not travel with this kernel: it stays in the status
+                # block (has_special, value) for the caller to route
+                assert int(t.status[1]) == 1 and int(t.status[2]) == int(v[k == EMPTY].sum())
+            except peer.ExchangeVoteError as e:
+                kinds.append(e.kind)
+        return kinds, out
+    res = _threads(2, body)
+    assert [k for k, _ in res] == [[3, 4, 0]] * 2
+    # arrivals are per-source partial aggregates of each shard: combine them and compare
+    want = {p: {a: b for a, b in d.items() if a != EMPTY} for p, d in reference(2, nparts).items()}
+    got = {}
+    for _, out in res:
+        for p, (kk, vv) in out.items():
+            d = got.setdefault(p, {})
+            for a, b in zip(kk.tolist(), vv.tolist()):
+                d[a] = d.get(a, 0) + b
+    assert got == want
