@@ -702,3 +702,105 @@ def test_table_exchange_of_the_generic_path(monkeypatch):
             for a, b in zip(kk.tolist(), vv.tolist()):
                 d[a] = d.get(a, 0) + b
     assert got == want
+
+
+class _FakeGroup:
+    """A two-thread stand-in for a torch.distributed group: rank = which thread asks."""
+
+    def __init__(self, world):
+        self.world = world
+        self.ranks = {}
+        self.barrier = threading.Barrier(world)
+        self.slots = [None] * world
+
+    def rank(self):
+        return self.ranks[threading.get_ident()]
+
+
+def test_reduce_exchange_host_objects_two_ranks(monkeypatch):
+    """Two ``ReduceExchange`` objects (one per thread) find each other through the IPC
+    entry points, run graph-less exchanges over several epochs, fail together when only
+    rank 1's result buffers are too small, and grow their arenas with the collective reset."""
+    import torch.distributed as dist
+
+    class Lib3(Lib):
+        def __init__(self):
+            self.libs = [ctypes.CDLL(emu.build(f)) for f in ("reduce_exchange", "hash_combine", "exchange")]
+    lib = Lib3()
+    monkeypatch.setattr(gpu, "require", lambda: lib)
+    monkeypatch.setattr(gpu, "_lib", lib)
+    monkeypatch.setattr(gpu, "_stream", lambda: c_void_p(0))
+    monkeypatch.setattr(gpu, "_pool", gpu.TablePool())
+    monkeypatch.setenv("BIGSLICE_NO_GRAPHS", "1")
+    for name, fake in (("Stream", _FakeStream), ("Event", _FakeEvent), ("stream", _Null)):
+        monkeypatch.setattr(torch.cuda, name, fake)
+    monkeypatch.setattr(torch.cuda, "synchronize", lambda *a: None)
+    monkeypatch.setattr(torch.cuda, "current_device", lambda: 0)
+    grp = _FakeGroup(2)
+    monkeypatch.setattr(dist, "get_world_size", lambda g=None: g.world)
+    monkeypatch.setattr(dist, "get_rank", lambda g=None: g.rank())
+
+    def all_gather_object(out, obj, group=None):
+        group.slots[group.rank()] = obj
+        group.barrier.wait()
+        out[:] = list(group.slots)
+        group.barrier.wait()
+    monkeypatch.setattr(dist, "all_gather_object", all_gather_object)
+    monkeypatch.setattr(dist, "barrier", lambda group=None: group.barrier.wait())
+    nparts = 4
+
+    def dests(ex, cap_rows):
+        pl, _ = ex.geometry(nparts)
+        return [(j, gpu.HashTable(gpu.table_capacity(cap_rows), torch.int64, "add", "cpu", warm=0),
+                 torch.empty(cap_rows, dtype=torch.int64), torch.empty(cap_rows, dtype=torch.int64), cap_rows)
+                for j in range(pl) if ex.rank + j * ex.world < nparts]
+
+    def body(r):
+        grp.ranks[threading.get_ident()] = r
+        grp.barrier.wait()
+        ex = rx.ReduceExchange(grp, 1 << 20, "cpu", timeout_s=20.0)
+        try:
+            assert (ex.world, ex.rank) == (2, r)
+            outs = []
+            for seed in range(3):
+                k, v = rows_of(r, 2, seed=seed)
+                t = gpu.HashTable(16384, torch.int64, "add", "cpu", warm=0)
+                t.combine(k, v)
+                ds = dests(ex, 2048)
+                pend = ex.exchange(t, nparts, ds, vote=(0, 3))
+                outs.append({ex.rank + j * ex.world: dict(zip(ok[:pend.rows(i)].tolist(), ov[:pend.rows(i)].tolist()))
+                             for i, (j, dt, ok, ov, cap) in enumerate(ds)})
+            # only rank 1's buffers are too small: both ranks fail, together
+            k, v = rows_of(r, 2)
+            t = gpu.HashTable(16384, torch.int64, "add", "cpu", warm=0)
+            t.combine(k, v)
+            pend = ex.exchange(t, nparts, dests(ex, 2048 if r == 0 else 32))
+            try:
+                pend.rows(0)
+                verdict = 0
+            except rx.ExchangeFailed as e:
+                verdict = e.code
+            # collective reset with a larger arena, then a clean exchange at epoch 1 again
+            ex.reset(4 << 20)
+            t = gpu.HashTable(16384, torch.int64, "add", "cpu", warm=0)
+            t.combine(k, v)
+            ds = dests(ex, 2048)
+            pend = ex.exchange(t, nparts, ds)
+            last = {ex.rank + j * ex.world: dict(zip(ok[:pend.rows(i)].tolist(), ov[:pend.rows(i)].tolist()))
+                    for i, (j, dt, ok, ov, cap) in enumerate(ds)}
+            return outs, verdict, last, ex.arena_bytes, ex.epoch
+        finally:
+            grp.barrier.wait()
+            ex.close()
+    res = _threads(2, body)
+    for seed in range(3):
+        got = {}
+        for outs, *_ in res:
+            got.update(outs[seed])
+        assert got == reference(2, nparts, seed=seed)
+    assert [r[1] for r in res] == [rx.DEST_OVERFLOW] * 2
+    last = {}
+    for r in res:
+        last.update(r[2])
+    assert last == reference(2, nparts)
+    assert all(r[3] == 4 << 20 and r[4] == 1 for r in res)
