@@ -804,3 +804,50 @@ def test_reduce_exchange_host_objects_two_ranks(monkeypatch):
         last.update(r[2])
     assert last == reference(2, nparts)
     assert all(r[3] == 4 << 20 and r[4] == 1 for r in res)
+
+
+def test_exchange_random_shapes(lib):
+    """Random worlds, shard counts (fewer shards than ranks, odd counts), table regions,
+    ops, value types and row counts (including ranks with no rows at all)."""
+    import random
+    rnd = random.Random(99)
+    for trial in range(12):
+        world = rnd.choice([1, 2, 3, 4])
+        regions = rnd.choice([1, 1, 2, 4])
+        nparts = rnd.choice([1, 2, 3, 5, 8])
+        if nparts * regions > 64:
+            continue
+        op = rnd.choice(["add", "min", "max"])
+        dt = rnd.choice([torch.int64, torch.int32, torch.float32, torch.float64])
+        sizes = [rnd.choice([0, 1, 37, 2500, 7000]) for _ in range(world)]
+        nkeys = rnd.choice([3, 200, 5000])
+
+        def rows(r):
+            g = torch.Generator().manual_seed(1000 * trial + r)
+            n = sizes[r]
+            k = torch.randint(0, nkeys, (n,), generator=g) * 1000003 - 5
+            if n > 10:
+                k[::7] = EMPTY
+            return k, torch.randint(-9, 9, (n,), generator=g).to(dt)
+
+        def body(r):
+            k, v = rows(r.rank)
+            return r.exchange(k, v, nparts, op=op, regions=regions, dest_cap=16384)
+        res = run_ranks(world, body, arena_bytes=4 << 20, lib=lib)
+        ks, vs = zip(*[rows(r) for r in range(world)])
+        k, v = torch.cat(ks), torch.cat(vs)
+        want = {}
+        if k.numel():
+            uk, inv = torch.unique(k, return_inverse=True)
+            red = {"add": "sum", "min": "amin", "max": "amax"}[op]
+            acc = torch.zeros(uk.numel(), dtype=dt).scatter_reduce_(0, inv, v, red, include_self=False)
+            dest = hashing.hash_tensor(uk, 0) % nparts
+            want = {(int(p), a): b for p, a, b in zip(dest.tolist(), uk.tolist(), acc.tolist())}
+        got = {}
+        for r, (rep, out) in enumerate(res):
+            assert rep.error == 0, (trial, world, nparts, regions, rep.error)
+            for p, (kk, vv) in out.items():
+                assert p % world == r
+                for a, b in zip(kk.tolist(), vv.tolist()):
+                    got[(p, a)] = b
+        assert got == want, (trial, world, nparts, regions, op, dt, sizes)
