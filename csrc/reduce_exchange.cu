@@ -209,8 +209,12 @@ __global__ void __launch_bounds__(RX_THREADS, RX_CTAS_PER_SM) rx_scatter_kernel(
   if (tid == 0) cta_err = 0;
   __syncthreads();
   // Rows are only sent by a healthy exchange; the scan (and the clearing) happens
-  // regardless, so the table always comes out empty and reusable.
-  const bool send = st->error == 0 && my_status == 0 && tst->failed == 0;
+  // regardless, so the table always comes out empty and reusable.  A landing overflow
+  // raised by a CTA that finished earlier does not stop the others: they keep reserving
+  // (rx_flush drops what does not fit), so `need_rows` ends up exact and one retry with a
+  // larger arena is enough.
+  const int err0 = st->error;
+  const bool send = (err0 == 0 || err0 == RX_LANDING_OVERFLOW) && my_status == 0 && tst->failed == 0;
   {
     const long long ntiles = (total + RX_TILE - 1) / RX_TILE;
     int4 nxt[RX_PER];
