@@ -850,3 +850,49 @@ def test_exchange_random_shapes(lib):
                 for a, b in zip(kk.tolist(), vv.tolist()):
                     got[(p, a)] = b
         assert got == want, (trial, world, nparts, regions, op, dt, sizes)
+
+
+def test_replicator_peer_store_broadcast(monkeypatch):
+    """``parallel/broadcast.Replicator`` in its peer-store mode (the fallback of the NVSwitch
+    multicast path, same kernel shape): every rank's rows land in every rank's buffer at the
+    right offsets, for several columns of different widths."""
+    import torch.distributed as dist
+    from bigslice_b200.parallel.broadcast import Replicator
+    xlib = ctypes.CDLL(emu.build("cogroup"))
+    monkeypatch.setattr(gpu, "require", lambda: xlib)
+    monkeypatch.setattr(gpu, "_stream", lambda: c_void_p(0))
+    world = 3
+    grp = _FakeGroup(world)
+
+    def all_gather_object(out, obj, group=None):
+        group.slots[group.rank()] = obj
+        group.barrier.wait()
+        out[:] = list(group.slots)
+        group.barrier.wait()
+    monkeypatch.setattr(dist, "all_gather_object", all_gather_object)
+
+    class Handle:
+        def barrier(self):
+            grp.barrier.wait()
+    nbytes = 1 << 20
+    bufs = [torch.zeros(nbytes, dtype=torch.uint8) for _ in range(world)]
+    ptrs = torch.tensor([b.data_ptr() for b in bufs], dtype=torch.int64)
+
+    def cols_of(r):
+        g = torch.Generator().manual_seed(r)
+        n = [400, 0, 1002][r]
+        return [torch.randint(-9, 9, (n,), generator=g), torch.randn(n, 2, generator=g, dtype=torch.float64),
+                torch.randn(n, 4, generator=g)]
+
+    def body(r):
+        grp.ranks[threading.get_ident()] = r
+        grp.barrier.wait()
+        rep = object.__new__(Replicator)
+        rep.group = rep.ctrl_group = grp
+        rep.world, rep.rank, rep.device, rep.nbytes = world, r, torch.device("cpu"), nbytes
+        rep.mode, rep.buf, rep.handle, rep.mc_ptr, rep.peer_ptrs, rep.why = "peer", bufs[r], Handle(), 0, ptrs, ""
+        return [rep.all_gather(cols_of(r)) for _ in range(2)][-1]
+    res = _threads(world, body)
+    want = [torch.cat([cols_of(r)[j] for r in range(world)]) for j in range(3)]
+    for got in res:
+        assert all(torch.equal(a, b) for a, b in zip(got, want))
