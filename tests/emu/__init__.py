@@ -159,9 +159,13 @@ def source_for(name: str) -> str:
 
 
 def asan_preload() -> str:
+    """LD_PRELOAD value for running an ``asan=True`` build inside python ("" without g++)."""
     libs = []
     for lib in ("libasan.so", "libstdc++.so"):
-        p = subprocess.run(["g++", "-print-file-name=" + lib], capture_output=True, text=True).stdout.strip()
+        try:
+            p = subprocess.run(["g++", "-print-file-name=" + lib], capture_output=True, text=True).stdout.strip()
+        except OSError:
+            return ""
         libs.append(os.path.realpath(p))
     return ":".join(libs)
 
