@@ -896,3 +896,57 @@ def test_replicator_peer_store_broadcast(monkeypatch):
     want = [torch.cat([cols_of(r)[j] for r in range(world)]) for j in range(3)]
     for got in res:
         assert all(torch.equal(a, b) for a, b in zip(got, want))
+
+
+def test_long_sequences_with_failures_of_every_kind(lib):
+    """Fifteen epochs on three ranks where a random epoch fails in a random way (vote
+    mismatch, failed producer, destination overflow on one rank, landing overflow): every
+    rank reports the same verdict every time, and the epochs around a failure are exact —
+    parity halves, acknowledgements, closing flags and tables stay consistent."""
+    import random
+    rnd = random.Random(7)
+    world, nparts, epochs = 3, 5, 15
+    plan = []
+    for e in range(epochs):
+        kind = rnd.choice(["ok", "ok", "ok", "fp", "producer", "dest", "landing"])
+        plan.append((kind, rnd.randrange(world)))
+
+    def rows(r, e, big):
+        g = torch.Generator().manual_seed(100 * e + r)
+        n = 60000 if big else 3000
+        k = torch.randint(0, 40000 if big else 700, (n,), generator=g) * 613 + 1
+        return k, torch.ones(n, dtype=torch.int64)
+
+    def body(r):
+        out = []
+        for e, (kind, who) in enumerate(plan):
+            k, v = rows(r.rank, e, kind == "landing")
+            vote = (0, 11)
+            kw = {}
+            if kind == "fp" and r.rank == who:
+                vote = (0, 12)
+            if kind == "producer" and r.rank == who:
+                vote = (1, 11)
+            if kind == "dest" and r.rank == who:
+                kw["out_cap"] = 8
+            rep, got = r.exchange(k, v, nparts, vote=vote, dest_cap=65536 if kind == "landing" else 8192, **kw)
+            out.append((rep.error, {p: dict(zip(a.tolist(), b.tolist())) for p, (a, b) in got.items()}
+                        if rep.error == 0 else None))
+        return out
+    # 1 MiB arena, 5 shards over 3 ranks: 2 local shards -> 5461 rows per region: the "landing" epochs overflow
+    res = run_ranks(world, body, arena_bytes=1 << 20, lib=lib)
+    expect = {"ok": 0, "fp": rx.FINGERPRINT, "producer": rx.PRODUCER_FAILED, "dest": rx.DEST_OVERFLOW,
+              "landing": rx.LANDING_OVERFLOW}
+    for e, (kind, who) in enumerate(plan):
+        verdicts = [res[r][e][0] for r in range(world)]
+        assert verdicts == [expect[kind]] * world, (e, kind, who, verdicts)
+        if kind == "ok":
+            ks, vs = zip(*[rows(r, e, False) for r in range(world)])
+            uk, cnt = torch.unique(torch.cat(ks), return_counts=True)
+            dest = hashing.hash_tensor(uk, 0) % nparts
+            want = {p: dict(zip(uk[dest == p].tolist(), cnt[dest == p].tolist())) for p in range(nparts)}
+            got = {}
+            for r in range(world):
+                got.update(res[r][e][1])
+            assert got == want, e
+    assert {k for k, _ in plan} >= {"ok", "fp", "producer", "dest", "landing"}
